@@ -1,0 +1,64 @@
+/* oracle/imd_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C, single thread, order-faithful) of the reference's
+ * force-and-integrate hot path.  It is the checker for the CUDA path; nothing in
+ * imd_b200/ may include, link or call it.  Parity of this oracle itself is pinned
+ * against the unmodified reference compiled into oracle/_ref (tests/test_oracle_vs_ref.py)
+ * and against the committed fixtures in tests/golden/ (generated from that reference by
+ * tools/make_golden.py) -- the reference tree ships no golden vectors of its own.
+ */
+#ifndef IMD_ORACLE_H
+#define IMD_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_sim orc_sim;
+
+/* which table: 0 = pair_pot (radial), 1 = embed_pot (not radial), 2 = rho_h_tab (radial) */
+enum { ORC_PAIR = 0, ORC_EMBED = 1, ORC_RHO = 2 };
+enum { ORC_NVE = 0, ORC_NVT = 1 };
+
+orc_sim *orc_create(int ntypes, const double box[9], const int pbc[3], double nbl_margin);
+void     orc_destroy(orc_sim *s);
+
+/* read_pot_table (src/imd_potential.c:161-282); returns 0 on success */
+int  orc_read_table(orc_sim *s, int which, const char *path);
+/* PAIR_INT2 / VAL_FUNC2 / DERIV_FUNC2 (src/potaccess.h:323-354, 465-495, 591-621) */
+void orc_pair_int(const orc_sim *s, int which, int col, double r2, double *pot, double *grad, int *is_short);
+int  orc_table_info(const orc_sim *s, int which, int col, double *begin, double *end, double *step, int *len);
+
+void orc_set_atoms(orc_sim *s, long n, const int *nummer, const int *sorte, const int *vsorte,
+                   const double *masse, const double *ort, const double *impuls);
+void orc_set_restrictions(orc_sim *s, int nvtypes, const double *restr3);
+void orc_set_integrator(orc_sim *s, int ensemble, double timestep, double temperature,
+                        double eta, double isq_tau_eta);
+void orc_set_box(orc_sim *s, const double box[9]);        /* make_box, src/imd_geom_3d.c:52-104 */
+
+void orc_calc_forces(orc_sim *s, int do_press_calc);      /* src/imd_forces_nbl.c:281-1999 */
+void orc_move_atoms(orc_sim *s, int do_press_calc);       /* src/imd_integrate.c:32-497, 891-1147 */
+void orc_check_nblist(orc_sim *s);                        /* src/imd_forces_nbl.c:2007-2037 */
+void orc_step(orc_sim *s, int nsteps);
+void orc_lin_deform(orc_sim *s, const double dx[3], const double dy[3], const double dz[3], double scale);
+
+long   orc_natoms(const orc_sim *s);
+int    orc_have_valid_nbl(const orc_sim *s);
+int    orc_nbl_count(const orc_sim *s);
+double orc_cellsz(const orc_sim *s);
+void   orc_get_celldims(const orc_sim *s, int out6[6]);
+/* tot_pot_energy, tot_kin_energy, virial, vir_xx,yy,zz,yz,zx,xy, volume, nactive, eta, temperature, timestep */
+void   orc_get_scalars(const orc_sim *s, double out[14]);
+void   orc_get_box(const orc_sim *s, double out9[9]);
+/* real atoms in current cell-traversal order; any pointer may be NULL */
+long   orc_get_atoms(const orc_sim *s, int *nummer, int *sorte, int *vsorte, double *masse, double *ort,
+                     double *impuls, double *kraft, double *poteng, double *rho, double *dF,
+                     double *presstens, double *nblpos);
+/* half Verlet list as (NUMMER_i, NUMMER_j, shift of j in box units); returns the pair count */
+long   orc_get_nbl_pairs(const orc_sim *s, int *pi, int *pj, signed char *shift, long cap);
+void   orc_tot_presstens(const orc_sim *s, double out6[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
