@@ -1,0 +1,32 @@
+# Builds the product: imd_b200/libimd_b200.so (hand-written sm_100a kernels + C ABI + C host helpers).
+# The oracle/ directory has its own Makefile (test infrastructure).
+NVCC     ?= nvcc
+CC       ?= gcc
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+CFLAGS   := -O2 -fPIC -Wall -std=c99 -D_POSIX_C_SOURCE=200809L
+CU       := $(wildcard imd_b200/csrc/*.cu)
+HC       := $(wildcard imd_b200/host/*.c)
+OBJ      := $(CU:imd_b200/csrc/%.cu=build/%.o) $(HC:imd_b200/host/%.c=build/host_%.o)
+LIB      := imd_b200/libimd_b200.so
+
+all: $(LIB)
+
+build/%.o: imd_b200/csrc/%.cu imd_b200/csrc/internal.cuh include/imd_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+build/host_%.o: imd_b200/host/%.c include/imd_b200.h
+	@mkdir -p build
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all oracle clean

@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s of the force-and-integrate hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE configs[1], "EAM Cu fcc 4M atoms, NVE with Verlet nbl + skin,
+single B200": a 100x100x100 fcc lattice (a0 = 3.615 A), synthetic Cu-like EAM tables in IMD format 2
+(2001 rows in r^2, 4001 rows in rho), T0 = 0.05, dt = 1 fs, nbl_margin 0.4.  One "step" is one MD step
+of all atoms: calc_forces + move_atoms + check_nblist, list rebuilds included when they fall due.
+N > 1: one process per GPU (torchrun), weak scaling, 4M atoms per GPU.
+
+Printed JSON (one line, rank 0):
+  value      whole-job atom-steps/s, state resident in HBM, timed with CUDA events on the launching
+             stream, max over ranks
+  e2e        the same metric through the C ABI with HOST buffers: upload of the atom state from pinned
+             host memory + K steps (energies read back every step) + download of positions, momenta and
+             forces, all inside the timed region
+  roofline   dominant kernel (pass 1: pair + density + embedding) against the measured HBM peak
+  cpu_baseline  the reference's own serial Verlet-list build (oracle/_ref) on a bounded sample
+--impl reference: the reference's own CPU implementation on all host threads (its OpenMP build).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = 648.0          # algorithmic bytes per atom-step, SURVEY.md section 8d (336 + 8*N_half, N_half = 39)
+B_PASS1 = 4 * 39 + 68  # of which pass 1 (list 4*N_half + R x,type 28 | W f 24, rho 8, e 8), section 8d
+B_PASS2 = 4 * 39 + 84
+METRIC = "atom-steps/s, EAM Cu fcc NVE at 1/2/4/8 B200 (% HBM roofline)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(tmp, ncell, seed):
+    from imd_b200 import synth
+    tabs = synth.make_eam_tables(tmp, "cu")
+    ort, box = synth.fcc_lattice(ncell, synth.CU_A0)
+    n = len(ort)
+    masse = np.full(n, synth.CU_MASS)
+    p = synth.maxwell_momenta(n, masse, 0.05, seed)
+    return tabs, box, np.arange(n, dtype=np.int32), np.zeros(n, np.int32), masse, ort, p
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_baseline_serial(tmp, budget_s=20.0):
+    """The reference's serial Verlet-list EAM build (oracle/_ref/libimdref_eam_fast.so, -O3, one core)
+    on a bounded sample of the same workload: 32^3 fcc cells = 131 072 atoms."""
+    code = r"""
+import sys, time, json
+sys.path.insert(0, %r)
+from oracle import ref_driver as rd
+from imd_b200 import synth
+p = synth.cu_param(%r, ncell=(32, 32, 32), name='cpu', starttemp=0.05)
+sim = rd.RefIMD('eam_fast', p)
+sim.step(3)
+n = sim.natoms; t0 = time.perf_counter(); k = 0
+while time.perf_counter() - t0 < %f:
+    sim.step(5); k += 5
+dt = time.perf_counter() - t0
+print(json.dumps(dict(value=n * k / dt, steps=k, natoms=n, seconds=dt)))
+""" % (ROOT, tmp, budget_s)
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=tmp, timeout=budget_s * 6 + 120)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": d["value"], "unit": "atom-steps/s", "cores": 1, "kind": "reference",
+                "sample": f"IMD serial imd_nve_eam_nbl build (-O3 -march=x86-64-v3), {d['natoms']} atoms (32^3 fcc cells) "
+                          f"x {d['steps']} steps, {d['seconds']:.1f} s, same tables/T0/dt"}
+    except Exception as e:  # the reference library is a prebuilt artefact; report rather than hide
+        return {"value": None, "unit": "atom-steps/s", "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+
+
+def reference_arm(args):
+    """--impl reference: IMD's own OpenMP CPU build (cell-pair algorithm, src/imd_main_risc_3d.c +
+    src/imd_forces_eam2.c) on all host threads; each 'step' is one MD step of a bounded sample."""
+    from imd_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    exe = os.path.join(ROOT, "oracle", "_ref", "imd_ref_omp_eam")
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    tmp = tempfile.mkdtemp(prefix="imdref_")
+    tabs = synth.make_eam_tables(tmp, "cu")
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    nc = 24
+
+    def run(nsteps):
+        p = synth.cu_param(tmp, ncell=(nc, nc, nc), name=f"omp{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs)
+        r = subprocess.run([exe, "-p", p], capture_output=True, text=True, cwd=tmp, env=env, timeout=3000)
+        m = re.search(r"([0-9.eE+-]+) seconds excluding setup time", r.stdout)
+        if not m:
+            raise RuntimeError("reference run failed:\n" + r.stdout[-1500:] + r.stderr[-1500:])
+        return float(m.group(1))
+
+    # size the bounded sample from a 4-step probe so that the two runs below take about 100 s in total
+    rate = 4 * nc ** 3 * 4 / max(run(4), 1e-6)
+    total_steps = 2 * args.warmup + args.steps
+    nc = int(min(100, max(16, round((rate * 100.0 / total_steps / 4) ** (1.0 / 3.0)))))
+    natoms = 4 * nc ** 3
+    t_w = run(args.warmup) if args.warmup > 0 else 0.0
+    t_all = run(args.warmup + args.steps)
+    dt = max(t_all - t_w, 1e-9)
+    v = natoms * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "atom-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "EAM Cu fcc NVE, Verlet-skin parameters, synthetic Cu tables (IMD format 2)",
+                       "sample_atoms": natoms, "parallelism": f"omp{cores}"},
+            "cpu_baseline": {"value": v, "unit": "atom-steps/s", "cores": cores, "kind": "reference",
+                             "sample": f"IMD OpenMP build imd_omp_nve_eam (cell-pair algorithm), {natoms} atoms x "
+                                       f"{args.steps} steps after {args.warmup} warm-up steps, main-loop wall time"},
+            "e2e": {"value": v, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from imd_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- imd_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nc = args.ncell
+    tmp = tempfile.mkdtemp(prefix="imdb200_")
+    tabs, box, num, typ, masse, ort, p = make_workload(tmp, (nc, nc, nc), 1234 + rank)
+    n = len(num)
+    kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"],
+              rho=tabs["atomic_e-density_file"], ensemble="nve", timestep=0.001, device=local, nbl_size=1.2)
+    sim = api.IMDB200(1, box, **kw)
+    stream = torch.cuda.current_stream()
+    sim.set_stream(stream.cuda_stream)
+    sim.set_atoms(num, typ, masse, ort, p)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    sim.run(args.warmup)
+    sim.timers(reset=True)
+    l0 = api.kernel_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.run(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = api.kernel_launches() - l0
+    tm = sim.timers()
+    sc = sim.scalars()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------------
+    hp = [torch.from_numpy(x).pin_memory().numpy() for x in (num, typ, masse, ort, p)]
+    out = dict(ort=np.zeros((n, 3)), impuls=np.zeros((n, 3)), kraft=np.zeros((n, 3)), nummer=np.zeros(n, np.int32))
+    ke = min(args.steps, max(20, args.steps // 4))
+    barrier()
+    t0 = time.perf_counter()
+    sim.set_atoms(*hp)                                     # H2D of the whole atom state
+    sim.run(ke)                                            # energies come back to the host every step
+    sim.L.imdb200_get_atoms(sim.h, out["nummer"].ctypes.data, None, None, None, out["ort"].ctypes.data,
+                            out["impuls"].ctypes.data, out["kraft"].ctypes.data, *([None] * 5))
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_v = world * n * ke / float(te.item())
+    h2d = n * (4 + 4 + 8 + 24 + 24) / ke + 0.0
+    d2h = (n * (4 + 24 + 24 + 24)) / ke + 16 * 8 + 8 * 4
+
+    if rank == 0:
+        peak, how = peaks()
+        t_p1 = tm["pass1_ms"] / max(tm["steps"], 1) * 1e-3
+        ach = B_PASS1 * n / t_p1 / 1e9 if t_p1 > 0 else 0.0
+        step_ach = B_ALG * (n * args.steps / (ms * 1e-3)) / 1e9
+        cpu = cpu_baseline_serial(tmp) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"EAM Cu fcc {n} atoms/GPU ({nc}^3 cells), NVE, Verlet nbl + skin 0.4, "
+                                   "synthetic Cu tables 2001/4001 rows, T0=0.05, dt=1fs",
+                       "global_atoms": world * n, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "cache": "inputs (>= 128 MB positions + 1.3 GB list per step) exceed the 126 MB L2",
+                       "rebuilds_in_window": int(tm["rebuilds"]), "nbl_len_per_atom": sc["nbl_len"] / n},
+            "clocks": clocks,
+            "e2e": {"value": e2e_v, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": ke, "note": "imdb200_set_atoms (pinned host arrays) + run + imdb200_get_atoms, wall clock"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_pass1 (pair + rho + embedding)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
+                         "algorithmic_bytes_per_atom": B_PASS1,
+                         "whole_step": {"achieved": step_ach, "frac": step_ach / peak, "bytes_per_atom_step": B_ALG}},
+            "phase_ms_per_step": {k: tm[k] / max(tm["steps"], 1) for k in
+                                  ("rebuild_ms", "pass1_ms", "pass2_ms", "integrate_ms", "ghost_ms")},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ncell", type=int, default=100, help="fcc unit cells per edge per GPU (100 -> 4M atoms)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,437 @@
+// api.cu -- the C ABI of include/imd_b200.h: handle life cycle, host<->device transfers and the
+// step loop of main_loop (src/imd_main_3d.c:155-870) kept resident on the device.
+#include "internal.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+
+int integrate_check_nblist(imdb200_sim *s);
+int integrate_lin_deform(imdb200_sim *s, const double dx[3], const double dy[3], const double dz[3], double scale);
+int integrate_deform_sample(imdb200_sim *s, int nvt, double size, const double *shift, const int *shear_def,
+                            const double *shear, const double *base);
+
+long long g_kernel_launches = 0;
+static thread_local char g_err[1024] = "";
+static void (*g_handler)(const char *) = nullptr;
+
+int imdb_fail(int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  if (g_handler) g_handler(g_err);
+  return code;
+}
+
+extern "C" {
+
+const char *imdb200_last_error(void) { return g_err; }
+void imdb200_set_error_handler(void (*h)(const char *)) { g_handler = h; }
+long long imdb200_kernel_launches(void) { return g_kernel_launches; }
+
+void imdb200_default_config(imdb200_config *c)
+{
+  memset(c, 0, sizeof(*c));
+  c->ntypes = 1; c->total_types = 1;
+  c->pbc_dirs[0] = c->pbc_dirs[1] = c->pbc_dirs[2] = 1;
+  c->cpu_dim[0] = c->cpu_dim[1] = c->cpu_dim[2] = 1;
+  c->nbl_margin = 0.4;   /* src/globals.h:419 */
+  c->nbl_size = 1.1;     /* src/globals.h:420 */
+  c->ensemble = IMDB200_ENS_NVE;
+  c->device = -1;
+  c->lanes_per_atom = 0;
+}
+
+int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
+{
+  if (!cfg || !out) return imdb_fail(IMDB200_ERR_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return imdb_fail(IMDB200_ERR_CUDA, "no CUDA device available (%s); imd_b200 has no CPU path", cudaGetErrorString(e));
+  if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return imdb_fail(IMDB200_ERR_CUDA, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev, prop.name, prop.major, prop.minor);
+  if (cfg->ntypes < 1 || cfg->ntypes * cfg->ntypes > IMDB_MAXCOL) return imdb_fail(IMDB200_ERR_ARG, "ntypes must be 1..4");
+  imdb200_sim *s = (imdb200_sim *) calloc(1, sizeof(imdb200_sim));
+  s->cfg = *cfg;
+  s->cfg.device = dev;
+  if (s->cfg.total_types < s->cfg.ntypes) s->cfg.total_types = s->cfg.ntypes;
+  if (s->cfg.nbl_size < 1.0) s->cfg.nbl_size = 1.1;
+  for (int d = 0; d < 3; d++) {
+    s->geom.box[0][d] = cfg->box_x[d]; s->geom.box[1][d] = cfg->box_y[d]; s->geom.box[2][d] = cfg->box_z[d];
+    s->geom.pbc[d] = cfg->pbc_dirs[d];
+    if (cfg->cpu_dim[d] < 1) { free(s); return imdb_fail(IMDB200_ERR_ARG, "cpu_dim must be >= 1"); }
+  }
+  s->nranks = cfg->cpu_dim[0] * cfg->cpu_dim[1] * cfg->cpu_dim[2];
+  s->rank = (cfg->my_coord[0] * cfg->cpu_dim[1] + cfg->my_coord[1]) * cfg->cpu_dim[2] + cfg->my_coord[2];
+  s->eta = cfg->eta;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  s->own_stream = 1;
+  CUDA_TRY(cudaMalloc(&s->d_scal, SC_COUNT * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->d_scal, 0, SC_COUNT * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &s->eta, sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMallocHost(&s->h_scal, SC_COUNT * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&s->d_flags, FL_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMemset(s->d_flags, 0, FL_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMallocHost(&s->h_flags, FL_COUNT * sizeof(int)));
+  for (int i = 0; i < 16; i++) CUDA_TRY(cudaEventCreate(&s->ev[i]));
+  *out = s;
+  return 0;
+}
+
+void imdb200_destroy(imdb200_sim *s)
+{
+  if (!s) return;
+  cudaStreamSynchronize(s->stream);
+  tables_free(s);
+  void *ptrs[] = {s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF, s->nblpos,
+                  s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start, s->cell_fill,
+                  s->cell_code, s->gcells, s->gcount, s->gstart, s->gsrc, s->scan_tmp, s->nbl, s->nnb, s->restr,
+                  s->d_scal, s->d_partial, s->d_flags};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (s->h_scal) cudaFreeHost(s->h_scal);
+  if (s->h_flags) cudaFreeHost(s->h_flags);
+  for (int i = 0; i < 16; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  if (s->own_stream) cudaStreamDestroy(s->stream);
+  free(s);
+}
+
+int imdb200_set_potentials(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_pot_table *embed,
+                           const imdb200_pot_table *rho)
+{
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  TRY(tables_upload(s, pair, embed, rho));
+  return geom_make_box(s);
+}
+
+int imdb200_set_stream(imdb200_sim *s, void *stream)
+{
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = 0; }
+  s->stream = (cudaStream_t) stream;
+  return 0;
+}
+
+int imdb200_set_restrictions(imdb200_sim *s, int total_types, const double *r)
+{
+  if (!s || total_types < 1 || !r) return imdb_fail(IMDB200_ERR_ARG, "bad restrictions");
+  if (s->restr) cudaFree(s->restr);
+  CUDA_TRY(cudaMalloc(&s->restr, 3 * total_types * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(s->restr, r, 3 * total_types * sizeof(double), cudaMemcpyHostToDevice));
+  int all1 = 1; double sum = 0;
+  for (int i = 0; i < 3 * total_types; i++) if (r[i] != 1.0) all1 = 0;
+  (void) sum;
+  s->n_restr = all1 ? 0 : total_types;
+  return 0;
+}
+
+static int ensure_partials(imdb200_sim *s)
+{
+  if (s->d_partial) cudaFree(s->d_partial);
+  s->d_partial = nullptr;
+  CUDA_TRY(cudaMalloc(&s->d_partial, ((size_t) s->cap_atoms * 32 / 128 + 64) * 8 * sizeof(double)));
+  return 0;
+}
+
+int imdb200_set_atoms(imdb200_sim *s, long n, const int *nummer, const int *sorte, const int *vsorte,
+                      const double *masse, const double *ort, const double *impuls)
+{
+  if (!s || n <= 0 || !nummer || !sorte || !masse || !ort) return imdb_fail(IMDB200_ERR_ARG, "bad atom arrays");
+  if (!s->have_tabs) return imdb_fail(IMDB200_ERR_ARG, "call imdb200_set_potentials before imdb200_set_atoms");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  if (s->nranks > 1) return imdb_fail(IMDB200_ERR_ARG, "multi-rank set_atoms goes through imdb200_comm_init first");
+  s->n_own = 0;
+  TRY(cells_ensure_capacity(s, n + n / 2 + 4096));
+  TRY(ensure_partials(s));
+  std::vector<double4> hp(n), hm(n);
+  for (long i = 0; i < n; i++) {
+    if (sorte[i] < 0 || sorte[i] >= s->cfg.ntypes) return imdb_fail(IMDB200_ERR_ARG, "atom %ld has type %d outside 0..ntypes-1", i, sorte[i]);
+    int vs = vsorte ? vsorte[i] : sorte[i];
+    hp[i].x = ort[3 * i]; hp[i].y = ort[3 * i + 1]; hp[i].z = ort[3 * i + 2];
+    long long w = ((long long) vs << 32) | (unsigned int) sorte[i];
+    memcpy(&hp[i].w, &w, 8);
+    hm[i].x = impuls ? impuls[3 * i] : 0.0; hm[i].y = impuls ? impuls[3 * i + 1] : 0.0; hm[i].z = impuls ? impuls[3 * i + 2] : 0.0;
+    hm[i].w = masse[i];
+  }
+  CUDA_TRY(cudaMemcpy(s->pos, hp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(s->mom, hm.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(s->nummer, nummer, n * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(s->frc, 0, n * sizeof(double4)));
+  s->n_own = n;
+  s->nactive = 3 * (long long) n;   /* src/imd_generate.c:450-451 */
+  s->n_ghost = 0;
+  s->have_valid_nbl = 0;
+  if (s->lanes == 0) {
+    int L = s->cfg.lanes_per_atom;
+    if (L == 0) { L = 1; while (L < 32 && n * L < 400000) L *= 2; }
+    if (L < 1 || L > 32 || (L & (L - 1))) return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
+    s->lanes = L;
+  }
+  return 0;
+}
+
+// ---- the step loop ------------------------------------------------------------------------------------
+static int fetch_scalars(imdb200_sim *s)
+{
+  CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (s->h_flags[FL_SHORT]) s->is_short = 1;
+  s->eta = s->h_scal[SC_ETA];
+  return 0;
+}
+
+static int ready(imdb200_sim *s)
+{
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
+  if (!s->have_tabs || s->n_own <= 0) return imdb_fail(IMDB200_ERR_ARG, "potentials and atoms must be set first");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  return 0;
+}
+
+static int calc_forces_async(imdb200_sim *s)
+{
+  if (!s->have_valid_nbl) TRY(cells_rebuild(s));       // fix_cells, send_cells, make_nblist (:304-317)
+  else TRY(cells_refresh_ghost_pos(s));                // send_cells(copy_cell,...) (:314)
+  TRY(forces_pass1(s));
+  if (s->tabs.have_eam) {
+    TRY(cells_refresh_ghost_dF(s));                    // send_cells(copy_dF,...) (:1115)
+    TRY(forces_pass2(s));
+  }
+  return 0;
+}
+
+int imdb200_calc_forces(imdb200_sim *s, int steps)
+{
+  (void) steps;
+  TRY(ready(s));
+  TRY(calc_forces_async(s));
+  TRY(fetch_scalars(s));
+  if (s->h_flags[FL_SHORT]) fprintf(stderr, "Short distance, pair, step %d!\n", steps); /* :982 */
+  return 0;
+}
+
+static void apply_check(imdb200_sim *s)
+{
+  const double lim = 0.5 * s->cfg.nbl_margin;
+  if (s->h_scal[SC_MAXD2] > lim * lim) s->have_valid_nbl = 0;   /* src/imd_forces_nbl.c:2036 */
+}
+
+int imdb200_move_atoms(imdb200_sim *s)
+{
+  TRY(ready(s));
+  if (s->nbl_count == 0) return imdb_fail(IMDB200_ERR_ARG, "move_atoms before the first calc_forces");
+  TRY(integrate_move(s));
+  return fetch_scalars(s);
+}
+
+int imdb200_check_nblist(imdb200_sim *s)
+{
+  TRY(ready(s));
+  if (s->nbl_count == 0) { s->have_valid_nbl = 0; return 0; }
+  TRY(integrate_check_nblist(s));
+  TRY(fetch_scalars(s));
+  apply_check(s);
+  return 0;
+}
+
+int imdb200_fix_cells(imdb200_sim *s) { TRY(ready(s)); s->have_valid_nbl = 0; return cells_rebuild(s); }
+int imdb200_make_nblist(imdb200_sim *s) { TRY(ready(s)); s->have_valid_nbl = 0; return cells_rebuild(s); }
+int imdb200_invalidate_nblist(imdb200_sim *s) { if (!s) return IMDB200_ERR_ARG; s->have_valid_nbl = 0; return 0; }
+int imdb200_set_press_calc(imdb200_sim *s, int on) { if (!s) return IMDB200_ERR_ARG; s->press_calc = on ? 1 : 0; return 0; }
+
+int imdb200_set_eta(imdb200_sim *s, double eta)
+{
+  if (!s) return IMDB200_ERR_ARG;
+  s->eta = eta;
+  CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &eta, sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+int imdb200_set_temperature(imdb200_sim *s, double t) { if (!s) return IMDB200_ERR_ARG; s->cfg.temperature = t; return 0; }
+
+int imdb200_run(imdb200_sim *s, int nsteps)
+{
+  TRY(ready(s));
+  for (int k = 0; k < nsteps; k++) {
+    const bool rebuild = !s->have_valid_nbl;
+    cudaEventRecord(s->ev[0], s->stream);
+    if (rebuild) TRY(cells_rebuild(s)); else TRY(cells_refresh_ghost_pos(s));
+    cudaEventRecord(s->ev[1], s->stream);
+    TRY(forces_pass1(s));
+    cudaEventRecord(s->ev[2], s->stream);
+    if (s->tabs.have_eam) { TRY(cells_refresh_ghost_dF(s)); TRY(forces_pass2(s)); }
+    cudaEventRecord(s->ev[3], s->stream);
+    TRY(integrate_move(s));
+    cudaEventRecord(s->ev[4], s->stream);
+    TRY(fetch_scalars(s));   // one sync per step: the host decides about the rebuild
+    apply_check(s);
+    float ms;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); s->t_ms[rebuild ? 0 : 4] += ms;
+    cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); s->t_ms[1] += ms;
+    cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]); s->t_ms[2] += ms;
+    cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]); s->t_ms[3] += ms;
+    s->t_ms[5] += rebuild ? 1.0 : 0.0;
+    s->t_ms[6] += 1.0;
+  }
+  if (s->is_short) fprintf(stderr, "Short distance!\n");
+  return 0;
+}
+
+int imdb200_get_timers(imdb200_sim *s, double out[8], int reset)
+{
+  if (!s) return IMDB200_ERR_ARG;
+  memcpy(out, s->t_ms, sizeof(s->t_ms));
+  if (reset) memset(s->t_ms, 0, sizeof(s->t_ms));
+  return 0;
+}
+
+int imdb200_lin_deform(imdb200_sim *s, const double dx[3], const double dy[3], const double dz[3], double scale)
+{
+  TRY(ready(s));
+  TRY(integrate_lin_deform(s, dx, dy, dz, scale));
+  // box vectors: box += scale * (D box)  (src/imd_deform.c:71-106)
+  Geom &g = s->geom;
+  for (int b = 0; b < 3; b++) {
+    double t0 = scale * (dx[0] * g.box[b][0] + dx[1] * g.box[b][1] + dx[2] * g.box[b][2]);
+    double t1 = scale * (dy[0] * g.box[b][0] + dy[1] * g.box[b][1] + dy[2] * g.box[b][2]);
+    double t2 = scale * (dz[0] * g.box[b][0] + dz[1] * g.box[b][1] + dz[2] * g.box[b][2]);
+    g.box[b][0] += t0; g.box[b][1] += t1; g.box[b][2] += t2;
+  }
+  return geom_make_box(s);
+}
+
+int imdb200_deform_sample(imdb200_sim *s, double size, const double *shift, const int *shear_def,
+                          const double *shear, const double *base)
+{
+  TRY(ready(s));
+  return integrate_deform_sample(s, s->cfg.total_types, size, shift, shear_def, shear, base);
+}
+
+// ---- results ----------------------------------------------------------------------------------------------
+int imdb200_get_scalars(imdb200_sim *s, imdb200_scalars *o)
+{
+  if (!s || !o) return imdb_fail(IMDB200_ERR_ARG, "null argument");
+  memset(o, 0, sizeof(*o));
+  if (s->d_scal && s->n_own > 0) TRY(fetch_scalars(s));
+  o->tot_pot_energy = s->h_scal[SC_EPOT];
+  o->tot_kin_energy = s->h_scal[SC_EKIN];
+  o->virial = s->h_scal[SC_VIRIAL];
+  o->volume = s->volume;
+  o->eta = s->eta;
+  o->max_displacement2 = s->h_scal[SC_MAXD2];
+  for (int d = 0; d < 6; d++) o->tot_presstens[d] = s->h_scal[SC_PXX + d];
+  o->natoms = s->n_own; o->nactive = s->nactive;
+  o->nbl_len = s->nbl_len;
+  o->have_valid_nbl = s->have_valid_nbl; o->nbl_count = s->nbl_count; o->is_short = s->is_short;
+  for (int d = 0; d < 3; d++) { o->global_cell_dim[d] = s->geom.gdim[d]; o->cell_dim[d] = s->geom.cdim[d]; }
+  o->cellsz = s->geom.cellsz;
+  return 0;
+}
+
+long imdb200_natoms_local(imdb200_sim *s) { return s ? s->n_own : 0; }
+
+long imdb200_get_atoms(imdb200_sim *s, int *nummer, int *sorte, int *vsorte, double *masse, double *ort,
+                       double *impuls, double *kraft, double *poteng, double *rho, double *dF,
+                       double *presstens, double *nblpos)
+{
+  if (!s || s->n_own <= 0) return 0;
+  cudaSetDevice(s->cfg.device);
+  cudaStreamSynchronize(s->stream);
+  const long n = s->n_own;
+  std::vector<double4> h(n);
+  if (ort || sorte || vsorte) {
+    cudaMemcpy(h.data(), s->pos, n * sizeof(double4), cudaMemcpyDeviceToHost);
+    for (long i = 0; i < n; i++) {
+      if (ort) { ort[3 * i] = h[i].x; ort[3 * i + 1] = h[i].y; ort[3 * i + 2] = h[i].z; }
+      long long w; memcpy(&w, &h[i].w, 8);
+      if (sorte) sorte[i] = (int) (w & 0xffffffffLL);
+      if (vsorte) vsorte[i] = (int) (w >> 32);
+    }
+  }
+  if (impuls || masse) {
+    cudaMemcpy(h.data(), s->mom, n * sizeof(double4), cudaMemcpyDeviceToHost);
+    for (long i = 0; i < n; i++) {
+      if (impuls) { impuls[3 * i] = h[i].x; impuls[3 * i + 1] = h[i].y; impuls[3 * i + 2] = h[i].z; }
+      if (masse) masse[i] = h[i].w;
+    }
+  }
+  if (kraft || poteng) {
+    cudaMemcpy(h.data(), s->frc, n * sizeof(double4), cudaMemcpyDeviceToHost);
+    for (long i = 0; i < n; i++) {
+      if (kraft) { kraft[3 * i] = h[i].x; kraft[3 * i + 1] = h[i].y; kraft[3 * i + 2] = h[i].z; }
+      if (poteng) poteng[i] = h[i].w;
+    }
+  }
+  if (nummer) cudaMemcpy(nummer, s->nummer, n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (rho) { if (s->tabs.have_eam) cudaMemcpy(rho, s->rho, n * sizeof(double), cudaMemcpyDeviceToHost); else memset(rho, 0, n * sizeof(double)); }
+  if (dF) { if (s->tabs.have_eam) cudaMemcpy(dF, s->dF, n * sizeof(double), cudaMemcpyDeviceToHost); else memset(dF, 0, n * sizeof(double)); }
+  if (presstens || nblpos) {
+    std::vector<double> t(6 * n);
+    if (presstens) {
+      for (int d = 0; d < 6; d++) cudaMemcpy(t.data() + d * n, s->presstens + d * s->cap_atoms, n * sizeof(double), cudaMemcpyDeviceToHost);
+      for (long i = 0; i < n; i++) for (int d = 0; d < 6; d++) presstens[6 * i + d] = t[d * n + i];
+    }
+    if (nblpos) {
+      for (int d = 0; d < 3; d++) cudaMemcpy(t.data() + d * n, s->nblpos + d * s->cap_atoms, n * sizeof(double), cudaMemcpyDeviceToHost);
+      for (long i = 0; i < n; i++) for (int d = 0; d < 3; d++) nblpos[3 * i + d] = t[d * n + i];
+    }
+  }
+  return n;
+}
+
+long imdb200_get_nblist(imdb200_sim *s, int *ni, int *nj, signed char *shift3, long cap)
+{
+  if (!s || !s->have_valid_nbl || !s->nbl) return -1;
+  cudaSetDevice(s->cfg.device);
+  cudaStreamSynchronize(s->stream);
+  if (cap <= 0 || !ni) return (long) s->nbl_len;
+  const long n = s->n_own, ntot = s->n_own + s->n_ghost;
+  const int L = s->lanes;
+  std::vector<int> nnb(n), num(n), gsrc(s->n_ghost > 0 ? s->n_ghost : 1), cid(ntot), code(s->geom.nall + 1);
+  std::vector<int> nbl((size_t) s->n_pad * s->max_nb);
+  cudaMemcpy(nnb.data(), s->nnb, n * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(num.data(), s->nummer, n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (s->n_ghost) cudaMemcpy(gsrc.data(), s->gsrc, s->n_ghost * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(cid.data(), s->cellid, ntot * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(code.data(), s->cell_code, s->geom.nall * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(nbl.data(), s->nbl, nbl.size() * sizeof(int), cudaMemcpyDeviceToHost);
+  const long rowstride = s->n_pad * L;
+  long cnt = 0;
+  for (long i = 0; i < n; i++)
+    for (int m = 0; m < nnb[i]; m++) {
+      int j = nbl[(size_t) (m / L) * rowstride + i * L + (m % L)];
+      int sx = 0, sy = 0, sz = 0, jn;
+      if (j >= n) { int c = code[cid[j]]; sx = c % 3 - 1; sy = (c / 3) % 3 - 1; sz = c / 9 - 1; jn = num[gsrc[j - n]]; }
+      else jn = num[j];
+      if (cnt < cap) {
+        ni[cnt] = num[i]; nj[cnt] = jn;
+        if (shift3) { shift3[3 * cnt] = (signed char) sx; shift3[3 * cnt + 1] = (signed char) sy; shift3[3 * cnt + 2] = (signed char) sz; }
+      }
+      cnt++;
+    }
+  return cnt;
+}
+
+int imdb200_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2, double *pot, double *grad)
+{
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  return tables_pair_int(s, which, col, n, r2, pot, grad);
+}
+
+int imdb200_comm_unique_id(void *id128) { (void) id128; return imdb_fail(IMDB200_ERR_COMM, "multi-GPU support not built yet"); }
+int imdb200_comm_init(imdb200_sim *s, const void *id128, int rank, int nranks)
+{ (void) s; (void) id128; (void) rank; (void) nranks; return imdb_fail(IMDB200_ERR_COMM, "multi-GPU support not built yet"); }
+
+} // extern "C"

@@ -1,0 +1,543 @@
+// cells.cu -- box/cell geometry, cell binning + sort (fix_cells), ghost images (send_cells) and the
+// Verlet neighbour-list build (make_nblist).
+//
+// Reference behaviour restated here (not its data structures):
+//   make_box / init_cells      src/imd_geom_3d.c:52-104, 113-248
+//   cell_coord                 src/imd_geom_3d.c:1054-1074
+//   do_boundaries              src/imd_main_3d.c:1972-2059
+//   fix_cells                  src/imd_fix_cells_3d.c:36-201
+//   send_cells + copy_cell     src/imd_comm_force_3d.c:222-396, 726-778
+//   make_nblist                src/imd_forces_nbl.c:136-273
+#include "internal.cuh"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+// =====================================================================================================
+// host: box and cell grid
+// =====================================================================================================
+static void cross(const double u[3], const double v[3], double w[3])
+{
+  w[0] = u[1] * v[2] - u[2] * v[1];
+  w[1] = u[2] * v[0] - u[0] * v[2];
+  w[2] = u[0] * v[1] - u[1] * v[0];
+}
+static double dot(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+static int plan_ghost_cells(imdb200_sim *s)
+{
+  const Geom &g = s->geom;
+  std::vector<GhostCell> gc;
+  for (int i = 0; i < g.cdim[0]; i++)
+    for (int j = 0; j < g.cdim[1]; j++)
+      for (int k = 0; k < g.cdim[2]; k++) {
+        int c[3] = {i, j, k}, src[3], sh[3], ghost = 0, ok = 1;
+        for (int d = 0; d < 3; d++) {
+          src[d] = c[d]; sh[d] = 0;
+          if (c[d] == 0) { ghost = 1; src[d] = g.cdim[d] - 2; sh[d] = -1; }
+          else if (c[d] == g.cdim[d] - 1) { ghost = 1; src[d] = 1; sh[d] = +1; }
+          // a buffer cell beyond a non-periodic face stays empty (nq = -1, src/imd_geom_3d.c:944-949)
+          if (sh[d] != 0 && !g.pbc[d]) ok = 0;
+        }
+        if (!ghost || !ok) continue;
+        GhostCell x;
+        x.dst = (i * g.cdim[1] + j) * g.cdim[2] + k;
+        x.src = (src[0] * g.cdim[1] + src[1]) * g.cdim[2] + src[2];
+        x.code = (sh[0] + 1) + 3 * (sh[1] + 1) + 9 * (sh[2] + 1);
+        x.peer = -1;
+        gc.push_back(x);
+      }
+  if (s->gcells) cudaFree(s->gcells);
+  if (s->gcount) cudaFree(s->gcount);
+  if (s->gstart) cudaFree(s->gstart);
+  s->gcells = nullptr; s->gcount = nullptr; s->gstart = nullptr;
+  s->n_gcells = (int) gc.size();
+  if (s->n_gcells) {
+    CUDA_TRY(cudaMalloc(&s->gcells, gc.size() * sizeof(GhostCell)));
+    CUDA_TRY(cudaMemcpy(s->gcells, gc.data(), gc.size() * sizeof(GhostCell), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&s->gcount, (gc.size() + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&s->gstart, (gc.size() + 1) * sizeof(int)));
+  }
+  return 0;
+}
+
+// init_cells (src/imd_geom_3d.c:113-248): cell grid from cellsz and the box heights.
+static int init_cells(imdb200_sim *s)
+{
+  Geom &g = s->geom;
+  if (!s->have_tabs) return imdb_fail(IMDB200_ERR_ARG, "set the potentials before the atoms (cellsz unknown)");
+  if (g.cellsz == 0.0) { // margin is added once (:122-126)
+    double r = sqrt(s->cellsz0) + s->cfg.nbl_margin;
+    g.cellsz = r * r;
+  }
+  for (int d = 0; d < 3; d++) {
+    double cell_scale = sqrt(1.0 * g.cellsz / s->height[d]);
+    g.gdim[d] = (int) (1.0 / cell_scale);
+    int cd = s->cfg.cpu_dim[d];
+    if (g.gdim[d] % cd) g.gdim[d] = (g.gdim[d] / cd) * cd;
+    if (g.gdim[d] < cd) return imdb_fail(IMDB200_ERR_CELLS, "global_cell_dim too small, need at least %d", cd);
+    s->min_height[d] = g.cellsz * (double) g.gdim[d] * g.gdim[d];
+    s->max_height[d] = g.cellsz * (double) (g.gdim[d] + cd) * (g.gdim[d] + cd);
+    g.cdim[d] = g.gdim[d] / cd + 2;
+    g.coff[d] = s->cfg.my_coord[d] * (g.cdim[d] - 2);
+  }
+  g.nall = g.cdim[0] * g.cdim[1] * g.cdim[2];
+  if (s->cell_count) { cudaFree(s->cell_count); cudaFree(s->cell_start); cudaFree(s->cell_fill); cudaFree(s->cell_code); cudaFree(s->scan_tmp); }
+  CUDA_TRY(cudaMalloc(&s->cell_code, (g.nall + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->cell_count, (g.nall + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->cell_start, (g.nall + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->cell_fill, (g.nall + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->scan_tmp, (g.nall / 1024 + 1024) * sizeof(int)));
+  TRY(plan_ghost_cells(s));
+  s->have_valid_nbl = 0;
+  return 0;
+}
+
+// make_box (src/imd_geom_3d.c:52-104)
+int geom_make_box(imdb200_sim *s)
+{
+  Geom &g = s->geom;
+  cross(g.box[1], g.box[2], g.tbox[0]);
+  cross(g.box[2], g.box[0], g.tbox[1]);
+  cross(g.box[0], g.box[1], g.tbox[2]);
+  s->volume = dot(g.box[0], g.tbox[0]);
+  if (s->volume == 0.0) return imdb_fail(IMDB200_ERR_ARG, "Box Edges are parallel.");
+  for (int i = 0; i < 3; i++) for (int d = 0; d < 3; d++) g.tbox[i][d] /= s->volume;
+  int redo = 0;
+  for (int d = 0; d < 3; d++) {
+    s->height[d] = 1.0 / dot(g.tbox[d], g.tbox[d]);
+    if (s->height[d] < s->min_height[d] || s->height[d] > s->max_height[d]) redo = 1;
+  }
+  if (redo) TRY(init_cells(s));
+  if (s->volume < 0) s->volume = -s->volume;
+  if (s->volume_init == 0.0) s->volume_init = s->volume;
+  else if (s->volume > 8 * s->volume_init) return imdb_fail(IMDB200_ERR_EXPLODE, "system seems to explode!");
+  return 0;
+}
+
+// =====================================================================================================
+// per-atom array capacity
+// =====================================================================================================
+template <typename T> static int regrow(T **p, long old_n, long new_cap)
+{
+  T *q = nullptr;
+  CUDA_TRY(cudaMalloc(&q, new_cap * sizeof(T)));
+  if (*p && old_n > 0) CUDA_TRY(cudaMemcpy(q, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice));
+  if (*p) cudaFree(*p);
+  *p = q;
+  return 0;
+}
+
+int cells_ensure_capacity(imdb200_sim *s, long need)
+{
+  if (need <= s->cap_atoms) return 0;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  long cap = need + need / 8 + 1024;
+  long n = s->n_own;
+  TRY(regrow(&s->pos, n, cap)); TRY(regrow(&s->pos_alt, 0, cap));
+  TRY(regrow(&s->mom, n, cap)); TRY(regrow(&s->mom_alt, 0, cap));
+  TRY(regrow(&s->frc, n, cap));
+  TRY(regrow(&s->nummer, n, cap)); TRY(regrow(&s->nummer_alt, 0, cap));
+  TRY(regrow(&s->rho, n, cap)); TRY(regrow(&s->dF, n, cap));
+  TRY(regrow(&s->cellid, n, cap)); TRY(regrow(&s->cellid_alt, 0, cap)); TRY(regrow(&s->perm, 0, cap));
+  TRY(regrow(&s->gsrc, 0, cap));
+  // SoA blocks whose stride is the capacity: contents are rebuilt before use
+  if (s->nblpos) cudaFree(s->nblpos);
+  if (s->presstens) cudaFree(s->presstens);
+  s->nblpos = nullptr; s->presstens = nullptr;
+  CUDA_TRY(cudaMalloc(&s->nblpos, 3 * cap * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&s->presstens, 6 * cap * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->presstens, 0, 6 * cap * sizeof(double)));
+  s->cap_atoms = cap;
+  s->have_valid_nbl = 0;
+  return 0;
+}
+
+// =====================================================================================================
+// exclusive scan (int32), three small kernels
+// =====================================================================================================
+__global__ void k_scan_blocks(const int *in, int *out, int n, int *sums)
+{
+  __shared__ int sm[1024];
+  const int base = blockIdx.x * 1024, t = threadIdx.x;
+  int v = (base + t < n) ? in[base + t] : 0;
+  sm[t] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int x = (t >= o) ? sm[t - o] : 0;
+    __syncthreads();
+    sm[t] += x;
+    __syncthreads();
+  }
+  if (base + t < n) out[base + t] = sm[t] - v;
+  if (t == 1023) sums[blockIdx.x] = sm[t];
+}
+__global__ void k_scan_sums(int *sums, int nb, int *total)
+{
+  __shared__ int sm[1024];
+  __shared__ int carry;
+  const int t = threadIdx.x;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int v = (base + t < nb) ? sums[base + t] : 0;
+    sm[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int x = (t >= o) ? sm[t - o] : 0;
+      __syncthreads();
+      sm[t] += x;
+      __syncthreads();
+    }
+    if (base + t < nb) sums[base + t] = carry + sm[t] - v;
+    __syncthreads();
+    if (t == 1023) carry += sm[t];
+    __syncthreads();
+  }
+  if (t == 0 && total) *total = carry;
+}
+__global__ void k_scan_add(int *out, int n, const int *sums)
+{
+  int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) out[i] += sums[blockIdx.x];
+}
+
+int scan_exclusive(imdb200_sim *s, const int *in, int *out, int n, int *total_dev)
+{
+  if (n <= 0) { if (total_dev) CUDA_TRY(cudaMemsetAsync(total_dev, 0, sizeof(int), s->stream)); return 0; }
+  int nb = cdiv(n, 1024);
+  k_scan_blocks<<<nb, 1024, 0, s->stream>>>(in, out, n, s->scan_tmp); LAUNCH_CHECK();
+  k_scan_sums<<<1, 1024, 0, s->stream>>>(s->scan_tmp, nb, total_dev); LAUNCH_CHECK();
+  k_scan_add<<<nb, 1024, 0, s->stream>>>(out, n, s->scan_tmp); LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// fix_cells: wrap, bin, sort
+// =====================================================================================================
+__device__ __forceinline__ double sprod_exact(double x, double y, double z, const double t[3])
+{ return __dadd_rn(__dadd_rn(__dmul_rn(x, t[0]), __dmul_rn(y, t[1])), __dmul_rn(z, t[2])); }
+
+// do_boundaries (src/imd_main_3d.c:1972-2059) + cell_coord (src/imd_geom_3d.c:1054-1074) +
+// local_cell_coord (src/imd_geom_mpi_3d.c:119-128), same operation order, no FMA.
+__global__ void k_wrap_bin(double4 *pos, long n, Geom g, int *cellid, int *cell_count, int *flags)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = pos[i];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (g.pbc[d] == 1) {
+      double f = -floor(sprod_exact(p.x, p.y, p.z, g.tbox[d]));
+      p.x = __dadd_rn(p.x, __dmul_rn(f, g.box[d][0]));
+      p.y = __dadd_rn(p.y, __dmul_rn(f, g.box[d][1]));
+      p.z = __dadd_rn(p.z, __dmul_rn(f, g.box[d][2]));
+    }
+  }
+  pos[i] = p;
+  int c[3];
+  bool lost = false;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    int v = __double2int_rz(__dmul_rn((double) g.gdim[d], sprod_exact(p.x, p.y, p.z, g.tbox[d])));
+    if (v >= g.gdim[d]) v = g.gdim[d] - 1; else if (v < 0) v = 0;
+    v = v - g.coff[d] + 1;
+    if (v < 1 || v > g.cdim[d] - 2) { lost = true; v = v < 1 ? 1 : g.cdim[d] - 2; }
+    c[d] = v;
+  }
+  if (lost) atomicAdd(&flags[FL_LOST], 1);
+  int ci = (c[0] * g.cdim[1] + c[1]) * g.cdim[2] + c[2];
+  cellid[i] = ci;
+  atomicAdd(&cell_count[ci], 1);
+}
+
+__global__ void k_scatter(const int *cellid, long n, const int *cell_start, int *cell_fill, int *perm)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cellid[i];
+  perm[cell_start[c] + atomicAdd(&cell_fill[c], 1)] = (int) i;
+}
+
+// Canonical order inside a cell: ascending atom number.  (The reference's order is history
+// dependent, src/imd_alloc.c:106-123; results do not depend on it -- SURVEY.md section 9 item 1 -- but a
+// canonical order makes every run bit-reproducible.)
+__global__ void k_sort_cells(const int *cell_start, const int *cell_count, int *perm, const int *nummer, int nall)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nall) return;
+  const int s0 = cell_start[c], n = cell_count[c];
+  for (int a = 1; a < n; a++) {
+    int pa = perm[s0 + a], ka = nummer[pa], b = a - 1;
+    while (b >= 0 && nummer[perm[s0 + b]] > ka) { perm[s0 + b + 1] = perm[s0 + b]; b--; }
+    perm[s0 + b + 1] = pa;
+  }
+}
+
+__global__ void k_gather(const int *perm, long n, const double4 *pos, const double4 *mom, const int *nummer,
+                         const int *cellid, double4 *pos2, double4 *mom2, int *nummer2, int *cellid2)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int p = perm[i];
+  pos2[i] = pos[p];
+  mom2[i] = mom[p];
+  nummer2[i] = nummer[p];
+  cellid2[i] = cellid[p];
+}
+
+// =====================================================================================================
+// ghost images (buffer cells)
+// =====================================================================================================
+__global__ void k_ghost_count(const GhostCell *gc, int ng, const int *cell_count, int *gcount)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ng) gcount[i] = cell_count[gc[i].src];
+}
+
+// one warp per ghost cell: record the source atom of every image and publish the cell's range
+__global__ void k_ghost_fill(const GhostCell *gc, int ng, const int *gstart, const int *gcount, long n_own,
+                             int *cell_start, int *cell_count, int *cell_code, int *gsrc)
+{
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= ng) return;
+  GhostCell x = gc[w];
+  int cnt = gcount[w], st = gstart[w], s0 = cell_start[x.src];
+  for (int t = lane; t < cnt; t += 32) gsrc[st + t] = s0 + t;
+  if (lane == 0) { cell_start[x.dst] = (int) n_own + st; cell_count[x.dst] = cnt; cell_code[x.dst] = x.code; }
+}
+
+// copy_cell (src/imd_comm_force_3d.c:726-778) for all three sweeps at once.  The reference adds
+// the box vectors stage by stage (up/down, then north/south, then east/west; :268-395), so the
+// image position is ((x + sz*box_z) + sy*box_y) + sx*box_x, each add rounded.
+__device__ __forceinline__ double4 image_pos(double4 p, int code, const Geom &g)
+{
+  int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
+  if (sz) { double f = (double) sz; p.x = __dadd_rn(p.x, f * g.box[2][0]); p.y = __dadd_rn(p.y, f * g.box[2][1]); p.z = __dadd_rn(p.z, f * g.box[2][2]); }
+  if (sy) { double f = (double) sy; p.x = __dadd_rn(p.x, f * g.box[1][0]); p.y = __dadd_rn(p.y, f * g.box[1][1]); p.z = __dadd_rn(p.z, f * g.box[1][2]); }
+  if (sx) { double f = (double) sx; p.x = __dadd_rn(p.x, f * g.box[0][0]); p.y = __dadd_rn(p.y, f * g.box[0][1]); p.z = __dadd_rn(p.z, f * g.box[0][2]); }
+  return p;
+}
+
+__global__ void k_ghost_pos(double4 *pos, long n_own, long n_ghost, const int *gsrc, const int *cellid_g,
+                            const int *cell_code, Geom g)
+{
+  long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (t >= n_ghost) return;
+  pos[n_own + t] = image_pos(pos[gsrc[t]], cell_code[cellid_g[t]], g);
+}
+
+__global__ void k_ghost_cellid(const GhostCell *gc, int ng, const int *gstart, const int *gcount, int *cellid_g)
+{
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= ng) return;
+  int cnt = gcount[w], st = gstart[w], dst = gc[w].dst;
+  for (int t = lane; t < cnt; t += 32) cellid_g[st + t] = dst;
+}
+
+__global__ void k_ghost_dF(double *dF, long n_own, long n_ghost, const int *gsrc)
+{
+  long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (t < n_ghost) dF[n_own + t] = dF[gsrc[t]];
+}
+
+int cells_refresh_ghost_pos(imdb200_sim *s)
+{
+  if (s->n_ghost == 0) return 0;
+  k_ghost_pos<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->pos, s->n_own, s->n_ghost, s->gsrc,
+                                                              s->cellid + s->n_own, s->cell_code, s->geom);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int cells_refresh_ghost_dF(imdb200_sim *s)
+{
+  if (s->n_ghost == 0) return 0;
+  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->n_own, s->n_ghost, s->gsrc);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// make_nblist
+// =====================================================================================================
+// One thread per owned atom scans the 27 cells around its own.  The list is FULL (both directions
+// of every pair) so that the force kernels never scatter; its symmetric closure is exactly the
+// reference's half list (src/imd_forces_nbl.c:218-269), because every pair is tested with the
+// reference's own operands and rounding:
+//   * the reference tests a pair once, from the atom whose cell comes first in the half stencil
+//     l=0..1, m=-l..1, n=(l==0?-m:-l)..1 (src/imd_geom_3d.c:895-899), as d = ort_j - ort_i where
+//     ort_j is the buffer-cell image (x_j + shift, added stage-wise) if the neighbour cell is a
+//     buffer cell;
+//   * for an "upper" neighbour cell we are that first atom: d = pos[j] - x_i with pos[j] the image;
+//   * for a "lower" neighbour cell the reference started from j and saw OUR image in the buffer
+//     cell on the opposite side: d = image(x_i, -shift) - x_j(unshifted).  When the lower cell is a
+//     real cell both are the same up to sign; when it is a buffer cell we rebuild exactly that.
+__global__ void __launch_bounds__(128)
+k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__restrict__ cellid,
+            const int *__restrict__ cell_start, const int *__restrict__ cell_count,
+            const int *__restrict__ cell_code, const int *__restrict__ gsrc,
+            int *__restrict__ nbl, int *__restrict__ nnb, int max_nb, long rowstride, int L,
+            int *flags, int count_only)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n_own) return;
+  const double4 xi = pos[i];
+  const int c1 = cellid[i];
+  const int cz = c1 % g.cdim[2], cy = (c1 / g.cdim[2]) % g.cdim[1], cx = c1 / (g.cdim[2] * g.cdim[1]);
+  int cnt = 0;
+  for (int l = -1; l <= 1; l++)
+    for (int m = -1; m <= 1; m++)
+      for (int n = -1; n <= 1; n++) {
+        const int c2 = ((cx + l) * g.cdim[1] + (cy + m)) * g.cdim[2] + (cz + n);
+        const int nj = cell_count[c2];
+        if (nj == 0) continue;
+        const int j0 = cell_start[c2];
+        const bool upper = (l > 0) || (l == 0 && (m > 0 || (m == 0 && n >= 0)));
+        const bool ghost = j0 >= n_own;
+        if (ghost && !upper) {
+          // our image as the reference's buffer cell on the far side holds it
+          const int code = cell_code[c2];               // shift of the images in c2
+          const int inv = 26 - code;                    // (-sx,-sy,-sz)
+          const double4 me = image_pos(xi, inv, g);
+          for (int t = 0; t < nj; t++) {
+            const int j = j0 + t;
+            const double4 xj = pos[gsrc[j - n_own]];
+            const double r2 = r2_exact(__dsub_rn(me.x, xj.x), __dsub_rn(me.y, xj.y), __dsub_rn(me.z, xj.z));
+            if (r2 < g.cellsz) {
+              if (!count_only && cnt < max_nb) nbl[(long) (cnt / L) * rowstride + i * L + (cnt % L)] = j;
+              cnt++;
+            }
+          }
+        } else {
+          for (int t = 0; t < nj; t++) {
+            const int j = j0 + t;
+            if (j == i) continue;
+            const double4 xj = pos[j];
+            const double r2 = r2_exact(__dsub_rn(xj.x, xi.x), __dsub_rn(xj.y, xi.y), __dsub_rn(xj.z, xi.z));
+            if (r2 < g.cellsz) {
+              if (!count_only && cnt < max_nb) nbl[(long) (cnt / L) * rowstride + i * L + (cnt % L)] = j;
+              cnt++;
+            }
+          }
+        }
+      }
+  if (!count_only) nnb[i] = cnt < max_nb ? cnt : max_nb;
+  atomicMax(&flags[FL_MAXNB], cnt);
+  if (!count_only && cnt > max_nb) atomicExch(&flags[FL_NBL_OVERFLOW], 1);
+}
+
+__global__ void k_save_nblpos(const double4 *pos, long n, long stride, double *nblpos)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = pos[i];
+  nblpos[i] = p.x; nblpos[stride + i] = p.y; nblpos[2 * stride + i] = p.z;
+}
+
+__global__ void k_sum_int(const int *v, long n, unsigned long long *out)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  unsigned long long x = (i < n) ? (unsigned long long) v[i] : 0ull;
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0 && x) atomicAdd(out, x);
+}
+
+static int alloc_nbl(imdb200_sim *s, int max_nb)
+{
+  const int L = s->lanes;
+  max_nb = ((max_nb + L - 1) / L) * L;
+  long n_pad = ((s->cap_atoms + 31) / 32) * 32;
+  if (s->nbl && max_nb <= s->max_nb && n_pad == s->n_pad) return 0;
+  if (s->nbl) cudaFree(s->nbl);
+  if (s->nnb) cudaFree(s->nnb);
+  s->nbl = nullptr; s->nnb = nullptr;
+  CUDA_TRY(cudaMalloc(&s->nbl, (size_t) n_pad * max_nb * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->nnb, (size_t) n_pad * sizeof(int)));
+  s->max_nb = max_nb;
+  s->n_pad = n_pad;
+  return 0;
+}
+
+static int read_flags(imdb200_sim *s)
+{
+  CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// fix_cells + send_cells + make_nblist, i.e. the `0 == have_valid_nbl` branch of calc_forces
+// (src/imd_forces_nbl.c:304-317)
+int cells_rebuild(imdb200_sim *s)
+{
+  const long n = s->n_own;
+  const Geom &g = s->geom;
+  cudaStream_t st = s->stream;
+  if (n <= 0) return imdb_fail(IMDB200_ERR_ARG, "no atoms");
+  // ---- fix_cells: wrap into the box, bin, sort into cell order ------------------------------------
+  CUDA_TRY(cudaMemsetAsync(s->cell_count, 0, (g.nall + 1) * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(s->cell_fill, 0, (g.nall + 1) * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, FL_COUNT * sizeof(int), st));
+  const int nb = cdiv(n, 256);
+  k_wrap_bin<<<nb, 256, 0, st>>>(s->pos, n, g, s->cellid, s->cell_count, s->d_flags); LAUNCH_CHECK();
+  TRY(scan_exclusive(s, s->cell_count, s->cell_start, g.nall, nullptr));
+  k_scatter<<<nb, 256, 0, st>>>(s->cellid, n, s->cell_start, s->cell_fill, s->perm); LAUNCH_CHECK();
+  k_sort_cells<<<cdiv(g.nall, 128), 128, 0, st>>>(s->cell_start, s->cell_count, s->perm, s->nummer, g.nall); LAUNCH_CHECK();
+  k_gather<<<nb, 256, 0, st>>>(s->perm, n, s->pos, s->mom, s->nummer, s->cellid, s->pos_alt, s->mom_alt,
+                               s->nummer_alt, s->cellid_alt);
+  LAUNCH_CHECK();
+  { double4 *t = s->pos; s->pos = s->pos_alt; s->pos_alt = t; }
+  { double4 *t = s->mom; s->mom = s->mom_alt; s->mom_alt = t; }
+  { int *t = s->nummer; s->nummer = s->nummer_alt; s->nummer_alt = t; }
+  { int *t = s->cellid; s->cellid = s->cellid_alt; s->cellid_alt = t; }
+  // ---- buffer cells: images of the boundary cells ---------------------------------------------------
+  CUDA_TRY(cudaMemsetAsync(s->cell_code, 0, (g.nall + 1) * sizeof(int), st));
+  s->n_ghost = 0;
+  if (s->n_gcells) {
+    k_ghost_count<<<cdiv(s->n_gcells, 256), 256, 0, st>>>(s->gcells, s->n_gcells, s->cell_count, s->gcount); LAUNCH_CHECK();
+    TRY(scan_exclusive(s, s->gcount, s->gstart, s->n_gcells, &s->d_flags[FL_NGHOST]));
+    TRY(read_flags(s));
+    if (s->h_flags[FL_LOST]) return imdb_fail(IMDB200_ERR_CELLS, "%d atoms left the local domain (atom migration between ranks failed)", s->h_flags[FL_LOST]);
+    s->n_ghost = s->h_flags[FL_NGHOST];
+    TRY(cells_ensure_capacity(s, n + s->n_ghost));
+    const int nbw = cdiv((long) s->n_gcells * 32, 256);
+    k_ghost_fill<<<nbw, 256, 0, st>>>(s->gcells, s->n_gcells, s->gstart, s->gcount, n, s->cell_start, s->cell_count,
+                                      s->cell_code, s->gsrc); LAUNCH_CHECK();
+    k_ghost_cellid<<<nbw, 256, 0, st>>>(s->gcells, s->n_gcells, s->gstart, s->gcount, s->cellid + n); LAUNCH_CHECK();
+    TRY(cells_refresh_ghost_pos(s));
+  }
+  // ---- make_nblist -------------------------------------------------------------------------------------
+  const int L = s->lanes;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    if (s->max_nb == 0 || attempt > 0) {
+      // size the table from an exact count (estimate_nblist_size, src/imd_forces_nbl.c:74-128)
+      CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
+      k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
+                                                s->gsrc, nullptr, nullptr, 0, 0, L, s->d_flags, 1); LAUNCH_CHECK();
+      TRY(read_flags(s));
+      int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 2;
+      TRY(alloc_nbl(s, want > 8 ? want : 8));
+    } else TRY(alloc_nbl(s, s->max_nb));
+    CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_NBL_OVERFLOW], 0, sizeof(int), st));
+    k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
+                                              s->gsrc, s->nbl, s->nnb, s->max_nb, s->n_pad * L, L, s->d_flags, 0); LAUNCH_CHECK();
+    TRY(read_flags(s));
+    if (!s->h_flags[FL_NBL_OVERFLOW]) break;
+    if (attempt == 2) return imdb_fail(IMDB200_ERR_NBL, "neighbor table full - increase nbl_size");
+  }
+  // total list length (last_nbl_len, src/imd_forces_nbl.c:270)
+  unsigned long long *d_len = (unsigned long long *) (s->d_scal + SC_COUNT - 1);
+  CUDA_TRY(cudaMemsetAsync(d_len, 0, sizeof(unsigned long long), st));
+  k_sum_int<<<cdiv(n, 256), 256, 0, st>>>(s->nnb, n, d_len); LAUNCH_CHECK();
+  // NBL_POS <- ORT (src/imd_forces_nbl.c:142-154)
+  k_save_nblpos<<<nb, 256, 0, st>>>(s->pos, n, s->cap_atoms, s->nblpos); LAUNCH_CHECK();
+  unsigned long long len = 0;
+  CUDA_TRY(cudaMemcpyAsync(&len, d_len, sizeof(len), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  s->nbl_len = (long long) len;
+  s->have_valid_nbl = 1;
+  s->nbl_count++;
+  return 0;
+}

@@ -1,0 +1,223 @@
+// integrate.cu -- leap-frog NVE / Nose-Hoover NVT step fused with the skin check, and deformation.
+//   move_atoms_nve   src/imd_integrate.c:32-497   (hot lines :192-217, 328-358, 410-433)
+//   move_atoms_nvt   src/imd_integrate.c:891-1147 (hot lines :907-908, 951, 1020-1027, 1103, 1140-1141)
+//   check_nblist     src/imd_forces_nbl.c:2007-2037
+//   lin_deform / deform_sample   src/imd_deform.c:35-119, 232-269
+#include "internal.cuh"
+
+struct IArgs {
+  double4 *pos, *mom, *frc;
+  const double *nblpos; long nstride;
+  const double *restr;
+  double *presstens; long pstride;
+  long n;
+  double dt;
+  const double *scal;
+  double *partial;
+  unsigned long long *maxd2;
+};
+
+#define IBLOCK 256
+
+__device__ __forceinline__ double block_max(double v)
+{
+  __shared__ double smx[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) smx[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? smx[threadIdx.x] : 0.0;
+  if (w == 0) for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <bool NVT, bool STRESS, bool RESTR>
+__global__ void __launch_bounds__(IBLOCK) k_move_atoms(IArgs a)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  double red[2] = {0.0, 0.0};
+  double d2 = 0.0;
+  if (i < a.n) {
+    double4 x = a.pos[i], p = a.mom[i], f = a.frc[i];
+    const double m = p.w, dt = a.dt;
+    double rx = 1.0, ry = 1.0, rz = 1.0;
+    if (RESTR) {
+      const double *r = a.restr + 3 * vsorte_of(x.w);
+      rx = r[0]; ry = r[1]; rz = r[2];
+      f.x *= rx; f.y *= ry; f.z *= rz;                                // :192-197
+      a.frc[i] = f;
+    }
+    if (!NVT) {
+      const double k1 = p.x * p.x + p.y * p.y + p.z * p.z;
+      p.x += dt * f.x; p.y += dt * f.y; p.z += dt * f.z;              // :213-217
+      const double k2 = p.x * p.x + p.y * p.y + p.z * p.z;
+      red[0] = (k1 + k2) / (4 * m);                                   // :329-335
+    } else {
+      const double eta = a.scal[SC_ETA];
+      const double reibung = 1.0 - eta * dt / 2.0;                    // :907
+      const double eins_d_reib = 1.0 / (1.0 + eta * dt / 2.0);        // :908
+      red[0] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;               // E_kin_1 :951
+      p.x = (p.x * reibung + dt * f.x) * eins_d_reib * rx;            // :1020-1027
+      p.y = (p.y * reibung + dt * f.y) * eins_d_reib * ry;
+      p.z = (p.z * reibung + dt * f.z) * eins_d_reib * rz;
+      red[1] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;               // E_kin_2
+    }
+    const double tmp = dt / m;                                         // :353-358
+    x.x += tmp * p.x; x.y += tmp * p.y; x.z += tmp * p.z;
+    a.mom[i] = p;
+    a.pos[i] = x;
+    if (STRESS) {                                                      // :410-433
+      double *s = a.presstens + i;
+      s[0] += p.x * p.x / m; s[a.pstride] += p.y * p.y / m; s[2 * a.pstride] += p.z * p.z / m;
+      s[3 * a.pstride] += p.y * p.z / m; s[4 * a.pstride] += p.z * p.x / m; s[5 * a.pstride] += p.x * p.y / m;
+    }
+    // check_nblist: same operands and rounding as the reference (exact -> identical rebuild steps)
+    const double ex = x.x - a.nblpos[i], ey = x.y - a.nblpos[a.nstride + i], ez = x.z - a.nblpos[2 * a.nstride + i];
+    d2 = r2_exact(ex, ey, ez);
+  }
+  d2 = block_max(d2);
+  if (threadIdx.x == 0) atomicMax(a.maxd2, (unsigned long long) __double_as_longlong(d2));
+  block_sum_store<2>(red, a.partial);
+}
+
+__global__ void k_check_nblist(const double4 *pos, const double *nblpos, long nstride, long n, unsigned long long *maxd2)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (i < n) {
+    const double4 x = pos[i];
+    d2 = r2_exact(x.x - nblpos[i], x.y - nblpos[nstride + i], x.z - nblpos[2 * nstride + i]);
+  }
+  d2 = block_max(d2);
+  if (threadIdx.x == 0) atomicMax(maxd2, (unsigned long long) __double_as_longlong(d2));
+}
+
+// tot_kin_energy and the Nose-Hoover variable (src/imd_integrate.c:1103, 1140-1141)
+__global__ void k_nvt_finish(double *scal, double dt, double nactive, double temperature, double isq_tau_eta)
+{
+  const double e1 = scal[SC_EKIN1], e2 = scal[SC_EKIN2];
+  scal[SC_EKIN] = (e1 + e2) / 4.0;
+  const double ttt = nactive * temperature;
+  scal[SC_ETA] += dt * (e2 / ttt - 1.0) * isq_tau_eta;
+}
+
+// presstens totals (calc_tot_presstens, src/imd_main_3d.c:2069-2130)
+__global__ void k_sum_presstens(const double *presstens, long pstride, long n, double *partial)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  double v[6];
+#pragma unroll
+  for (int d = 0; d < 6; d++) v[d] = (i < n) ? presstens[d * pstride + i] : 0.0;
+  block_sum_store<6>(v, partial);
+}
+
+int integrate_move(imdb200_sim *s)
+{
+  IArgs a;
+  a.pos = s->pos; a.mom = s->mom; a.frc = s->frc;
+  a.nblpos = s->nblpos; a.nstride = s->cap_atoms;
+  a.restr = s->restr;
+  a.presstens = s->presstens; a.pstride = s->cap_atoms;
+  a.n = s->n_own; a.dt = s->cfg.timestep;
+  a.scal = s->d_scal; a.partial = s->d_partial;
+  a.maxd2 = (unsigned long long *) (s->d_scal + SC_MAXD2);
+  const int nb = cdiv(s->n_own, IBLOCK);
+  CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
+  const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT, st = s->press_calc != 0, re = s->n_restr > 0;
+#define GO(N, S, R) k_move_atoms<N, S, R><<<nb, IBLOCK, 0, s->stream>>>(a)
+  if (nvt) { if (st) { if (re) GO(true, true, true); else GO(true, true, false); }
+             else    { if (re) GO(true, false, true); else GO(true, false, false); } }
+  else     { if (st) { if (re) GO(false, true, true); else GO(false, true, false); }
+             else    { if (re) GO(false, false, true); else GO(false, false, false); } }
+#undef GO
+  LAUNCH_CHECK();
+  if (nvt) {
+    const int slots[2] = {SC_EKIN1, SC_EKIN2};
+    TRY(reduce_finish(s, nb, 2, slots, 0));
+    // every rank would first all-reduce E_kin_1/2 here (src/imd_integrate.c:1104-1130)
+    k_nvt_finish<<<1, 1, 0, s->stream>>>(s->d_scal, s->cfg.timestep, (double) s->nactive,
+                                         s->cfg.temperature, s->cfg.isq_tau_eta);
+    LAUNCH_CHECK();
+  } else {
+    const int slots[2] = {SC_EKIN, SC_EKIN2};
+    TRY(reduce_finish(s, nb, 2, slots, 0));
+  }
+  if (st) {
+    k_sum_presstens<<<nb, IBLOCK, 0, s->stream>>>(s->presstens, s->cap_atoms, s->n_own, s->d_partial); LAUNCH_CHECK();
+    const int slots[6] = {SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX, SC_PXY};
+    TRY(reduce_finish(s, nb, 6, slots, 0));
+  }
+  return 0;
+}
+
+int integrate_check_nblist(imdb200_sim *s)
+{
+  CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
+  k_check_nblist<<<cdiv(s->n_own, IBLOCK), IBLOCK, 0, s->stream>>>(s->pos, s->nblpos, s->cap_atoms, s->n_own,
+                                                                    (unsigned long long *) (s->d_scal + SC_MAXD2));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- deformation ----------------------------------------------------------------------------------------
+struct Mat3 { double m[3][3]; };
+__global__ void k_lin_deform(double4 *pos, long n, Mat3 D, double scale)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 x = pos[i];
+  // tmport = D x ; ort += scale * tmport  (src/imd_deform.c:59-67), reference operation order
+  const double t0 = __dadd_rn(__dadd_rn(__dmul_rn(D.m[0][0], x.x), __dmul_rn(D.m[0][1], x.y)), __dmul_rn(D.m[0][2], x.z));
+  const double t1 = __dadd_rn(__dadd_rn(__dmul_rn(D.m[1][0], x.x), __dmul_rn(D.m[1][1], x.y)), __dmul_rn(D.m[1][2], x.z));
+  const double t2 = __dadd_rn(__dadd_rn(__dmul_rn(D.m[2][0], x.x), __dmul_rn(D.m[2][1], x.y)), __dmul_rn(D.m[2][2], x.z));
+  x.x = __dadd_rn(x.x, __dmul_rn(scale, t0));
+  x.y = __dadd_rn(x.y, __dmul_rn(scale, t1));
+  x.z = __dadd_rn(x.z, __dmul_rn(scale, t2));
+  pos[i] = x;
+}
+
+int integrate_lin_deform(imdb200_sim *s, const double dx[3], const double dy[3], const double dz[3], double scale)
+{
+  Mat3 D;
+  for (int d = 0; d < 3; d++) { D.m[0][d] = dx[d]; D.m[1][d] = dy[d]; D.m[2][d] = dz[d]; }
+  k_lin_deform<<<cdiv(s->n_own, 256), 256, 0, s->stream>>>(s->pos, s->n_own, D, scale);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+struct DefArgs { const double *shift, *shear, *base; const int *shear_def; double size; };
+__global__ void k_deform_sample(double4 *pos, long n, DefArgs d)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 x = pos[i];
+  const int vs = vsorte_of(x.w);
+  double shear = 1.0;
+  if (d.shear_def[vs] == 1) {                                          // src/imd_deform.c:248-255
+    const double ox = x.x - d.base[3 * vs], oy = x.y - d.base[3 * vs + 1], oz = x.z - d.base[3 * vs + 2];
+    shear = __dadd_rn(__dadd_rn(__dmul_rn(d.shear[3 * vs], ox), __dmul_rn(d.shear[3 * vs + 1], oy)), __dmul_rn(d.shear[3 * vs + 2], oz));
+  }
+  const double f = __dmul_rn(shear, d.size);                           // :260-264
+  x.x = __dadd_rn(x.x, __dmul_rn(f, d.shift[3 * vs]));
+  x.y = __dadd_rn(x.y, __dmul_rn(f, d.shift[3 * vs + 1]));
+  x.z = __dadd_rn(x.z, __dmul_rn(f, d.shift[3 * vs + 2]));
+  pos[i] = x;
+}
+
+int integrate_deform_sample(imdb200_sim *s, int nvt, double size, const double *shift, const int *shear_def,
+                            const double *shear, const double *base)
+{
+  double *d = nullptr; int *di = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 9 * nvt * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&di, nvt * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(d, shift, 3 * nvt * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d + 3 * nvt, shear, 3 * nvt * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d + 6 * nvt, base, 3 * nvt * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(di, shear_def, nvt * sizeof(int), cudaMemcpyHostToDevice));
+  DefArgs a; a.shift = d; a.shear = d + 3 * nvt; a.base = d + 6 * nvt; a.shear_def = di; a.size = size;
+  k_deform_sample<<<cdiv(s->n_own, 256), 256, 0, s->stream>>>(s->pos, s->n_own, a);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  cudaFree(d); cudaFree(di);
+  return 0;
+}

@@ -1,0 +1,198 @@
+// internal.cuh -- shared declarations of the sm_100a engine behind include/imd_b200.h.
+//
+// Device data layout (all arrays live in HBM, one simulation handle per GPU):
+//   pos   double4[n_own + n_ghost]  x,y,z + (vsorte<<32 | sorte) bit-cast into .w
+//                                   owned atoms first, sorted by cell (x slowest, z fastest like
+//                                   PTR_3D_V, src/makros.h:438), inside a cell by atom number;
+//                                   ghost (buffer-cell) images after them, grouped by ghost cell
+//   mom   double4[n_own]            px,py,pz + mass in .w          (IMPULS, MASSE)
+//   frc   double4[n_own]            fx,fy,fz + per-atom Epot in .w (KRAFT, POTENG)
+//   rho   double[n_own]             host electron density          (EAM_RHO)
+//   dF    double[n_own + n_ghost]   2 F'(rho) of owners and images (EAM_DF)
+//   nblpos double[3][n_pad]         reference positions of the skin check (NBL_POS)
+//   nbl   int32[max_nb/L][n_pad*L]  FULL neighbour list, lane-interleaved rows so that a warp
+//                                   reads 128 contiguous bytes per row; nnb int32[n_own]
+// 32-byte atom records make every gather exactly one 32-byte sector.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/imd_b200.h"
+
+#define IMDB_MAXCOL 16 // ntypes <= 4
+#define IMDB_TWO52 4503599627370496.0
+
+// ---- potential tables in derived (polynomial-coefficient) form ---------------------------------
+// PAIR_INT2 (src/potaccess.h:323-354) evaluates on interval k, with chi in [0,1):
+//    val  = p0 + chi*dv + 0.5*chi*(chi-1)*d2v,   grad = 2*istep*(dv + (chi-0.5)*d2v)
+// with dv = p1-p0, d2v = p2-2*p1+p0.  We precompute per (k,col) on the host, in double:
+//    c0 = p0, c1 = dv - 0.5*d2v, c2 = 0.5*d2v, g1 = 2*istep*c1, g2 = 4*istep*c2
+// so that val = c0 + chi*(c1 + chi*c2) and grad = g1 + chi*g2: 3 DFMA instead of ~12 DP ops
+// and one contiguous fetch instead of three strided ones.  k and chi themselves are computed
+// with the reference's exact operation sequence (see tab_index()).
+enum { TAB_PAIR = 0, TAB_EMBED = 1, TAB_RHO = 2 };
+
+struct TabMeta {          // per-column header of a pot_table_t
+  double begin[IMDB_MAXCOL], end[IMDB_MAXCOL], invstep[IMDB_MAXCOL];
+  int ncols, nrows;       // nrows = rows of the derived table (maxsteps)
+};
+
+struct DevTables {
+  TabMeta pair, embed, rho;
+  const double *pairVG;   // [nrows][ncols][6]  c0 c1 c2 g1 g2 -      value+grad of phi
+  const double *embedVG;  // [nrows][ntypes][6]                      value+grad of F
+  const double *rhoV;     // [nrows][ncols][4]  c0 c1 c2 -            value of rho   (pass 1)
+  const double *rhoG;     // [nrows][ncols][2]  g1 g2                 grad of rho    (pass 2)
+  const double *fused1;   // [nrows][ncols][8]  phi:c0 c1 c2 g1 g2  rho:c0 c1 c2   (pass 1, shared grid)
+  int have_eam, fused, ntypes;
+};
+
+// ---- geometry ------------------------------------------------------------------------------------
+struct Geom {
+  double box[3][3];       // box_x, box_y, box_z
+  double tbox[3][3];      // reciprocal vectors, SPROD(box_i,tbox_j) = delta_ij (make_box)
+  int pbc[3];
+  int gdim[3];            // global_cell_dim
+  int cdim[3];            // local cell_dim incl. the two buffer layers
+  int coff[3];            // my_coord * (cell_dim-2): global cell coordinate of local cell 1
+  int nall;               // cdim.x*cdim.y*cdim.z
+  double cellsz;          // (r_cut_max + nbl_margin)^2
+};
+
+// one buffer (ghost) cell of the local grid and where its content comes from
+struct GhostCell { int dst, src; int code; int peer; };
+// code = (sx+1) + 3*(sy+1) + 9*(sz+1), s in {-1,0,1}: image shift in box units
+
+struct imdb200_sim {
+  imdb200_config cfg;
+  Geom geom;
+  double height[3], min_height[3], max_height[3], volume, volume_init;
+  double cellsz0;                 // max table end (r^2) before the margin is added
+  DevTables tabs;
+  void *tab_mem[8];
+  int have_tabs;
+  cudaStream_t stream; int own_stream;
+  // atoms
+  long n_own, n_ghost, cap_atoms; // capacity of the per-atom arrays
+  double4 *pos, *pos_alt, *mom, *mom_alt, *frc;
+  int *nummer, *nummer_alt;
+  double *rho, *dF, *nblpos, *presstens; // presstens [6][cap] SoA
+  int *cellid, *cellid_alt, *perm;
+  // cells
+  int *cell_count, *cell_start, *cell_fill, *cell_code;
+  GhostCell *gcells; int n_gcells;
+  int *gcount, *gstart;
+  int *gsrc; unsigned char *gcode;      // per ghost atom
+  int *scan_tmp;
+  // neighbour list
+  int *nbl, *nnb; long nbl_cap_rows; int max_nb, lanes; long n_pad;
+  int have_valid_nbl, nbl_count; long long nbl_len;
+  // restrictions / deformation tables per virtual type
+  double *restr; int n_restr;
+  // scalars
+  double *d_scal;      // device scalar block, see SC_*
+  double *h_scal;      // pinned mirror
+  double *d_partial;   // per-block partial sums
+  int *d_flags, *h_flags;
+  int press_calc, is_short;
+  long long nactive;   // sum of the restriction components over all atoms (3N by default)
+  double eta;
+  // timers
+  cudaEvent_t ev[16];
+  double t_ms[8];
+  // comm
+  void *nccl_comm; int rank, nranks;
+};
+
+enum { SC_EPOT = 0, SC_VIRIAL, SC_EKIN, SC_EKIN2, SC_MAXD2, SC_ETA, SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX,
+       SC_PXY, SC_EKIN1, SC_COUNT = 16 };
+enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_COUNT = 8 };
+
+// ---- error handling --------------------------------------------------------------------------------
+int imdb_fail(int code, const char *fmt, ...);
+extern long long g_kernel_launches;
+#define CUDA_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return imdb_fail(IMDB200_ERR_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define LAUNCH_CHECK() do { g_kernel_launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+  return imdb_fail(IMDB200_ERR_CUDA, "%s:%d: kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+#define TRY(call) do { int r_ = (call); if (r_) return r_; } while (0)
+
+static inline int cdiv(long a, long b) { return (int) ((a + b - 1) / b); }
+
+// ---- cross-file entry points -------------------------------------------------------------------------
+int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_pot_table *embed,
+                  const imdb200_pot_table *rho);
+void tables_free(imdb200_sim *s);
+int tables_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2, double *pot, double *grad);
+
+int geom_make_box(imdb200_sim *s);           // make_box + init_cells when needed
+int cells_ensure_capacity(imdb200_sim *s, long n_atoms_total);
+int cells_rebuild(imdb200_sim *s);            // fix_cells + ghost images + make_nblist
+int cells_refresh_ghost_pos(imdb200_sim *s);  // send_cells(copy_cell...)
+int cells_refresh_ghost_dF(imdb200_sim *s);   // send_cells(copy_dF...)
+int scan_exclusive(imdb200_sim *s, const int *in, int *out, int n, int *total_dev);
+
+int forces_pass1(imdb200_sim *s);             // pair + rho + embedding
+int forces_pass2(imdb200_sim *s);             // EAM force pass
+int integrate_move(imdb200_sim *s);           // move_atoms_nve/nvt + check_nblist fused
+int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate);
+
+// ---- device helpers ------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ int sorte_of(double w) { return (int) (__double_as_longlong(w) & 0xffffffffLL); }
+__device__ __forceinline__ int vsorte_of(double w) { return (int) (__double_as_longlong(w) >> 32); }
+__device__ __forceinline__ double pack_types(int sorte, int vsorte)
+{ return __longlong_as_double(((long long) vsorte << 32) | (unsigned int) sorte); }
+
+// r2 = SPROD(d,d) with the reference's rounding: ((dx*dx)+(dy*dy))+(dz*dz), no FMA
+// (src/makros.h:409, src/imd_forces_nbl.c:252-258).
+__device__ __forceinline__ double r2_exact(double dx, double dy, double dz)
+{ return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)); }
+
+// Table index exactly as PAIR_INT2 computes it (src/potaccess.h:329-341):
+//   r2a = MIN(r2,end) - begin; if (r2a<0) {r2a=0; is_short=1;}  r2a *= invstep; k=(int)r2a; chi=r2a-k
+// (int) truncation of the non-negative r2a is done on the FP64 pipe: adding 2^52 with
+// round-toward-zero leaves floor(r2a) in the low mantissa bits, and subtracting 2^52 again gives
+// it back as a double -- both exact -- instead of the slow F2I/I2F conversion pipe.
+__device__ __forceinline__ void tab_index(double r2, double begin, double end, double invstep,
+                                          int &k, double &chi, int &is_short)
+{
+  double r2a = fmin(r2, end) - begin;
+  if (r2a < 0.0) { r2a = 0.0; is_short = 1; }
+  r2a = __dmul_rn(r2a, invstep);
+  double tk = __dadd_rz(r2a, IMDB_TWO52);
+  k = __double2loint(tk);
+  chi = r2a - (tk - IMDB_TWO52);
+}
+
+__device__ __forceinline__ double2 ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV values; thread 0 of the block writes them to partial[blockIdx.x*NV + v].
+template <int NV> __device__ __forceinline__ void block_sum_store(double (&v)[NV], double *partial)
+{
+  __shared__ double sm[32][NV];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) sm[w][i] = v[i];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double x = (lane < nw) ? sm[lane][i] : 0.0;
+      x = warp_sum(x);
+      if (lane == 0) partial[(size_t) blockIdx.x * NV + i] = x;
+    }
+  }
+}
+#endif

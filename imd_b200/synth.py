@@ -211,3 +211,24 @@ def lj_param(outdir, ncell=(8, 8, 8), *, name="lj", maxsteps=20, starttemp=0.004
     if extra:
         kw.update(extra)
     return write_param(os.path.join(outdir, name + ".param"), **kw)
+
+
+def fcc_lattice(ncell, a0, offset=0.25):
+    """Positions of an fcc crystal of ncell unit cells (like IMD's _fcc generator, src/imd_generate.c:306-484,
+    but in plain lexicographic order).  Returns (n,3) float64 and the box matrix."""
+    nx, ny, nz = ncell
+    base = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]]) + offset
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cells = np.stack([ix, iy, iz], -1).reshape(-1, 1, 3).astype(np.float64)
+    ort = ((cells + base[None]) * a0).reshape(-1, 3)
+    box = np.diag([nx * a0, ny * a0, nz * a0]).astype(np.float64)
+    return ort, box
+
+
+def maxwell_momenta(n, mass, temperature, seed=1):
+    """Gaussian momenta with sigma = sqrt(T m) and zero total momentum (what maxwell() produces,
+    src/imd_maxwell.c:80-295, from numpy's generator instead of drand48)."""
+    rng = np.random.default_rng(seed)
+    p = rng.standard_normal((n, 3)) * np.sqrt(temperature * np.asarray(mass).reshape(-1, 1))
+    p -= p.mean(axis=0)
+    return p

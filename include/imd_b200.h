@@ -1,0 +1,186 @@
+/* imd_b200.h -- C ABI of the B200-native force-and-integrate engine.
+ *
+ * This is the drop-in boundary for IMD's NVE/NVT step loop.  IMD has
+ * no run-time plugin ABI: its "operator interface" is link-time substitution of
+ *     calc_forces / make_nblist / check_nblist / fix_cells / move_atoms / lin_deform ...
+ * selected by the Makefile (precedent: FORCESOURCES = imd_forces_cbe.c, src/Makefile:1141-1143;
+ * the same surface is listed for scripting in src/imd.i:37-71).  Each entry point below
+ * names the reference symbol it replaces.  All arguments are plain C: pointers, sizes and
+ * doubles, host memory unless stated otherwise.  There is no CPU fallback anywhere: every
+ * entry point needs a CUDA device of compute capability 10.0 (B200, sm_100a) and returns
+ * IMDB200_ERR_CUDA (or calls the error handler) without one.
+ *
+ * Error convention: functions return 0 on success, a negative IMDB200_ERR_* otherwise, and
+ * leave a message retrievable by imdb200_last_error().  A host that wants IMD's convention
+ * (error() -> imderror() prints and exits, src/imd_misc.c:78-98, src/makros.h:23) installs
+ * its handler with imdb200_set_error_handler(); it is then called before the function returns.
+ *
+ * Threading: one host thread (or process) per simulation handle / GPU, like one MPI rank per
+ * domain in the reference.  Handles are independent.
+ */
+#ifndef IMD_B200_H
+#define IMD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMDB200_VERSION 1
+
+enum {
+  IMDB200_OK = 0,
+  IMDB200_ERR_ARG = -1,     /* bad argument / call order                                  */
+  IMDB200_ERR_CUDA = -2,    /* CUDA runtime error, or no sm_100 device                    */
+  IMDB200_ERR_NBL = -3,     /* "neighbor table full" (src/imd_forces_nbl.c:265-267)       */
+  IMDB200_ERR_CELLS = -4,   /* "global_cell_dim too small" (src/imd_geom_3d.c:163-177)    */
+  IMDB200_ERR_COMM = -5,    /* NCCL / halo exchange failure                               */
+  IMDB200_ERR_IO = -6,      /* file errors of the host-side readers                       */
+  IMDB200_ERR_EXPLODE = -7  /* "system seems to explode!" (src/imd_geom_3d.c:96)          */
+};
+
+enum { IMDB200_ENS_NVE = 0, IMDB200_ENS_NVT = 1 }; /* ensemble keyword, src/imd_param.c:377-444 */
+
+typedef struct imdb200_sim imdb200_sim;
+
+/* Mirrors pot_table_t (src/types.h:416-428): ncols columns interleaved row by row,
+ * table[k*ncols+col], (maxsteps+2) rows allocated, the two pad rows already filled by
+ * init_threepoint (src/imd_potential.c:1256-1272). */
+typedef struct {
+  double *begin, *end, *step, *invstep;
+  int *len;
+  int ncols, maxsteps;
+  double *table;
+} imdb200_pot_table;
+
+/* The run-time parameters of the hot path; names follow IMD's parameter-file keys
+ * (src/imd_param.c) and globals (src/globals.h). */
+typedef struct {
+  int ntypes;              /* ntypes                                                       */
+  int total_types;         /* total_types (virtual types; >= ntypes)                       */
+  double box_x[3], box_y[3], box_z[3]; /* box_x / box_y / box_z                            */
+  int pbc_dirs[3];         /* pbc_dirs                                                     */
+  int cpu_dim[3];          /* cpu_dim: process (GPU) grid                                  */
+  int my_coord[3];         /* this rank's coordinates in the grid (MPI_Cart_coords)        */
+  double nbl_margin;       /* nbl_margin (default 0.4, src/globals.h:419)                  */
+  double nbl_size;         /* nbl_size   (default 1.1)                                     */
+  double timestep;         /* timestep                                                     */
+  int ensemble;            /* IMDB200_ENS_*                                                */
+  double temperature;      /* starttemp (NVT target)                                       */
+  double eta;              /* eta                                                          */
+  double isq_tau_eta;      /* 1/tau_eta^2                                                  */
+  int device;              /* CUDA device ordinal, -1: current device                      */
+  int lanes_per_atom;      /* 0 = choose; else 1,2,4,8,16,32 lanes cooperate on one atom   */
+} imdb200_config;
+
+void        imdb200_default_config(imdb200_config *cfg);
+const char *imdb200_last_error(void);
+void        imdb200_set_error_handler(void (*handler)(const char *msg));
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+long long   imdb200_kernel_launches(void);
+
+/* ---- setup ------------------------------------------------------------------------------ */
+/* replaces: globals filled by read_parameters() + make_box() + init_cells()
+ * (src/imd_param.c:3880, src/imd_geom_3d.c:52-104, 113-426) */
+int  imdb200_create(const imdb200_config *cfg, imdb200_sim **out);
+void imdb200_destroy(imdb200_sim *sim);
+
+/* replaces: the device-side view of pair_pot, embed_pot, rho_h_tab after setup_potentials()
+ * (src/imd_potential.c:43-130).  embed and rho may both be NULL: pair interactions only
+ * (imd_nve_nbl build).  cellsz (max table end, in r^2) is taken from the tables the way
+ * read_pot_table does (src/imd_potential.c:406). */
+int  imdb200_set_potentials(imdb200_sim *sim, const imdb200_pot_table *pair,
+                            const imdb200_pot_table *embed, const imdb200_pot_table *rho);
+
+/* restrictions per virtual type (3 doubles each); default all 1 (src/imd_param.c:2053-2066) */
+int  imdb200_set_restrictions(imdb200_sim *sim, int total_types, const double *restrictions);
+
+/* replaces: the per-cell atom arrays filled by generate_atoms()/read_atoms()
+ * (src/imd_generate.c, src/imd_io_3d.c:44-).  Arrays are in any order; ort/impuls are
+ * n x 3.  Only atoms inside this rank's domain are kept when cpu_dim != 1 1 1.
+ * vsorte may be NULL (= sorte), impuls may be NULL (= 0). */
+int  imdb200_set_atoms(imdb200_sim *sim, long n, const int *nummer, const int *sorte,
+                       const int *vsorte, const double *masse, const double *ort,
+                       const double *impuls);
+
+/* run all kernels of this handle on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g.
+ * torch.cuda.current_stream().cuda_stream, so that the caller's events bracket our launches */
+int  imdb200_set_stream(imdb200_sim *sim, void *cuda_stream);
+
+/* multi-GPU: attach an initialised NCCL communicator (ncclComm_t passed as void*) whose
+ * rank order is x-major over cpu_dim like MPI_Cart_create (src/imd_geom_mpi_3d.c:43-62).
+ * Alternatively let the library create it from a ncclUniqueId broadcast by the host. */
+int  imdb200_comm_unique_id(void *id128);                 /* rank 0: fills 128 bytes        */
+int  imdb200_comm_init(imdb200_sim *sim, const void *id128, int rank, int nranks);
+
+/* ---- the step loop ---------------------------------------------------------------------- */
+/* replaces: void calc_forces(int steps)  (src/imd_forces_nbl.c:281-1999; prototypes.h:173) */
+int  imdb200_calc_forces(imdb200_sim *sim, int steps);
+/* replaces: (*move_atoms)() = move_atoms_nve / move_atoms_nvt (src/imd_integrate.c:32, 891) */
+int  imdb200_move_atoms(imdb200_sim *sim);
+/* replaces: void check_nblist(void) (src/imd_forces_nbl.c:2007-2037) */
+int  imdb200_check_nblist(imdb200_sim *sim);
+/* replaces: void fix_cells(void) (src/imd_fix_cells_3d.c:36-201) + do_boundaries */
+int  imdb200_fix_cells(imdb200_sim *sim);
+/* replaces: void make_nblist(void) (src/imd_forces_nbl.c:136-273) */
+int  imdb200_make_nblist(imdb200_sim *sim);
+/* nsteps iterations of { calc_forces; move_atoms; check_nblist } kept on the device
+ * (main_loop body, src/imd_main_3d.c:405, 559, 768-772) */
+int  imdb200_run(imdb200_sim *sim, int nsteps);
+/* do_press_calc (src/imd_main_3d.c:183-195): accumulate the per-atom stress tensor */
+int  imdb200_set_press_calc(imdb200_sim *sim, int on);
+int  imdb200_invalidate_nblist(imdb200_sim *sim);         /* have_valid_nbl = 0              */
+int  imdb200_set_eta(imdb200_sim *sim, double eta);
+int  imdb200_set_temperature(imdb200_sim *sim, double temperature);
+
+/* replaces: lin_deform(dx,dy,dz,scale) (src/imd_deform.c:35-119) incl. make_box() */
+int  imdb200_lin_deform(imdb200_sim *sim, const double dx[3], const double dy[3],
+                        const double dz[3], double scale);
+/* replaces: deform_sample() (src/imd_deform.c:232-269); arrays per virtual type */
+int  imdb200_deform_sample(imdb200_sim *sim, double deform_size, const double *deform_shift,
+                           const int *shear_def, const double *deform_shear,
+                           const double *deform_base);
+
+/* ---- results ---------------------------------------------------------------------------- */
+/* globals after a step, summed over ranks like the MPI_Allreduce sites
+ * (src/imd_forces_nbl.c:1975-1994, src/imd_integrate.c:437-466, 1104-1130) */
+typedef struct {
+  double tot_pot_energy, tot_kin_energy, virial;
+  double volume;
+  double eta;
+  double max_displacement2;  /* check_nblist's max |x - nbl_pos|^2                          */
+  double tot_presstens[6];   /* xx yy zz yz zx xy (calc_tot_presstens, imd_main_3d.c:2069)   */
+  long long natoms, nactive;
+  long long nbl_len;         /* stored (full-list) neighbour entries on this rank            */
+  int have_valid_nbl, nbl_count, is_short;
+  int global_cell_dim[3], cell_dim[3];
+  double cellsz;
+} imdb200_scalars;
+int  imdb200_get_scalars(imdb200_sim *sim, imdb200_scalars *out);
+
+/* copy the owned atoms back to the host (any pointer may be NULL); returns the count.
+ * Order: the device's cell-sorted order; identify atoms by nummer (NUMMER, types.h:189). */
+long imdb200_get_atoms(imdb200_sim *sim, int *nummer, int *sorte, int *vsorte, double *masse,
+                       double *ort, double *impuls, double *kraft, double *poteng,
+                       double *eam_rho, double *eam_dF, double *presstens, double *nbl_pos);
+long imdb200_natoms_local(imdb200_sim *sim);
+/* test hook: the neighbour list as (nummer_i, nummer_j, image shift of j) triples; the list is
+ * stored in full (both directions).  Returns the number of entries (call with cap = 0 first). */
+long imdb200_get_nblist(imdb200_sim *sim, int *nummer_i, int *nummer_j, signed char *shift3, long cap);
+/* interpolate through the device tables with the kernels' own lookup code (test hook for
+ * PAIR_INT2, src/potaccess.h:323-354); which: 0 pair, 1 embed, 2 rho */
+int  imdb200_pair_int(imdb200_sim *sim, int which, int col, long n, const double *r2,
+                      double *pot, double *grad);
+/* device time (ms) spent in each phase since the last reset: rebuild, pass1, pass2, integrate, comm */
+int  imdb200_get_timers(imdb200_sim *sim, double out_ms[8], int reset);
+
+/* ---- host-side helpers kept from IMD's setup layer (plain C, no CUDA) -------------------- */
+/* replaces: read_pot_table() + init_threepoint() (src/imd_potential.c:161-462, 1256-1272).
+ * default_format: DEFAULT_POTFILE_TYPE (2 in EAM builds, 1 otherwise; src/config.h:57-63). */
+int  imdb200_read_pot_table(imdb200_pot_table *pt, const char *filename, int ncols, int radial,
+                            int ntypes, int default_format, double *cellsz);
+void imdb200_free_pot_table(imdb200_pot_table *pt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMD_B200_H */

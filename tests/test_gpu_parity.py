@@ -1,0 +1,151 @@
+"""GPU: the CUDA engine, called through the C ABI, against (a) the fixtures the unmodified reference
+produced, (b) the CPU oracle on seeded inputs, (c) size-independent properties at BASELINE's full size."""
+import numpy as np
+import pytest
+
+from tests import common
+from imd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["cu_nve", "nial_nvt", "lj_nve", "cu_slab", "cu_long"]
+
+
+@pytest.fixture(scope="module")
+def api(built_lib):
+    from imd_b200 import api as a
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return a
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 32])
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_reference_fixture(api, name, lanes, tmp_path):
+    g = common.load_golden(name)
+    sim = common.make_sim(api.IMDB200, g, str(tmp_path), lanes_per_atom=lanes)
+    out = common.run_protocol(sim, g)
+    errs = common.compare(out, g, full_list=True, rtol=1e-10, traj_rtol=1e-8)
+    assert np.array_equal(sim.celldims()[0], g["gdim"])
+    assert sim.cellsz == float(g["cellsz"])
+    print(name, lanes, {k: f"{v:.1e}" for k, v in errs.items()})
+    sim.close()
+
+
+def test_cuda_potaccess_known_answers(api, tmp_path):
+    """Device table lookup against PAIR_INT2 known answers from the reference macro."""
+    g = common.load_golden("potaccess")
+    paths = common.write_tables(g, str(tmp_path))
+    sim = api.IMDB200(2, np.eye(3) * 20.0, pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
+    for key in g:
+        if not key.startswith("x:"):
+            continue
+        _, which, col = key.split(":")
+        v, gr = sim.pair_int(int(which), int(col), g[key])
+        rv, rg = g[f"v:{which}:{col}"], g[f"g:{which}:{col}"]
+        assert np.max(np.abs(v - rv)) <= 1e-13 * max(1.0, np.max(np.abs(rv))), (which, col)
+        assert np.max(np.abs(gr - rg)) <= 1e-12 * max(1.0, np.max(np.abs(rg))), (which, col)
+    sim.close()
+
+
+def _thermal_cu(tmp_path, ncell, temp=0.08, seed=3):
+    tabs = synth.make_eam_tables(str(tmp_path), "cu")
+    ort, box = synth.fcc_lattice(ncell, synth.CU_A0)
+    n = len(ort)
+    rng = np.random.default_rng(seed)
+    ort = ort + rng.normal(0, 0.05, ort.shape)
+    masse = np.full(n, synth.CU_MASS)
+    p = synth.maxwell_momenta(n, masse, temp, seed)
+    return tabs, box, np.arange(n, dtype=np.int32), np.zeros(n, np.int32), masse, ort, p
+
+
+@pytest.mark.parametrize("lanes", [0, 1, 8])
+def test_cuda_vs_oracle_seeded_16k(api, lanes, tmp_path):
+    """Same seeded input through the CPU oracle and the CUDA path (16 384 atoms, 8 steps)."""
+    from oracle import oracle as orc
+    tabs, box, num, typ, m, x, p = _thermal_cu(tmp_path, (16, 16, 16))
+    kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"])
+    o = orc.OracleIMD(1, box, **kw)
+    o.set_atoms(num, typ, m, x, p); o.set_integrator("nve", 0.001)
+    c = api.IMDB200(1, box, ensemble="nve", timestep=0.001, lanes_per_atom=lanes, **kw)
+    c.set_atoms(num, typ, m, x, p)
+    for s in range(8):
+        o.calc_forces(s); c.calc_forces(s)
+        if s in (0, 7):
+            a, b = o.atoms(), c.atoms()
+            tol = 1e-10 if s == 0 else 1e-8
+            for k in ("kraft", "poteng", "rho", "dF"):
+                assert common.relerr(b[k], a[k]) <= tol, (s, k, common.relerr(b[k], a[k]))
+            so, sc = o.scalars(), c.scalars()
+            assert abs(sc["tot_pot_energy"] - so["tot_pot_energy"]) <= tol * abs(so["tot_pot_energy"])
+            assert abs(sc["virial"] - so["virial"]) <= tol * abs(so["virial"])
+        if s == 0:
+            from oracle.oracle import canonical_pairs
+            want = common.symmetric_closure(canonical_pairs(*o.nbl_pairs()))
+            pr, sh = c.nbl_pairs()
+            got = np.unique(np.column_stack([pr.astype(np.int64), sh.astype(np.int64)]), axis=0)
+            assert got.shape == want.shape and np.array_equal(got, want)
+        o.move_atoms(); c.move_atoms(); o.check_nblist(); c.check_nblist()
+        assert o.have_valid_nbl == c.have_valid_nbl
+        assert abs(c.scalars()["tot_kin_energy"] - o.scalars()["tot_kin_energy"]) <= 1e-9 * o.scalars()["tot_kin_energy"]
+    c.close()
+
+
+def test_cuda_run_loop_equals_stepwise_calls(api, tmp_path):
+    """imdb200_run (device-resident loop) must give bit-identical state to the three separate calls."""
+    tabs, box, num, typ, m, x, p = _thermal_cu(tmp_path, (8, 8, 8), temp=0.15)
+    kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"],
+              ensemble="nve", timestep=0.001)
+    a = api.IMDB200(1, box, **kw); a.set_atoms(num, typ, m, x, p)
+    b = api.IMDB200(1, box, **kw); b.set_atoms(num, typ, m, x, p)
+    a.run(30)
+    for s in range(30):
+        b.calc_forces(s); b.move_atoms(); b.check_nblist()
+    A, B = a.atoms(), b.atoms()
+    assert np.array_equal(A["ort"], B["ort"]) and np.array_equal(A["impuls"], B["impuls"])
+    assert a.nbl_count == b.nbl_count and a.nbl_count >= 2
+    a.close(); b.close()
+
+
+def test_full_size_properties_4m(api, tmp_path):
+    """BASELINE config 2 at full size (100^3 fcc cells = 4 000 000 atoms): size-independent properties."""
+    tabs = synth.make_eam_tables(str(tmp_path), "cu")
+    ort, box = synth.fcc_lattice((100, 100, 100), synth.CU_A0)
+    n = len(ort)
+    masse = np.full(n, synth.CU_MASS)
+    sim = api.IMDB200(1, box, ensemble="nve", timestep=0.001, pair=tabs["core_potential_file"],
+                      embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"])
+    # (1) perfect lattice: zero forces, uniform energy/density, 78 neighbours per atom inside r_list
+    sim.set_atoms(np.arange(n, dtype=np.int32), np.zeros(n, np.int32), masse, ort)
+    sim.calc_forces(0)
+    a = sim.atoms(sort=False)
+    assert np.max(np.abs(a["kraft"])) < 1e-11
+    assert np.ptp(a["poteng"]) < 1e-11 and np.ptp(a["rho"]) < 1e-11
+    sc = sim.scalars()
+    assert sc["nbl_len"] == 78 * n
+    gd, _ = sim.celldims()
+    assert tuple(gd) == (61, 61, 61)
+    assert abs(sc["tot_pot_energy"] - n * a["poteng"][0]) <= 1e-10 * abs(sc["tot_pot_energy"])
+    # (2) thermal state: Newton's third law (sum F = 0), momentum and energy conservation over 40 steps
+    p = synth.maxwell_momenta(n, masse, 0.05, 11)
+    sim.set_atoms(np.arange(n, dtype=np.int32), np.zeros(n, np.int32), masse, ort, p)
+    sim.calc_forces(0)
+    a = sim.atoms(sort=False)
+    fscale = np.abs(a["kraft"]).max()
+    sim.run(15)
+    sim.calc_forces(15)
+    a = sim.atoms(sort=False)
+    fscale = np.abs(a["kraft"]).max()
+    assert fscale > 0.1
+    assert np.max(np.abs(a["kraft"].sum(axis=0))) <= 1e-9 * fscale * np.sqrt(n)
+    e0 = None
+    es = []
+    for _ in range(5):
+        sim.run(5)
+        s = sim.scalars()
+        es.append(s["tot_pot_energy"] + s["tot_kin_energy"])
+    # leap-frog pairs Epot(x_s) with the mean of old/new kinetic energy: conserved to O(dt^2)
+    assert (max(es) - min(es)) / n < 2e-6, es
+    assert np.max(np.abs(sim.atoms(sort=False)["impuls"].sum(axis=0))) < 1e-7
+    assert sim.nbl_count >= 2
+    sim.close()

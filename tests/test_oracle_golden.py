@@ -1,0 +1,55 @@
+"""CPU: the oracle (oracle/imd_oracle.c) against the fixtures the unmodified reference produced."""
+import numpy as np
+import pytest
+
+from tests import common
+from oracle import oracle as orc
+
+CASES = ["cu_nve", "nial_nvt", "lj_nve", "cu_slab", "cu_long"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_fixture(name, tmp_path):
+    g = common.load_golden(name)
+    sim = common.make_sim(orc.OracleIMD, g, str(tmp_path))
+    out = common.run_protocol(sim, g)
+    errs = common.compare(out, g, full_list=False, rtol=1e-13, traj_rtol=1e-11)
+    assert np.array_equal(sim.celldims()[0], g["gdim"])
+    assert sim.cellsz == float(g["cellsz"])
+    print(name, {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+def test_oracle_potaccess_known_answers(tmp_path):
+    """PAIR_INT2 known answers computed by the reference's own macro (src/potaccess.h:323-354)."""
+    g = common.load_golden("potaccess")
+    paths = common.write_tables(g, str(tmp_path))
+    sim = orc.OracleIMD(2, np.eye(3) * 20.0, pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
+    for key in g:
+        if not key.startswith("x:"):
+            continue
+        _, which, col = key.split(":")
+        v, gr = sim.pair_int(int(which), int(col), g[key])
+        assert np.array_equal(v, g[f"v:{which}:{col}"]), (which, col)
+        assert np.array_equal(gr, g[f"g:{which}:{col}"]), (which, col)
+
+
+def test_oracle_perfect_lattice_known_answers(tmp_path):
+    """First-principles known answers: perfect fcc -> zero forces, 78 neighbours
+    inside r_list (5th..6th shell), identical per-atom energies."""
+    from imd_b200 import synth
+    tabs = synth.make_eam_tables(str(tmp_path), "cu", nr=601, nrho=801)
+    a0, nc = synth.CU_A0, 5
+    base = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]]) + 0.25
+    cells = np.stack(np.meshgrid(*[np.arange(nc)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    ort = ((cells[:, None, :] + base[None]) * a0).reshape(-1, 3)
+    n = len(ort)
+    sim = orc.OracleIMD(1, np.eye(3) * a0 * nc, pair=tabs["core_potential_file"],
+                        embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"])
+    sim.set_atoms(np.arange(n), np.zeros(n, int), np.full(n, synth.CU_MASS), ort)
+    sim.set_integrator("nve", 0.001)
+    sim.calc_forces(0)
+    a = sim.atoms()
+    assert np.max(np.abs(a["kraft"])) < 1e-12
+    assert np.ptp(a["poteng"]) < 1e-12 and np.ptp(a["rho"]) < 1e-12
+    pairs, _ = sim.nbl_pairs()
+    assert len(pairs) == 39 * n

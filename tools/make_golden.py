@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built by oracle/Makefile
+from /root/reference/src).  Run in the build container only; the fixtures are committed because
+/root/reference does not exist on the GPU box.
+
+    python tools/make_golden.py            # all cases
+
+Each fixture holds: the potential tables (as arrays, re-written to IMD format by tests/common.py),
+the start state written by the reference after its own thermalisation, and what the reference
+computed from it: per-atom forces/energies/densities, scalars per step, the Verlet neighbour set,
+rebuild flags and the final state.  The reference ships no golden vectors of its own
+(SURVEY.md section 4), so these are the pinned parity targets.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from imd_b200 import synth  # noqa: E402
+from oracle import ref_driver as rd  # noqa: E402
+from oracle.oracle import canonical_pairs  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # BASELINE config 2 in miniature: EAM Cu fcc, NVE, Verlet list + skin, 3x3x3 cells
+    "cu_nve": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=40, nsteps=24,
+                   record=[0, 23], press=True, variant="eam"),
+    # BASELINE config 3 in miniature: binary EAM Ni-Al (B2), NVT, two-species tables, 2x2x2 cells
+    "nial_nvt": dict(kind="nial", ncell=(5, 5, 5), ensemble="nvt", starttemp=0.06, warm=40, nsteps=16,
+                     record=[0, 15], press=True, variant="eam"),
+    # BASELINE config 1 in miniature: LJ Ar, tabulated pair potential (mklj layout), NVE
+    "lj_nve": dict(kind="lj", ncell=(4, 4, 4), ensemble="nve", starttemp=0.006, warm=40, nsteps=16,
+                   record=[0, 15], press=True, variant="pair"),
+    # free surfaces: no periodic images along z, one-cell-thick ghost shell only in x,y
+    "cu_slab": dict(kind="cu", ncell=(5, 5, 4), ensemble="nve", starttemp=0.05, warm=20, nsteps=8,
+                    record=[0, 7], press=False, variant="eam", extra=dict(pbc_dirs=[1, 1, 0])),
+    # non-cubic box, more cells, longer run with several rebuilds
+    "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
+                    record=[0, 59], press=False, variant="eam"),
+}
+
+
+def table_arrays(paths):
+    out = {}
+    for key in ("core_potential_file", "embedding_energy_file", "atomic_e-density_file", "potfile"):
+        if key in paths:
+            with open(paths[key]) as f:
+                out["table:" + key] = np.frombuffer(f.read().encode(), dtype=np.uint8)
+    return out
+
+
+def make_case(name, c):
+    tmp = tempfile.mkdtemp(prefix="gold_" + name)
+    if c["kind"] == "cu":
+        tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+        p = synth.cu_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
+                           tables=tabs, extra=c.get("extra"))
+        ntypes = 1
+    elif c["kind"] == "nial":
+        tabs = synth.make_eam_tables(tmp, "nial", nr=601, nrho=801)
+        p = synth.nial_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
+                             tables=tabs, extra=c.get("extra"))
+        ntypes = 2
+    else:
+        tabs = synth.make_lj_table(tmp, nsteps=1200)
+        p = synth.lj_param(tmp, ncell=c["ncell"], starttemp=c["starttemp"], table=tabs, extra=c.get("extra"))
+        ntypes = 2
+    spec = dict(variant=c["variant"], paramfile=p, warm=c["warm"], nsteps=c["nsteps"],
+                record_atoms=c["record"], record_nbl=[0], press=c["press"])
+    out = rd.run_in_subprocess(spec, tmp)
+    g = dict(table_arrays(tabs))
+    g["ntypes"] = ntypes
+    g["ensemble"] = c["ensemble"]
+    g["press"] = int(c["press"])
+    g["nsteps"] = c["nsteps"]
+    g["record"] = np.array(c["record"])
+    g["pbc"] = np.array(c.get("extra", {}).get("pbc_dirs", [1, 1, 1]))
+    g["box"] = out["box"]
+    g["cellsz"] = out["cellsz"]
+    g["gdim"], g["cdim"] = out["celldims"]
+    sc0 = out["frames"][0]["scalars"]
+    g["timestep"] = sc0["timestep"]; g["temperature"] = sc0["temperature"]; g["eta0"] = sc0["eta"]
+    g["nactive"] = sc0["nactive"]
+    g["isq_tau_eta"] = 1.0 / 0.1 ** 2 if c["ensemble"] == "nvt" else 0.0
+    for k in ("nummer", "sorte", "vsorte", "masse", "ort", "impuls"):
+        g["start:" + k] = out["start"][k]
+    for k in ("ort", "impuls"):
+        g["final:" + k] = out["final"][k]
+    keys = ["tot_pot_energy", "virial"]
+    g["epot"] = np.array([f["scalars"]["tot_pot_energy"] for f in out["frames"]])
+    g["virial"] = np.array([f["scalars"]["virial"] for f in out["frames"]])
+    g["ekin"] = np.array([f["after"]["tot_kin_energy"] for f in out["frames"]])
+    g["eta"] = np.array([f["after"]["eta"] for f in out["frames"]])
+    g["valid"] = np.array([f["valid"] for f in out["frames"]])
+    g["nbl_count"] = out["nbl_count"]
+    for s in c["record"]:
+        a = out["frames"][s]["atoms"]
+        for k in ("kraft", "poteng", "rho", "dF", "presstens", "ort"):
+            g[f"f{s}:{k}"] = a[k]
+        if c["press"]:
+            g[f"f{s}:tot_presstens"] = out["frames"][s]["tot_presstens"]
+    fr0 = out["frames"][0]
+    g["nbl"] = canonical_pairs(fr0["nbl_pairs"], fr0["nbl_shift"]).astype(np.int32)
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **g)
+    print(f"{name}: {out['natoms']} atoms, cells {g['gdim']}, {len(g['nbl'])} pairs, "
+          f"{out['nbl_count']} list builds, {os.path.getsize(path) / 1024:.0f} kB")
+
+
+def make_potaccess():
+    """Known answers of PAIR_INT2 through the reference's own macro (src/potaccess.h:323-354)."""
+    tmp = tempfile.mkdtemp(prefix="gold_pot")
+    tabs = synth.make_eam_tables(tmp, "nial", nr=601, nrho=801)
+    p = synth.nial_param(tmp, ncell=(5, 5, 5), tables=tabs)
+    import pickle, subprocess
+    code = f"""
+import sys, pickle, numpy as np
+sys.path.insert(0, {ROOT!r})
+from oracle import ref_driver as rd
+sim = rd.RefIMD('eam', {p!r})
+rng = np.random.default_rng(7)
+out = {{}}
+for which, ncol, lo, hi in ((0, 4, 0.5, 31.0), (2, 4, 0.5, 31.0), (1, 2, -1.0, 45.0)):
+    for col in range(ncol):
+        x = np.concatenate([rng.uniform(lo, hi, 300), [lo, hi, 1.0, 30.25, 30.249999999, 0.0, 40.0]])
+        v, g = sim.pair_int(which, col, x)
+        out[(which, col)] = (x, v, g)
+pickle.dump(out, open({os.path.join(tmp, 'pa.pkl')!r}, 'wb'))
+"""
+    subprocess.check_call([sys.executable, "-c", code], cwd=tmp, stdout=subprocess.DEVNULL)
+    out = pickle.load(open(os.path.join(tmp, "pa.pkl"), "rb"))
+    g = dict(table_arrays(tabs))
+    g["ntypes"] = 2
+    for (which, col), (x, v, gr) in out.items():
+        g[f"x:{which}:{col}"] = x; g[f"v:{which}:{col}"] = v; g[f"g:{which}:{col}"] = gr
+    np.savez_compressed(os.path.join(GOLD, "potaccess.npz"), **g)
+    print("potaccess: done")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES) + ["potaccess"]
+    for n in names:
+        if n == "potaccess":
+            make_potaccess()
+        else:
+            make_case(n, CASES[n])
