@@ -93,7 +93,7 @@ void imdb200_destroy(imdb200_sim *s)
   if (!s) return;
   cudaStreamSynchronize(s->stream);
   tables_free(s);
-  void *ptrs[] = {s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF, s->nblpos,
+  void *ptrs[] = {s->posdf, s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF, s->nblpos,
                   s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start, s->cell_fill,
                   s->cell_code, s->gcells, s->gcount, s->gstart, s->gsrc, s->scan_tmp, s->nbl, s->nnb, s->restr,
                   s->d_scal, s->d_partial, s->d_flags};
@@ -406,11 +406,10 @@ long imdb200_get_nblist(imdb200_sim *s, int *ni, int *nj, signed char *shift3, l
   cudaMemcpy(cid.data(), s->cellid, ntot * sizeof(int), cudaMemcpyDeviceToHost);
   cudaMemcpy(code.data(), s->cell_code, s->geom.nall * sizeof(int), cudaMemcpyDeviceToHost);
   cudaMemcpy(nbl.data(), s->nbl, nbl.size() * sizeof(int), cudaMemcpyDeviceToHost);
-  const long rowstride = s->n_pad * L;
   long cnt = 0;
   for (long i = 0; i < n; i++)
     for (int m = 0; m < nnb[i]; m++) {
-      int j = nbl[(size_t) (m / L) * rowstride + i * L + (m % L)];
+      int j = nbl[nbl_index(i, m, L, s->max_nb / L)];
       int sx = 0, sy = 0, sz = 0, jn;
       if (j >= n) { int c = code[cid[j]]; sx = c % 3 - 1; sy = (c / 3) % 3 - 1; sz = c / 9 - 1; jn = num[gsrc[j - n]]; }
       else jn = num[j];

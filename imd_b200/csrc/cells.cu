@@ -137,7 +137,7 @@ int cells_ensure_capacity(imdb200_sim *s, long need)
   long n = s->n_own;
   TRY(regrow(&s->pos, n, cap)); TRY(regrow(&s->pos_alt, 0, cap));
   TRY(regrow(&s->mom, n, cap)); TRY(regrow(&s->mom_alt, 0, cap));
-  TRY(regrow(&s->frc, n, cap));
+  TRY(regrow(&s->frc, n, cap)); TRY(regrow(&s->posdf, 0, cap));
   TRY(regrow(&s->nummer, n, cap)); TRY(regrow(&s->nummer_alt, 0, cap));
   TRY(regrow(&s->rho, n, cap)); TRY(regrow(&s->dF, n, cap));
   TRY(regrow(&s->cellid, n, cap)); TRY(regrow(&s->cellid_alt, 0, cap)); TRY(regrow(&s->perm, 0, cap));
@@ -336,10 +336,13 @@ __global__ void k_ghost_cellid(const GhostCell *gc, int ng, const int *gstart, c
   for (int t = lane; t < cnt; t += 32) cellid_g[st + t] = dst;
 }
 
-__global__ void k_ghost_dF(double *dF, long n_own, long n_ghost, const int *gsrc)
+__global__ void k_ghost_dF(double *dF, double4 *posdf, const double4 *pos, long n_own, long n_ghost, const int *gsrc)
 {
   long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
-  if (t < n_ghost) dF[n_own + t] = dF[gsrc[t]];
+  if (t >= n_ghost) return;
+  const double d = dF[gsrc[t]];
+  dF[n_own + t] = d;
+  if (posdf) { const double4 p = pos[n_own + t]; posdf[n_own + t] = make_double4(p.x, p.y, p.z, d); }
 }
 
 int cells_refresh_ghost_pos(imdb200_sim *s)
@@ -354,7 +357,8 @@ int cells_refresh_ghost_pos(imdb200_sim *s)
 int cells_refresh_ghost_dF(imdb200_sim *s)
 {
   if (s->n_ghost == 0) return 0;
-  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->n_own, s->n_ghost, s->gsrc);
+  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->tabs.ntypes == 1 ? s->posdf : nullptr, s->pos, s->n_own,
+                                                             s->n_ghost, s->gsrc);
   LAUNCH_CHECK();
   return 0;
 }
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(128)
 k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__restrict__ cellid,
             const int *__restrict__ cell_start, const int *__restrict__ cell_count,
             const int *__restrict__ cell_code, const int *__restrict__ gsrc,
-            int *__restrict__ nbl, int *__restrict__ nnb, int max_nb, long rowstride, int L,
+            int *__restrict__ nbl, int *__restrict__ nnb, int max_nb, int L,
             int *flags, int count_only)
 {
   long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
@@ -406,7 +410,7 @@ k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__re
             const double4 xj = pos[gsrc[j - n_own]];
             const double r2 = r2_exact(__dsub_rn(me.x, xj.x), __dsub_rn(me.y, xj.y), __dsub_rn(me.z, xj.z));
             if (r2 < g.cellsz) {
-              if (!count_only && cnt < max_nb) nbl[(long) (cnt / L) * rowstride + i * L + (cnt % L)] = j;
+              if (!count_only && cnt < max_nb) nbl[nbl_index(i, cnt, L, max_nb / L)] = j;
               cnt++;
             }
           }
@@ -417,7 +421,7 @@ k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__re
             const double4 xj = pos[j];
             const double r2 = r2_exact(__dsub_rn(xj.x, xi.x), __dsub_rn(xj.y, xi.y), __dsub_rn(xj.z, xi.z));
             if (r2 < g.cellsz) {
-              if (!count_only && cnt < max_nb) nbl[(long) (cnt / L) * rowstride + i * L + (cnt % L)] = j;
+              if (!count_only && cnt < max_nb) nbl[nbl_index(i, cnt, L, max_nb / L)] = j;
               cnt++;
             }
           }
@@ -514,7 +518,7 @@ int cells_rebuild(imdb200_sim *s)
       // size the table from an exact count (estimate_nblist_size, src/imd_forces_nbl.c:74-128)
       CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
       k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
-                                                s->gsrc, nullptr, nullptr, 0, 0, L, s->d_flags, 1); LAUNCH_CHECK();
+                                                s->gsrc, nullptr, nullptr, 0, L, s->d_flags, 1); LAUNCH_CHECK();
       TRY(read_flags(s));
       int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 2;
       TRY(alloc_nbl(s, want > 8 ? want : 8));
@@ -522,7 +526,7 @@ int cells_rebuild(imdb200_sim *s)
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_NBL_OVERFLOW], 0, sizeof(int), st));
     k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
-                                              s->gsrc, s->nbl, s->nnb, s->max_nb, s->n_pad * L, L, s->d_flags, 0); LAUNCH_CHECK();
+                                              s->gsrc, s->nbl, s->nnb, s->max_nb, L, s->d_flags, 0); LAUNCH_CHECK();
     TRY(read_flags(s));
     if (!s->h_flags[FL_NBL_OVERFLOW]) break;
     if (attempt == 2) return imdb_fail(IMDB200_ERR_NBL, "neighbor table full - increase nbl_size");

@@ -10,8 +10,9 @@
 //   rho   double[n_own]             host electron density          (EAM_RHO)
 //   dF    double[n_own + n_ghost]   2 F'(rho) of owners and images (EAM_DF)
 //   nblpos double[3][n_pad]         reference positions of the skin check (NBL_POS)
-//   nbl   int32[max_nb/L][n_pad*L]  FULL neighbour list, lane-interleaved rows so that a warp
-//                                   reads 128 contiguous bytes per row; nnb int32[n_own]
+//   nbl   int32[n_pad*L/32][max_nb/L][32]  FULL neighbour list in warp blocks: the 32 lanes of a warp
+//                                   (L lanes per atom) read one contiguous 128-byte row per iteration
+//                                   and a warp's whole list is one contiguous block; nnb int32[n_own]
 // 32-byte atom records make every gather exactly one 32-byte sector.
 #pragma once
 #include <cuda_runtime.h>
@@ -26,10 +27,13 @@
 // PAIR_INT2 (src/potaccess.h:323-354) evaluates on interval k, with chi in [0,1):
 //    val  = p0 + chi*dv + 0.5*chi*(chi-1)*d2v,   grad = 2*istep*(dv + (chi-0.5)*d2v)
 // with dv = p1-p0, d2v = p2-2*p1+p0.  We precompute per (k,col) on the host, in double:
-//    c0 = p0, c1 = dv - 0.5*d2v, c2 = 0.5*d2v, g1 = 2*istep*c1, g2 = 4*istep*c2
-// so that val = c0 + chi*(c1 + chi*c2) and grad = g1 + chi*g2: 3 DFMA instead of ~12 DP ops
-// and one contiguous fetch instead of three strided ones.  k and chi themselves are computed
-// with the reference's exact operation sequence (see tab_index()).
+//    c0 = p0, c1 = dv - 0.5*d2v, c2 = 0.5*d2v
+// so that val = c0 + chi*(c1 + chi*c2) and grad = 2*istep*(c1 + 2*chi*c2): 2-4 DFMA instead of
+// ~12 DP ops, and 24 bytes per lookup (one 16-byte + one 8-byte fetch) instead of three strided
+// ones.  The force kernels are bound by the L1/shared-memory gather pipe (profiles/), so bytes per
+// lookup are what counts: the gradient of phi is derived from (c1,c2) in registers, and pass 2
+// fetches only a 16-byte (h1,h2) = istep*(c1, 2*c2) pair, grad/2 = h1 + chi*h2.
+// k and chi are computed with the reference's operation sequence (see tab_index()).
 enum { TAB_PAIR = 0, TAB_EMBED = 1, TAB_RHO = 2 };
 
 struct TabMeta {          // per-column header of a pot_table_t
@@ -39,12 +43,14 @@ struct TabMeta {          // per-column header of a pot_table_t
 
 struct DevTables {
   TabMeta pair, embed, rho;
-  const double *pairVG;   // [nrows][ncols][6]  c0 c1 c2 g1 g2 -      value+grad of phi
-  const double *embedVG;  // [nrows][ntypes][6]                      value+grad of F
-  const double *rhoV;     // [nrows][ncols][4]  c0 c1 c2 -            value of rho   (pass 1)
-  const double *rhoG;     // [nrows][ncols][2]  g1 g2                 grad of rho    (pass 2)
-  const double *fused1;   // [nrows][ncols][8]  phi:c0 c1 c2 g1 g2  rho:c0 c1 c2   (pass 1, shared grid)
-  int have_eam, fused, ntypes;
+  const double2 *pairAB;  // [nrows][ncols]  (c0,c1) of phi
+  const double  *pairC;   // [nrows][ncols]  c2 of phi
+  const double2 *rhoAB;   // [nrows][ncols]  (c0,c1) of rho           (pass 1)
+  const double  *rhoC;    // [nrows][ncols]  c2 of rho
+  const double2 *rhoH;    // [nrows][ncols]  (h1,h2): rho'/2 = h1+chi*h2 (pass 2; the 0.5 of :1203 folded in)
+  const double  *embedVG; // [nrows][ntypes][6]  c0 c1 c2 g1 g2 -     value+grad of F (once per atom)
+  int have_eam, shared_grid, ntypes;
+  int smem1, smem2;       // dynamic shared memory (bytes) to stage the pass-1 / pass-2 tables; 0 = leave in HBM/L1
 };
 
 // ---- geometry ------------------------------------------------------------------------------------
@@ -77,6 +83,7 @@ struct imdb200_sim {
   double4 *pos, *pos_alt, *mom, *mom_alt, *frc;
   int *nummer, *nummer_alt;
   double *rho, *dF, *nblpos, *presstens; // presstens [6][cap] SoA
+  double4 *posdf;                 // single-species EAM: x,y,z + 2F'(rho) in .w, the pass-2 gather record
   int *cellid, *cellid_alt, *perm;
   // cells
   int *cell_count, *cell_start, *cell_fill, *cell_code;
@@ -118,6 +125,13 @@ extern long long g_kernel_launches;
 #define TRY(call) do { int r_ = (call); if (r_) return r_; } while (0)
 
 static inline int cdiv(long a, long b) { return (int) ((a + b - 1) / b); }
+
+// position of entry m of atom i in the warp-blocked neighbour list (L lanes per atom, R = max_nb/L rows)
+__host__ __device__ inline size_t nbl_index(long i, int m, int L, int R)
+{
+  const long slot = i * L + (m % L);
+  return (size_t) (slot >> 5) * ((size_t) R * 32) + (size_t) (m / L) * 32 + (size_t) (slot & 31);
+}
 
 // ---- cross-file entry points -------------------------------------------------------------------------
 int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_pot_table *embed,
@@ -165,7 +179,33 @@ __device__ __forceinline__ void tab_index(double r2, double begin, double end, d
   chi = r2a - (tk - IMDB_TWO52);
 }
 
+// Same index for the force kernels: r2 is known to be inside the column's cut-off (the MIN clamp is
+// inactive) and the subtraction and scaling are contracted into one DFMA.  k and chi can differ from
+// tab_index() only when r2a*invstep is within an ulp of an integer; the interpolant is continuous
+// there, so values move by ~1e-16 relative (parity bar 1e-10).
+__device__ __forceinline__ void tab_index_fast(double r2, double nbegin_istep, double invstep, int &k, double &chi,
+                                               int &is_short)
+{
+  double t = fma(r2, invstep, nbegin_istep);     // (r2 - begin) * invstep
+  if (t < 0.0) { t = 0.0; is_short = 1; }
+  const double tk = __dadd_rz(t, IMDB_TWO52);
+  k = __double2loint(tk);
+  chi = t - (tk - IMDB_TWO52);
+}
+
+// val = c0 + chi*(c1 + chi*c2); grad = G*(c1 + 2*chi*c2) with G = 2*invstep
+__device__ __forceinline__ double tab_val(double2 ab, double c2, double chi) { return fma(chi, fma(chi, c2, ab.y), ab.x); }
+__device__ __forceinline__ double tab_grad(double2 ab, double c2, double chi, double G) { return G * fma(chi + chi, c2, ab.y); }
+
 __device__ __forceinline__ double2 ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+// one 32-byte atom record = one sector, fetched with a single 256-bit load (LDG.E.ENL2.256, sm_100)
+__device__ __forceinline__ double4 ld_atom(const double4 *p)
+{
+  double4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ double warp_sum(double v)
 {

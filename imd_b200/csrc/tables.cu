@@ -28,13 +28,13 @@ static inline void coef(const imdb200_pot_table *pt, int k, int col, double out[
   out[4] = 4 * istep * out[2];
 }
 
-static int upload(imdb200_sim *s, int slot, const std::vector<double> &h, const double **dev)
+template <typename T> static int upload(imdb200_sim *s, int slot, const std::vector<T> &h, const T **dev)
 {
   void *p = nullptr;
-  CUDA_TRY(cudaMalloc(&p, h.size() * sizeof(double)));
-  CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&p, h.size() * sizeof(T)));
+  CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   s->tab_mem[slot] = p;
-  *dev = (const double *) p;
+  *dev = (const T *) p;
   return 0;
 }
 
@@ -42,6 +42,20 @@ void tables_free(imdb200_sim *s)
 {
   for (int i = 0; i < 8; i++) { if (s->tab_mem[i]) cudaFree(s->tab_mem[i]); s->tab_mem[i] = nullptr; }
   s->have_tabs = 0;
+}
+
+// (c0,c1) and c2 arrays of one table
+static void split_coefs(const imdb200_pot_table *pt, std::vector<double2> &ab, std::vector<double> &c)
+{
+  double c5[5];
+  ab.assign((size_t) pt->maxsteps * pt->ncols, make_double2(0.0, 0.0));
+  c.assign((((size_t) pt->maxsteps * pt->ncols + 1) / 2) * 2, 0.0);   // even length: staged 16 bytes at a time
+  for (int k = 0; k < pt->maxsteps; k++)
+    for (int col = 0; col < pt->ncols; col++) {
+      coef(pt, k, col, c5);
+      ab[(size_t) k * pt->ncols + col] = make_double2(c5[0], c5[1]);
+      c[(size_t) k * pt->ncols + col] = c5[2];
+    }
 }
 
 int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_pot_table *embed,
@@ -58,56 +72,50 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
   T.ntypes = nt;
   T.have_eam = rho != nullptr;
   TRY(fill_meta(T.pair, pair));
-  double c5[5];
-  {
-    std::vector<double> h((size_t) pair->maxsteps * pair->ncols * 6, 0.0);
-    for (int k = 0; k < pair->maxsteps; k++)
-      for (int c = 0; c < pair->ncols; c++) { coef(pair, k, c, c5); memcpy(&h[((size_t) k * pair->ncols + c) * 6], c5, 5 * sizeof(double)); }
-    TRY(upload(s, 0, h, &T.pairVG));
-  }
+  std::vector<double2> ab; std::vector<double> c;
+  split_coefs(pair, ab, c);
+  TRY(upload(s, 0, ab, &T.pairAB));
+  TRY(upload(s, 1, c, &T.pairC));
+  size_t bytes1 = (size_t) pair->maxsteps * pair->ncols * 24 + 8, bytes2 = 0;
   // cellsz = max end of the radial tables (src/imd_potential.c:364, 406)
   double cz = 0.0;
-  for (int c = 0; c < pair->ncols; c++) cz = cz > pair->end[c] ? cz : pair->end[c];
+  for (int col = 0; col < pair->ncols; col++) cz = cz > pair->end[col] ? cz : pair->end[col];
   if (rho) {
-    for (int c = 0; c < rho->ncols; c++) cz = cz > rho->end[c] ? cz : rho->end[c];
+    for (int col = 0; col < rho->ncols; col++) cz = cz > rho->end[col] ? cz : rho->end[col];
     TRY(fill_meta(T.embed, embed));
     TRY(fill_meta(T.rho, rho));
     {
+      double c5[5];
       std::vector<double> h((size_t) embed->maxsteps * embed->ncols * 6, 0.0);
       for (int k = 0; k < embed->maxsteps; k++)
-        for (int c = 0; c < embed->ncols; c++) { coef(embed, k, c, c5); memcpy(&h[((size_t) k * embed->ncols + c) * 6], c5, 5 * sizeof(double)); }
-      TRY(upload(s, 1, h, &T.embedVG));
+        for (int col = 0; col < embed->ncols; col++) { coef(embed, k, col, c5); memcpy(&h[((size_t) k * embed->ncols + col) * 6], c5, 5 * sizeof(double)); }
+      TRY(upload(s, 2, h, &T.embedVG));
     }
-    {
-      std::vector<double> hv((size_t) rho->maxsteps * rho->ncols * 4, 0.0), hg((size_t) rho->maxsteps * rho->ncols * 2, 0.0);
-      for (int k = 0; k < rho->maxsteps; k++)
-        for (int c = 0; c < rho->ncols; c++) {
-          coef(rho, k, c, c5);
-          memcpy(&hv[((size_t) k * rho->ncols + c) * 4], c5, 3 * sizeof(double));
-          memcpy(&hg[((size_t) k * rho->ncols + c) * 2], c5 + 3, 2 * sizeof(double));
-        }
-      TRY(upload(s, 2, hv, &T.rhoV));
-      TRY(upload(s, 3, hg, &T.rhoG));
-    }
+    split_coefs(rho, ab, c);
+    TRY(upload(s, 3, ab, &T.rhoAB));
+    TRY(upload(s, 4, c, &T.rhoC));
+    std::vector<double2> hh(ab.size());
+    for (int k = 0; k < rho->maxsteps; k++)
+      for (int col = 0; col < rho->ncols; col++) {
+        const size_t e = (size_t) k * rho->ncols + col;
+        // rho'/2 = istep*(c1 + 2*chi*c2): exact scalings of the products the reference forms
+        hh[e] = make_double2(rho->invstep[col] * ab[e].y, 2 * rho->invstep[col] * c[e]);
+      }
+    TRY(upload(s, 5, hh, &T.rhoH));
+    bytes1 += (size_t) rho->maxsteps * rho->ncols * 24 + 8;
+    bytes2 = (size_t) rho->maxsteps * rho->ncols * 16;
     // Shared grid: phi and rho use the same begin/invstep in every column, so one (k,chi)
     // serves both lookups of a pair in pass 1.  Inside `r2 <= end` / `r2 < end` the MIN(r2,end)
     // clamp of PAIR_INT2 is inactive, so differing ends do not matter.
-    int fused = 1;
-    for (int c = 0; c < pair->ncols; c++)
-      if (pair->begin[c] != rho->begin[c] || pair->invstep[c] != rho->invstep[c]) fused = 0;
-    if (fused) {
-      const int nr = pair->maxsteps > rho->maxsteps ? pair->maxsteps : rho->maxsteps;
-      std::vector<double> h((size_t) nr * pair->ncols * 8, 0.0);
-      for (int k = 0; k < nr; k++)
-        for (int c = 0; c < pair->ncols; c++) {
-          double *o = &h[((size_t) k * pair->ncols + c) * 8];
-          if (k < pair->maxsteps) { coef(pair, k, c, c5); memcpy(o, c5, 5 * sizeof(double)); }
-          if (k < rho->maxsteps) { coef(rho, k, c, c5); memcpy(o + 5, c5, 3 * sizeof(double)); }
-        }
-      TRY(upload(s, 4, h, &T.fused1));
-      T.fused = 1;
-    }
+    T.shared_grid = 1;
+    for (int col = 0; col < pair->ncols; col++)
+      if (pair->begin[col] != rho->begin[col] || pair->invstep[col] != rho->invstep[col]) T.shared_grid = 0;
   }
+  // Tables are staged in shared memory when they leave at least ~100 KB of the 228 KB SM array to L1
+  // (the position gathers live there); otherwise they stay in HBM and are served by L1/L2.
+  const size_t limit = 128 * 1024;
+  T.smem1 = bytes1 <= limit ? (int) bytes1 : 0;
+  T.smem2 = (bytes2 && bytes2 <= limit) ? (int) bytes2 : 0;
   s->cellsz0 = cz;
   s->have_tabs = 1;
   return 0;
@@ -121,16 +129,19 @@ __global__ void k_pair_int(DevTables T, int which, int col, long n, const double
   const TabMeta &m = which == TAB_PAIR ? T.pair : (which == TAB_EMBED ? T.embed : T.rho);
   int k, sh = 0; double chi;
   tab_index(r2[i], m.begin[col], m.end[col], m.invstep[col], k, chi, sh);
-  double c0, c1, c2, g1, g2;
-  if (which == TAB_RHO) {
-    const double *v = T.rhoV + ((size_t) k * m.ncols + col) * 4, *g = T.rhoG + ((size_t) k * m.ncols + col) * 2;
-    c0 = v[0]; c1 = v[1]; c2 = v[2]; g1 = g[0]; g2 = g[1];
+  const size_t e = (size_t) k * m.ncols + col;
+  if (which == TAB_EMBED) {
+    const double *v = T.embedVG + e * 6;
+    pot[i] = fma(chi, fma(chi, v[2], v[1]), v[0]);
+    grad[i] = fma(chi, v[4], v[3]);
   } else {
-    const double *v = (which == TAB_PAIR ? T.pairVG : T.embedVG) + ((size_t) k * m.ncols + col) * 6;
-    c0 = v[0]; c1 = v[1]; c2 = v[2]; g1 = v[3]; g2 = v[4];
+    const double2 ab = which == TAB_PAIR ? T.pairAB[e] : T.rhoAB[e];
+    const double c2 = which == TAB_PAIR ? T.pairC[e] : T.rhoC[e];
+    pot[i] = tab_val(ab, c2, chi);
+    // phi' as pass 1 forms it, rho' as pass 2 forms it
+    grad[i] = which == TAB_PAIR ? tab_grad(ab, c2, chi, 2.0 * m.invstep[col])
+                                : 2.0 * fma(chi, T.rhoH[e].y, T.rhoH[e].x);
   }
-  pot[i] = fma(chi, fma(chi, c2, c1), c0);
-  grad[i] = fma(chi, g2, g1);
 }
 
 int tables_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2, double *pot, double *grad)
