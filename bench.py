@@ -178,10 +178,22 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+def load_profile_traffic(n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if it was taken
+    on this workload."""
+    p = os.path.join(ROOT, "profiles", "top_kernel.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if int(d.get("natoms", -1)) == int(n):
+            return d
+    return None
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
-    from imd_b200 import api
+    from imd_b200 import api, synth
+    from imd_b200 import dist as idist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,11 +205,21 @@ def ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nc = args.ncell
     tmp = tempfile.mkdtemp(prefix="imdb200_")
-    tabs, box, num, typ, masse, ort, p = make_workload(tmp, (nc, nc, nc), 1234 + rank)
+    # weak scaling: every GPU owns one nc^3-cell block of a (px*nc, py*nc, pz*nc) crystal; the process grid is
+    # the one calc_cpu_dim picks (2 1 1 / 2 2 1 / 2 2 2), like `size_per_cpu 1` (src/imd_generate.c:292-296)
+    grid = idist.grid_for(world)
+    coord = api.cart_coords(rank, grid)
+    tabs, box1, num, typ, masse, ort, p = make_workload(tmp, (nc, nc, nc), 1234 + rank)
     n = len(num)
+    ort = ort + np.array(coord) * nc * synth.CU_A0
+    num = num + rank * n
+    box = box1 * np.array(grid)[:, None]
     kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"],
               rho=tabs["atomic_e-density_file"], ensemble="nve", timestep=0.001, device=local, nbl_size=1.2)
-    sim = api.IMDB200(1, box, **kw)
+    if world > 1:
+        sim = idist.create(1, box, cpu_dim=grid, **kw)      # halo exchange: NCCL p2p inside the library
+    else:
+        sim = api.IMDB200(1, box, **kw)
     stream = torch.cuda.current_stream()
     sim.set_stream(stream.cuda_stream)
     sim.set_atoms(num, typ, masse, ort, p)
@@ -224,17 +246,21 @@ def ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = api.kernel_launches() - l0
     tm = sim.timers()
-    sc = sim.scalars()
+    sc = sim.raw_scalars()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * n * args.steps / (ms_max * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers -------------------------------------------------
-    hp = [torch.from_numpy(x).pin_memory().numpy() for x in (num, typ, masse, ort, p)]
-    out = dict(ort=np.zeros((n, 3)), impuls=np.zeros((n, 3)), kraft=np.zeros((n, 3)), nummer=np.zeros(n, np.int32))
-    ke = min(args.steps, max(20, args.steps // 4))
+    # ---- end to end through the C ABI with HOST buffers ---------------------------------------------------
+    # the whole job as a user of the C ABI runs it: atom state uploaded from pinned host arrays, K steps with
+    # the energies read back to the host every step, positions / momenta / forces downloaded; wall clock
+    hp = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy() for x in (num, typ, masse, ort, p)]
+    out = {k: torch.empty(shape, dtype=dt).pin_memory().numpy() for k, shape, dt in
+           (("ort", (n, 3), torch.float64), ("impuls", (n, 3), torch.float64), ("kraft", (n, 3), torch.float64),
+            ("nummer", (n,), torch.int32))}
+    ke = args.steps
     barrier()
     t0 = time.perf_counter()
     sim.set_atoms(*hp)                                     # H2D of the whole atom state
@@ -246,14 +272,16 @@ def ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_v = world * n * ke / float(te.item())
-    h2d = n * (4 + 4 + 8 + 24 + 24) / ke + 0.0
-    d2h = (n * (4 + 24 + 24 + 24)) / ke + 16 * 8 + 8 * 4
+    h2d = world * n * (4 + 4 + 8 + 24 + 24) / ke
+    d2h = world * (n * (4 + 24 + 24 + 24)) / ke + world * (16 * 8 + 8 * 4)
 
     if rank == 0:
         peak, how = peaks()
-        t_p1 = tm["pass1_ms"] / max(tm["steps"], 1) * 1e-3
+        steps_t = max(tm["steps"], 1)
+        t_p1 = tm["pass1_ms"] / steps_t * 1e-3
         ach = B_PASS1 * n / t_p1 / 1e9 if t_p1 > 0 else 0.0
         step_ach = B_ALG * (n * args.steps / (ms * 1e-3)) / 1e9
+        prof = load_profile_traffic(n)
         cpu = cpu_baseline_serial(tmp) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
@@ -261,18 +289,24 @@ def ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"EAM Cu fcc {n} atoms/GPU ({nc}^3 cells), NVE, Verlet nbl + skin 0.4, "
                                    "synthetic Cu tables 2001/4001 rows, T0=0.05, dt=1fs",
-                       "global_atoms": world * n, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "global_atoms": world * n,
+                       "parallelism": ("spatial domain decomposition cpu_dim %d %d %d, NCCL p2p halo" % grid)
+                       if world > 1 else "single GPU",
                        "cache": "inputs (>= 128 MB positions + 1.3 GB list per step) exceed the 126 MB L2",
-                       "rebuilds_in_window": int(tm["rebuilds"]), "nbl_len_per_atom": sc["nbl_len"] / n},
+                       "rebuilds_in_window": int(tm["rebuilds"]), "nbl_len_per_atom": sc.nbl_len / n},
             "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": ke, "note": "imdb200_set_atoms (pinned host arrays) + run + imdb200_get_atoms, wall clock"},
+                    "steps": ke, "note": "imdb200_set_atoms (pinned host arrays) + imdb200_run (scalars to the host every "
+                                         "step) + imdb200_get_atoms, wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_pass1 (pair + rho + embedding)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
-                         "algorithmic_bytes_per_atom": B_PASS1,
+                         "unit": "GB/s", "frac": ach / peak,
+                         "traffic": prof["dram_bytes_per_launch"] if prof else None,
+                         "traffic_source": prof["source"] if prof else None, "peak_source": how,
+                         "algorithmic_bytes_per_launch": B_PASS1 * n, "algorithmic_bytes_per_atom": B_PASS1,
+                         "limiter": "L1/shared data pipe (gathers), see profiles/",
                          "whole_step": {"achieved": step_ach, "frac": step_ach / peak, "bytes_per_atom_step": B_ALG}},
-            "phase_ms_per_step": {k: tm[k] / max(tm["steps"], 1) for k in
+            "phase_ms_per_step": {k: tm[k] / steps_t for k in
                                   ("rebuild_ms", "pass1_ms", "pass2_ms", "integrate_ms", "ghost_ms")},
         }
         if cpu:

@@ -52,7 +52,8 @@ EXPORTS = [
     "imdb200_set_press_calc", "imdb200_invalidate_nblist", "imdb200_set_eta", "imdb200_set_temperature",
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
-    "imdb200_read_pot_table", "imdb200_free_pot_table",
+    "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local",
 ]
 
 _lib = None
@@ -100,6 +101,17 @@ def load_library():
     L.imdb200_free_pot_table.argtypes = [C.POINTER(PotTable)]
     L.imdb200_comm_unique_id.argtypes = [vp]
     L.imdb200_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    i3 = C.POINTER(C.c_int)
+    L.imdb200_calc_cpu_dim.argtypes = [C.c_int, i3]
+    L.imdb200_calc_cpu_dim.restype = None
+    L.imdb200_cart_rank.argtypes = [i3, i3]
+    L.imdb200_cart_coords.argtypes = [C.c_int, i3, i3]
+    L.imdb200_cart_coords.restype = None
+    L.imdb200_halo_peers.argtypes = [i3, i3, i3, i3, i3]
+    L.imdb200_halo_peers.restype = None
+    L.imdb200_send_forces.argtypes = [vp, vp, C.c_int, C.c_long]
+    L.imdb200_nghost_local.restype = C.c_long
+    L.imdb200_nghost_local.argtypes = [vp]
     _lib = L
     return L
 
@@ -127,6 +139,42 @@ def read_pot_table(path, ncols, radial, ntypes, default_format=2):
 
 def kernel_launches():
     return int(load_library().imdb200_kernel_launches())
+
+
+# ---- process grid helpers (host-side C, no GPU needed) -----------------------------------------------
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def calc_cpu_dim(num_cpus, cpu_dim=(0, 0, 0)):
+    """calc_cpu_dim (src/imd_geom_mpi_3d.c:201-266)."""
+    cd = _i3(cpu_dim)
+    load_library().imdb200_calc_cpu_dim(int(num_cpus), cd)
+    return tuple(cd)
+
+
+def cart_coords(rank, cpu_dim):
+    out = _i3((0, 0, 0))
+    load_library().imdb200_cart_coords(int(rank), _i3(cpu_dim), out)
+    return tuple(out)
+
+
+def cart_rank(coord, cpu_dim):
+    return int(load_library().imdb200_cart_rank(_i3(coord), _i3(cpu_dim)))
+
+
+def halo_peers(cpu_dim, my_coord, pbc=(1, 1, 1)):
+    """26 neighbour ranks + image shift codes (setup_mpi_topology, src/imd_geom_mpi_3d.c:57-88)."""
+    peer = (C.c_int * 27)(); code = (C.c_int * 27)()
+    load_library().imdb200_halo_peers(_i3(cpu_dim), _i3(my_coord), _i3(pbc), peer, code)
+    return list(peer), list(code)
+
+
+def comm_unique_id():
+    """rank 0: a fresh ncclUniqueId (128 bytes) to hand to every rank's IMDB200.comm_init."""
+    buf = C.create_string_buffer(128)
+    _chk(load_library().imdb200_comm_unique_id(buf))
+    return buf.raw
 
 
 class IMDB200:
@@ -185,6 +233,19 @@ class IMDB200:
             self._tabs += [te, tr]
         _chk(self.L.imdb200_set_potentials(self.h, C.byref(tp), C.byref(te) if eam else None,
                                            C.byref(tr) if eam else None))
+
+    def comm_init(self, unique_id, rank, nranks):
+        """Join the NCCL communicator of the process grid (one process per GPU); see imdb200_comm_init."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _chk(self.L.imdb200_comm_init(self.h, buf, int(rank), int(nranks)))
+
+    def send_forces(self, dev_ptr, ncomp, stride):
+        """send_forces analogue on a caller-owned device field (see imdb200_send_forces)."""
+        _chk(self.L.imdb200_send_forces(self.h, C.c_void_p(int(dev_ptr)), int(ncomp), int(stride)))
+
+    @property
+    def nghost(self):
+        return int(self.L.imdb200_nghost_local(self.h))
 
     def set_atoms(self, nummer, sorte, masse, ort, impuls=None, vsorte=None):
         a = [np.ascontiguousarray(nummer, np.int32), np.ascontiguousarray(sorte, np.int32),

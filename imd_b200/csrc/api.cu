@@ -79,7 +79,9 @@ int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
   CUDA_TRY(cudaMalloc(&s->d_scal, SC_COUNT * sizeof(double)));
   CUDA_TRY(cudaMemset(s->d_scal, 0, SC_COUNT * sizeof(double)));
   CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &s->eta, sizeof(double), cudaMemcpyHostToDevice));
+  s->d_glob = s->d_scal;            // one rank: the local block is the global one
   CUDA_TRY(cudaMallocHost(&s->h_scal, SC_COUNT * sizeof(double)));
+  memset(s->h_scal, 0, SC_COUNT * sizeof(double));
   CUDA_TRY(cudaMalloc(&s->d_flags, FL_COUNT * sizeof(int)));
   CUDA_TRY(cudaMemset(s->d_flags, 0, FL_COUNT * sizeof(int)));
   CUDA_TRY(cudaMallocHost(&s->h_flags, FL_COUNT * sizeof(int)));
@@ -91,12 +93,14 @@ int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
 void imdb200_destroy(imdb200_sim *s)
 {
   if (!s) return;
+  cudaSetDevice(s->cfg.device);
   cudaStreamSynchronize(s->stream);
   tables_free(s);
-  void *ptrs[] = {s->posdf, s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF, s->nblpos,
-                  s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start, s->cell_fill,
-                  s->cell_code, s->gcells, s->gcount, s->gstart, s->gsrc, s->scan_tmp, s->nbl, s->nnb, s->restr,
-                  s->d_scal, s->d_partial, s->d_flags};
+  comm_free(s);
+  void *ptrs[] = {s->posdf, s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF,
+                  s->nblpos, s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start,
+                  s->cell_fill, s->cell_code, s->gsrc, s->ghost_num, s->ghost_raw, s->scan_tmp, s->nbl, s->nnb,
+                  s->restr, s->d_scal, s->d_partial, s->d_flags, s->xfer};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->h_flags) cudaFreeHost(s->h_flags);
@@ -144,34 +148,66 @@ static int ensure_partials(imdb200_sim *s)
   return 0;
 }
 
+// ---- host <-> device transfer of atom arrays: raw user arrays are copied as they are and (un)packed on
+// the device, so the host side does no per-atom work and pinned user buffers are copied at full speed ------
+static int ensure_xfer(imdb200_sim *s, size_t bytes)
+{
+  if (bytes <= s->xfer_bytes) return 0;
+  if (s->xfer) cudaFree(s->xfer);
+  s->xfer = nullptr; s->xfer_bytes = 0;
+  CUDA_TRY(cudaMalloc(&s->xfer, bytes));
+  s->xfer_bytes = bytes;
+  return 0;
+}
+
+__global__ void k_pack_atoms(long n, const double *ort, const double *impuls, const double *masse, const int *sorte,
+                             const int *vsorte, int ntypes, double4 *pos, double4 *mom, double4 *frc, int *flags)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int so = sorte[i], vs = vsorte ? vsorte[i] : so;
+  if (so < 0 || so >= ntypes) atomicExch(&flags[FL_BADTYPE], 1);
+  pos[i] = make_double4(ort[3 * i], ort[3 * i + 1], ort[3 * i + 2], pack_types(so, vs));
+  mom[i] = impuls ? make_double4(impuls[3 * i], impuls[3 * i + 1], impuls[3 * i + 2], masse[i])
+                  : make_double4(0.0, 0.0, 0.0, masse[i]);
+  frc[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+}
+
 int imdb200_set_atoms(imdb200_sim *s, long n, const int *nummer, const int *sorte, const int *vsorte,
                       const double *masse, const double *ort, const double *impuls)
 {
   if (!s || n <= 0 || !nummer || !sorte || !masse || !ort) return imdb_fail(IMDB200_ERR_ARG, "bad atom arrays");
   if (!s->have_tabs) return imdb_fail(IMDB200_ERR_ARG, "call imdb200_set_potentials before imdb200_set_atoms");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
-  if (s->nranks > 1) return imdb_fail(IMDB200_ERR_ARG, "multi-rank set_atoms goes through imdb200_comm_init first");
+  if (s->nranks > 1 && !s->nccl_comm) return imdb_fail(IMDB200_ERR_COMM, "cpu_dim has %d ranks: call imdb200_comm_init before imdb200_set_atoms", s->nranks);
+  cudaStream_t st = s->stream;
   s->n_own = 0;
   TRY(cells_ensure_capacity(s, n + n / 2 + 4096));
   TRY(ensure_partials(s));
-  std::vector<double4> hp(n), hm(n);
-  for (long i = 0; i < n; i++) {
-    if (sorte[i] < 0 || sorte[i] >= s->cfg.ntypes) return imdb_fail(IMDB200_ERR_ARG, "atom %ld has type %d outside 0..ntypes-1", i, sorte[i]);
-    int vs = vsorte ? vsorte[i] : sorte[i];
-    hp[i].x = ort[3 * i]; hp[i].y = ort[3 * i + 1]; hp[i].z = ort[3 * i + 2];
-    long long w = ((long long) vs << 32) | (unsigned int) sorte[i];
-    memcpy(&hp[i].w, &w, 8);
-    hm[i].x = impuls ? impuls[3 * i] : 0.0; hm[i].y = impuls ? impuls[3 * i + 1] : 0.0; hm[i].z = impuls ? impuls[3 * i + 2] : 0.0;
-    hm[i].w = masse[i];
-  }
-  CUDA_TRY(cudaMemcpy(s->pos, hp.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(s->mom, hm.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(s->nummer, nummer, n * sizeof(int), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemset(s->frc, 0, n * sizeof(double4)));
+  // staging layout: ort[3n] impuls[3n] masse[n] | sorte[n] vsorte[n]
+  TRY(ensure_xfer(s, (size_t) n * (7 * sizeof(double) + 2 * sizeof(int))));
+  double *d_ort = (double *) s->xfer, *d_imp = d_ort + 3 * n, *d_m = d_imp + 3 * n;
+  int *d_so = (int *) (d_m + n), *d_vs = d_so + n;
+  CUDA_TRY(cudaMemcpyAsync(d_ort, ort, 3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (impuls) CUDA_TRY(cudaMemcpyAsync(d_imp, impuls, 3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_m, masse, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_so, sorte, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (vsorte) CUDA_TRY(cudaMemcpyAsync(d_vs, vsorte, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s->nummer, nummer, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, FL_COUNT * sizeof(int), st));
+  k_pack_atoms<<<cdiv(n, 256), 256, 0, st>>>(n, d_ort, impuls ? d_imp : nullptr, d_m, d_so, vsorte ? d_vs : nullptr,
+                                             s->cfg.ntypes, s->pos, s->mom, s->frc, s->d_flags);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (s->h_flags[FL_BADTYPE]) return imdb_fail(IMDB200_ERR_ARG, "an atom has a type outside 0..ntypes-1");
   s->n_own = n;
-  s->nactive = 3 * (long long) n;   /* src/imd_generate.c:450-451 */
+  s->natoms_global = s->nranks > 1 ? 0 : n;     // multi-rank: counted after the first binning
+  s->need_filter = s->nranks > 1;               // keep only the atoms of this rank's domain
+  s->nactive = 3 * (long long) n;               /* src/imd_generate.c:450-451 */
   s->n_ghost = 0;
   s->have_valid_nbl = 0;
+  s->nbl_count = 0;
   if (s->lanes == 0) {
     int L = s->cfg.lanes_per_atom;
     if (L == 0) { L = 1; while (L < 32 && n * L < 400000) L *= 2; }
@@ -184,7 +220,8 @@ int imdb200_set_atoms(imdb200_sim *s, long n, const int *nummer, const int *sort
 // ---- the step loop ------------------------------------------------------------------------------------
 static int fetch_scalars(imdb200_sim *s)
 {
-  CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  TRY(comm_sync_scalars(s));     // MPI_Allreduce sites: every rank sees the sums over all domains
+  CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_glob, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   if (s->h_flags[FL_SHORT]) s->is_short = 1;
@@ -195,7 +232,7 @@ static int fetch_scalars(imdb200_sim *s)
 static int ready(imdb200_sim *s)
 {
   if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
-  if (!s->have_tabs || s->n_own <= 0) return imdb_fail(IMDB200_ERR_ARG, "potentials and atoms must be set first");
+  if (!s->have_tabs || (s->n_own <= 0 && s->nranks == 1)) return imdb_fail(IMDB200_ERR_ARG, "potentials and atoms must be set first");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
   return 0;
 }
@@ -203,10 +240,10 @@ static int ready(imdb200_sim *s)
 static int calc_forces_async(imdb200_sim *s)
 {
   if (!s->have_valid_nbl) TRY(cells_rebuild(s));       // fix_cells, send_cells, make_nblist (:304-317)
-  else TRY(cells_refresh_ghost_pos(s));                // send_cells(copy_cell,...) (:314)
+  else TRY(comm_ghost_pos(s));                         // send_cells(copy_cell,...) (:314)
   TRY(forces_pass1(s));
   if (s->tabs.have_eam) {
-    TRY(cells_refresh_ghost_dF(s));                    // send_cells(copy_dF,...) (:1115)
+    TRY(comm_ghost_dF(s));                             // send_cells(copy_dF,...) (:1115)
     TRY(forces_pass2(s));
   }
   return 0;
@@ -266,11 +303,11 @@ int imdb200_run(imdb200_sim *s, int nsteps)
   for (int k = 0; k < nsteps; k++) {
     const bool rebuild = !s->have_valid_nbl;
     cudaEventRecord(s->ev[0], s->stream);
-    if (rebuild) TRY(cells_rebuild(s)); else TRY(cells_refresh_ghost_pos(s));
+    if (rebuild) TRY(cells_rebuild(s)); else TRY(comm_ghost_pos(s));
     cudaEventRecord(s->ev[1], s->stream);
     TRY(forces_pass1(s));
     cudaEventRecord(s->ev[2], s->stream);
-    if (s->tabs.have_eam) { TRY(cells_refresh_ghost_dF(s)); TRY(forces_pass2(s)); }
+    if (s->tabs.have_eam) { TRY(comm_ghost_dF(s)); TRY(forces_pass2(s)); }
     cudaEventRecord(s->ev[3], s->stream);
     TRY(integrate_move(s));
     cudaEventRecord(s->ev[4], s->stream);
@@ -323,7 +360,8 @@ int imdb200_get_scalars(imdb200_sim *s, imdb200_scalars *o)
 {
   if (!s || !o) return imdb_fail(IMDB200_ERR_ARG, "null argument");
   memset(o, 0, sizeof(*o));
-  if (s->d_scal && s->n_own > 0) TRY(fetch_scalars(s));
+  // host-side only: the values fetched by the last calc_forces / move_atoms / check_nblist / run.  No device
+  // access and no communication, so a single rank may ask (the step calls themselves are collective).
   o->tot_pot_energy = s->h_scal[SC_EPOT];
   o->tot_kin_energy = s->h_scal[SC_EKIN];
   o->virial = s->h_scal[SC_VIRIAL];
@@ -331,7 +369,7 @@ int imdb200_get_scalars(imdb200_sim *s, imdb200_scalars *o)
   o->eta = s->eta;
   o->max_displacement2 = s->h_scal[SC_MAXD2];
   for (int d = 0; d < 6; d++) o->tot_presstens[d] = s->h_scal[SC_PXX + d];
-  o->natoms = s->n_own; o->nactive = s->nactive;
+  o->natoms = s->natoms_global ? s->natoms_global : s->n_own; o->nactive = s->nactive;
   o->nbl_len = s->nbl_len;
   o->have_valid_nbl = s->have_valid_nbl; o->nbl_count = s->nbl_count; o->is_short = s->is_short;
   for (int d = 0; d < 3; d++) { o->global_cell_dim[d] = s->geom.gdim[d]; o->cell_dim[d] = s->geom.cdim[d]; }
@@ -340,6 +378,40 @@ int imdb200_get_scalars(imdb200_sim *s, imdb200_scalars *o)
 }
 
 long imdb200_natoms_local(imdb200_sim *s) { return s ? s->n_own : 0; }
+long imdb200_nghost_local(imdb200_sim *s) { return s ? s->n_ghost : 0; }
+
+int imdb200_send_forces(imdb200_sim *s, double *dev_field, int ncomp, long stride)
+{
+  TRY(ready(s));
+  if (!dev_field || stride < s->n_own + s->n_ghost) return imdb_fail(IMDB200_ERR_ARG, "field must hold natoms_local + nghost_local entries per component");
+  if (!s->have_valid_nbl) return imdb_fail(IMDB200_ERR_ARG, "no buffer cells yet: call imdb200_calc_forces or imdb200_fix_cells first");
+  TRY(comm_reverse_add(s, dev_field, ncomp, stride));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// unpack kernels: device records -> the plain arrays of the C ABI
+__global__ void k_unpack3(const double4 *src, long n, double *v3, double *w)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = src[i];
+  if (v3) { v3[3 * i] = p.x; v3[3 * i + 1] = p.y; v3[3 * i + 2] = p.z; }
+  if (w) w[i] = p.w;
+}
+__global__ void k_unpack_types(const double4 *pos, long n, int *sorte, int *vsorte)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double w = pos[i].w;
+  sorte[i] = sorte_of(w); vsorte[i] = vsorte_of(w);
+}
+__global__ void k_unpack_soa(const double *src, long stride, int ncomp, long n, double *out)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < ncomp; c++) out[(size_t) ncomp * i + c] = src[c * stride + i];
+}
 
 long imdb200_get_atoms(imdb200_sim *s, int *nummer, int *sorte, int *vsorte, double *masse, double *ort,
                        double *impuls, double *kraft, double *poteng, double *rho, double *dF,
@@ -347,46 +419,36 @@ long imdb200_get_atoms(imdb200_sim *s, int *nummer, int *sorte, int *vsorte, dou
 {
   if (!s || s->n_own <= 0) return 0;
   cudaSetDevice(s->cfg.device);
-  cudaStreamSynchronize(s->stream);
   const long n = s->n_own;
-  std::vector<double4> h(n);
-  if (ort || sorte || vsorte) {
-    cudaMemcpy(h.data(), s->pos, n * sizeof(double4), cudaMemcpyDeviceToHost);
-    for (long i = 0; i < n; i++) {
-      if (ort) { ort[3 * i] = h[i].x; ort[3 * i + 1] = h[i].y; ort[3 * i + 2] = h[i].z; }
-      long long w; memcpy(&w, &h[i].w, 8);
-      if (sorte) sorte[i] = (int) (w & 0xffffffffLL);
-      if (vsorte) vsorte[i] = (int) (w >> 32);
-    }
+  cudaStream_t st = s->stream;
+  if (ensure_xfer(s, (size_t) n * 7 * sizeof(double))) return -1;
+  double *b3 = (double *) s->xfer, *b1 = b3 + 6 * n;     // up to 6 components + 1 scalar
+  const int nb = cdiv(n, 256);
+#define D2H(dst, src, bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)
+  if (ort) { k_unpack3<<<nb, 256, 0, st>>>(s->pos, n, b3, nullptr); g_kernel_launches++; D2H(ort, b3, 3 * n * sizeof(double)); }
+  if (sorte || vsorte) {
+    int *bi = (int *) b3;
+    k_unpack_types<<<nb, 256, 0, st>>>(s->pos, n, bi, bi + n); g_kernel_launches++;
+    if (sorte) D2H(sorte, bi, n * sizeof(int));
+    if (vsorte) D2H(vsorte, bi + n, n * sizeof(int));
   }
   if (impuls || masse) {
-    cudaMemcpy(h.data(), s->mom, n * sizeof(double4), cudaMemcpyDeviceToHost);
-    for (long i = 0; i < n; i++) {
-      if (impuls) { impuls[3 * i] = h[i].x; impuls[3 * i + 1] = h[i].y; impuls[3 * i + 2] = h[i].z; }
-      if (masse) masse[i] = h[i].w;
-    }
+    k_unpack3<<<nb, 256, 0, st>>>(s->mom, n, impuls ? b3 : nullptr, masse ? b1 : nullptr); g_kernel_launches++;
+    if (impuls) D2H(impuls, b3, 3 * n * sizeof(double));
+    if (masse) D2H(masse, b1, n * sizeof(double));
   }
   if (kraft || poteng) {
-    cudaMemcpy(h.data(), s->frc, n * sizeof(double4), cudaMemcpyDeviceToHost);
-    for (long i = 0; i < n; i++) {
-      if (kraft) { kraft[3 * i] = h[i].x; kraft[3 * i + 1] = h[i].y; kraft[3 * i + 2] = h[i].z; }
-      if (poteng) poteng[i] = h[i].w;
-    }
+    k_unpack3<<<nb, 256, 0, st>>>(s->frc, n, kraft ? b3 : nullptr, poteng ? b1 : nullptr); g_kernel_launches++;
+    if (kraft) D2H(kraft, b3, 3 * n * sizeof(double));
+    if (poteng) D2H(poteng, b1, n * sizeof(double));
   }
-  if (nummer) cudaMemcpy(nummer, s->nummer, n * sizeof(int), cudaMemcpyDeviceToHost);
-  if (rho) { if (s->tabs.have_eam) cudaMemcpy(rho, s->rho, n * sizeof(double), cudaMemcpyDeviceToHost); else memset(rho, 0, n * sizeof(double)); }
-  if (dF) { if (s->tabs.have_eam) cudaMemcpy(dF, s->dF, n * sizeof(double), cudaMemcpyDeviceToHost); else memset(dF, 0, n * sizeof(double)); }
-  if (presstens || nblpos) {
-    std::vector<double> t(6 * n);
-    if (presstens) {
-      for (int d = 0; d < 6; d++) cudaMemcpy(t.data() + d * n, s->presstens + d * s->cap_atoms, n * sizeof(double), cudaMemcpyDeviceToHost);
-      for (long i = 0; i < n; i++) for (int d = 0; d < 6; d++) presstens[6 * i + d] = t[d * n + i];
-    }
-    if (nblpos) {
-      for (int d = 0; d < 3; d++) cudaMemcpy(t.data() + d * n, s->nblpos + d * s->cap_atoms, n * sizeof(double), cudaMemcpyDeviceToHost);
-      for (long i = 0; i < n; i++) for (int d = 0; d < 3; d++) nblpos[3 * i + d] = t[d * n + i];
-    }
-  }
+  if (nummer) D2H(nummer, s->nummer, n * sizeof(int));
+  if (rho) { if (s->tabs.have_eam) D2H(rho, s->rho, n * sizeof(double)); else memset(rho, 0, n * sizeof(double)); }
+  if (dF) { if (s->tabs.have_eam) D2H(dF, s->dF, n * sizeof(double)); else memset(dF, 0, n * sizeof(double)); }
+  if (presstens) { k_unpack_soa<<<nb, 256, 0, st>>>(s->presstens, s->cap_atoms, 6, n, b3); g_kernel_launches++; D2H(presstens, b3, 6 * n * sizeof(double)); }
+  if (nblpos) { k_unpack_soa<<<nb, 256, 0, st>>>(s->nblpos, s->cap_atoms, 3, n, b3); g_kernel_launches++; D2H(nblpos, b3, 3 * n * sizeof(double)); }
+#undef D2H
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
   return n;
 }
 
@@ -398,11 +460,11 @@ long imdb200_get_nblist(imdb200_sim *s, int *ni, int *nj, signed char *shift3, l
   if (cap <= 0 || !ni) return (long) s->nbl_len;
   const long n = s->n_own, ntot = s->n_own + s->n_ghost;
   const int L = s->lanes;
-  std::vector<int> nnb(n), num(n), gsrc(s->n_ghost > 0 ? s->n_ghost : 1), cid(ntot), code(s->geom.nall + 1);
+  std::vector<int> nnb(n), num(n), gnum(s->n_ghost > 0 ? s->n_ghost : 1), cid(ntot), code(s->geom.nall + 1);
   std::vector<int> nbl((size_t) s->n_pad * s->max_nb);
   cudaMemcpy(nnb.data(), s->nnb, n * sizeof(int), cudaMemcpyDeviceToHost);
   cudaMemcpy(num.data(), s->nummer, n * sizeof(int), cudaMemcpyDeviceToHost);
-  if (s->n_ghost) cudaMemcpy(gsrc.data(), s->gsrc, s->n_ghost * sizeof(int), cudaMemcpyDeviceToHost);
+  if (s->n_ghost) cudaMemcpy(gnum.data(), s->ghost_num, s->n_ghost * sizeof(int), cudaMemcpyDeviceToHost);
   cudaMemcpy(cid.data(), s->cellid, ntot * sizeof(int), cudaMemcpyDeviceToHost);
   cudaMemcpy(code.data(), s->cell_code, s->geom.nall * sizeof(int), cudaMemcpyDeviceToHost);
   cudaMemcpy(nbl.data(), s->nbl, nbl.size() * sizeof(int), cudaMemcpyDeviceToHost);
@@ -411,7 +473,8 @@ long imdb200_get_nblist(imdb200_sim *s, int *ni, int *nj, signed char *shift3, l
     for (int m = 0; m < nnb[i]; m++) {
       int j = nbl[nbl_index(i, m, L, s->max_nb / L)];
       int sx = 0, sy = 0, sz = 0, jn;
-      if (j >= n) { int c = code[cid[j]]; sx = c % 3 - 1; sy = (c / 3) % 3 - 1; sz = c / 9 - 1; jn = num[gsrc[j - n]]; }
+      // image shift of j as this rank applies it (periodic wrap); 0 for images of a neighbour domain's atoms
+      if (j >= n) { int c = code[cid[j]]; sx = c % 3 - 1; sy = (c / 3) % 3 - 1; sz = c / 9 - 1; jn = gnum[j - n]; }
       else jn = num[j];
       if (cnt < cap) {
         ni[cnt] = num[i]; nj[cnt] = jn;
@@ -428,9 +491,5 @@ int imdb200_pair_int(imdb200_sim *s, int which, int col, long n, const double *r
   CUDA_TRY(cudaSetDevice(s->cfg.device));
   return tables_pair_int(s, which, col, n, r2, pot, grad);
 }
-
-int imdb200_comm_unique_id(void *id128) { (void) id128; return imdb_fail(IMDB200_ERR_COMM, "multi-GPU support not built yet"); }
-int imdb200_comm_init(imdb200_sim *s, const void *id128, int rank, int nranks)
-{ (void) s; (void) id128; (void) rank; (void) nranks; return imdb_fail(IMDB200_ERR_COMM, "multi-GPU support not built yet"); }
 
 } // extern "C"

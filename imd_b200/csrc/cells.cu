@@ -25,43 +25,6 @@ static void cross(const double u[3], const double v[3], double w[3])
 }
 static double dot(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-static int plan_ghost_cells(imdb200_sim *s)
-{
-  const Geom &g = s->geom;
-  std::vector<GhostCell> gc;
-  for (int i = 0; i < g.cdim[0]; i++)
-    for (int j = 0; j < g.cdim[1]; j++)
-      for (int k = 0; k < g.cdim[2]; k++) {
-        int c[3] = {i, j, k}, src[3], sh[3], ghost = 0, ok = 1;
-        for (int d = 0; d < 3; d++) {
-          src[d] = c[d]; sh[d] = 0;
-          if (c[d] == 0) { ghost = 1; src[d] = g.cdim[d] - 2; sh[d] = -1; }
-          else if (c[d] == g.cdim[d] - 1) { ghost = 1; src[d] = 1; sh[d] = +1; }
-          // a buffer cell beyond a non-periodic face stays empty (nq = -1, src/imd_geom_3d.c:944-949)
-          if (sh[d] != 0 && !g.pbc[d]) ok = 0;
-        }
-        if (!ghost || !ok) continue;
-        GhostCell x;
-        x.dst = (i * g.cdim[1] + j) * g.cdim[2] + k;
-        x.src = (src[0] * g.cdim[1] + src[1]) * g.cdim[2] + src[2];
-        x.code = (sh[0] + 1) + 3 * (sh[1] + 1) + 9 * (sh[2] + 1);
-        x.peer = -1;
-        gc.push_back(x);
-      }
-  if (s->gcells) cudaFree(s->gcells);
-  if (s->gcount) cudaFree(s->gcount);
-  if (s->gstart) cudaFree(s->gstart);
-  s->gcells = nullptr; s->gcount = nullptr; s->gstart = nullptr;
-  s->n_gcells = (int) gc.size();
-  if (s->n_gcells) {
-    CUDA_TRY(cudaMalloc(&s->gcells, gc.size() * sizeof(GhostCell)));
-    CUDA_TRY(cudaMemcpy(s->gcells, gc.data(), gc.size() * sizeof(GhostCell), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&s->gcount, (gc.size() + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&s->gstart, (gc.size() + 1) * sizeof(int)));
-  }
-  return 0;
-}
-
 // init_cells (src/imd_geom_3d.c:113-248): cell grid from cellsz and the box heights.
 static int init_cells(imdb200_sim *s)
 {
@@ -84,12 +47,12 @@ static int init_cells(imdb200_sim *s)
   }
   g.nall = g.cdim[0] * g.cdim[1] * g.cdim[2];
   if (s->cell_count) { cudaFree(s->cell_count); cudaFree(s->cell_start); cudaFree(s->cell_fill); cudaFree(s->cell_code); cudaFree(s->scan_tmp); }
-  CUDA_TRY(cudaMalloc(&s->cell_code, (g.nall + 1) * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&s->cell_count, (g.nall + 1) * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&s->cell_start, (g.nall + 1) * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&s->cell_fill, (g.nall + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->cell_code, (g.nall + NBIN_EXTRA) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->cell_count, (g.nall + NBIN_EXTRA) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->cell_start, (g.nall + NBIN_EXTRA) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->cell_fill, (g.nall + NBIN_EXTRA) * sizeof(int)));
   CUDA_TRY(cudaMalloc(&s->scan_tmp, (g.nall / 1024 + 1024) * sizeof(int)));
-  TRY(plan_ghost_cells(s));
+  TRY(comm_plan(s));
   s->have_valid_nbl = 0;
   return 0;
 }
@@ -141,7 +104,7 @@ int cells_ensure_capacity(imdb200_sim *s, long need)
   TRY(regrow(&s->nummer, n, cap)); TRY(regrow(&s->nummer_alt, 0, cap));
   TRY(regrow(&s->rho, n, cap)); TRY(regrow(&s->dF, n, cap));
   TRY(regrow(&s->cellid, n, cap)); TRY(regrow(&s->cellid_alt, 0, cap)); TRY(regrow(&s->perm, 0, cap));
-  TRY(regrow(&s->gsrc, 0, cap));
+  TRY(regrow(&s->gsrc, 0, cap)); TRY(regrow(&s->ghost_num, 0, cap)); TRY(regrow(&s->ghost_raw, 0, cap));
   // SoA blocks whose stride is the capacity: contents are rebuilt before use
   if (s->nblpos) cudaFree(s->nblpos);
   if (s->presstens) cudaFree(s->presstens);
@@ -221,7 +184,11 @@ __device__ __forceinline__ double sprod_exact(double x, double y, double z, cons
 
 // do_boundaries (src/imd_main_3d.c:1972-2059) + cell_coord (src/imd_geom_3d.c:1054-1074) +
 // local_cell_coord (src/imd_geom_mpi_3d.c:119-128), same operation order, no FMA.
-__global__ void k_wrap_bin(double4 *pos, long n, Geom g, int *cellid, int *cell_count, int *flags)
+// An atom whose cell belongs to another rank goes into one of the extra bins behind the cell grid:
+// nall + d for "leaves in direction d" (fix_cells, src/imd_fix_cells_3d.c:100-175: it is sent to that
+// neighbour), or nall + 27 when set_atoms handed us atoms of other domains (they are dropped).
+struct BinArgs { int cpu_dim[3], my_coord[3]; int filter; };
+__global__ void k_wrap_bin(double4 *pos, long n, Geom g, BinArgs b, int *cellid, int *cell_count, int *flags)
 {
   long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -236,18 +203,28 @@ __global__ void k_wrap_bin(double4 *pos, long n, Geom g, int *cellid, int *cell_
     }
   }
   pos[i] = p;
-  int c[3];
-  bool lost = false;
+  int c[3], dir = 13;
+  bool away = false, lost = false;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     int v = __double2int_rz(__dmul_rn((double) g.gdim[d], sprod_exact(p.x, p.y, p.z, g.tbox[d])));
     if (v >= g.gdim[d]) v = g.gdim[d] - 1; else if (v < 0) v = 0;
-    v = v - g.coff[d] + 1;
-    if (v < 1 || v > g.cdim[d] - 2) { lost = true; v = v < 1 ? 1 : g.cdim[d] - 2; }
+    const int per = g.cdim[d] - 2, owner = v / per, me = b.my_coord[d], np = b.cpu_dim[d];
+    if (owner != me) {
+      away = true;
+      const int stride = d == 0 ? 1 : (d == 1 ? 3 : 9);
+      if (owner == (me + 1) % np) dir += stride;
+      else if (owner == (me + np - 1) % np) dir -= stride;
+      else lost = true;                                     // "Atom jumped multiple CPUs" (:170)
+      v = 1;
+    } else v = v - g.coff[d] + 1;
     c[d] = v;
   }
-  if (lost) atomicAdd(&flags[FL_LOST], 1);
   int ci = (c[0] * g.cdim[1] + c[1]) * g.cdim[2] + c[2];
+  if (away) {
+    if (b.filter) ci = g.nall + 27;
+    else { ci = g.nall + dir; if (lost) atomicAdd(&flags[FL_LOST], 1); }
+  }
   cellid[i] = ci;
   atomicAdd(&cell_count[ci], 1);
 }
@@ -288,82 +265,6 @@ __global__ void k_gather(const int *perm, long n, const double4 *pos, const doub
 }
 
 // =====================================================================================================
-// ghost images (buffer cells)
-// =====================================================================================================
-__global__ void k_ghost_count(const GhostCell *gc, int ng, const int *cell_count, int *gcount)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ng) gcount[i] = cell_count[gc[i].src];
-}
-
-// one warp per ghost cell: record the source atom of every image and publish the cell's range
-__global__ void k_ghost_fill(const GhostCell *gc, int ng, const int *gstart, const int *gcount, long n_own,
-                             int *cell_start, int *cell_count, int *cell_code, int *gsrc)
-{
-  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= ng) return;
-  GhostCell x = gc[w];
-  int cnt = gcount[w], st = gstart[w], s0 = cell_start[x.src];
-  for (int t = lane; t < cnt; t += 32) gsrc[st + t] = s0 + t;
-  if (lane == 0) { cell_start[x.dst] = (int) n_own + st; cell_count[x.dst] = cnt; cell_code[x.dst] = x.code; }
-}
-
-// copy_cell (src/imd_comm_force_3d.c:726-778) for all three sweeps at once.  The reference adds
-// the box vectors stage by stage (up/down, then north/south, then east/west; :268-395), so the
-// image position is ((x + sz*box_z) + sy*box_y) + sx*box_x, each add rounded.
-__device__ __forceinline__ double4 image_pos(double4 p, int code, const Geom &g)
-{
-  int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
-  if (sz) { double f = (double) sz; p.x = __dadd_rn(p.x, f * g.box[2][0]); p.y = __dadd_rn(p.y, f * g.box[2][1]); p.z = __dadd_rn(p.z, f * g.box[2][2]); }
-  if (sy) { double f = (double) sy; p.x = __dadd_rn(p.x, f * g.box[1][0]); p.y = __dadd_rn(p.y, f * g.box[1][1]); p.z = __dadd_rn(p.z, f * g.box[1][2]); }
-  if (sx) { double f = (double) sx; p.x = __dadd_rn(p.x, f * g.box[0][0]); p.y = __dadd_rn(p.y, f * g.box[0][1]); p.z = __dadd_rn(p.z, f * g.box[0][2]); }
-  return p;
-}
-
-__global__ void k_ghost_pos(double4 *pos, long n_own, long n_ghost, const int *gsrc, const int *cellid_g,
-                            const int *cell_code, Geom g)
-{
-  long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
-  if (t >= n_ghost) return;
-  pos[n_own + t] = image_pos(pos[gsrc[t]], cell_code[cellid_g[t]], g);
-}
-
-__global__ void k_ghost_cellid(const GhostCell *gc, int ng, const int *gstart, const int *gcount, int *cellid_g)
-{
-  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= ng) return;
-  int cnt = gcount[w], st = gstart[w], dst = gc[w].dst;
-  for (int t = lane; t < cnt; t += 32) cellid_g[st + t] = dst;
-}
-
-__global__ void k_ghost_dF(double *dF, double4 *posdf, const double4 *pos, long n_own, long n_ghost, const int *gsrc)
-{
-  long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
-  if (t >= n_ghost) return;
-  const double d = dF[gsrc[t]];
-  dF[n_own + t] = d;
-  if (posdf) { const double4 p = pos[n_own + t]; posdf[n_own + t] = make_double4(p.x, p.y, p.z, d); }
-}
-
-int cells_refresh_ghost_pos(imdb200_sim *s)
-{
-  if (s->n_ghost == 0) return 0;
-  k_ghost_pos<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->pos, s->n_own, s->n_ghost, s->gsrc,
-                                                              s->cellid + s->n_own, s->cell_code, s->geom);
-  LAUNCH_CHECK();
-  return 0;
-}
-
-int cells_refresh_ghost_dF(imdb200_sim *s)
-{
-  if (s->n_ghost == 0) return 0;
-  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->tabs.ntypes == 1 ? s->posdf : nullptr, s->pos, s->n_own,
-                                                             s->n_ghost, s->gsrc);
-  LAUNCH_CHECK();
-  return 0;
-}
-
-// =====================================================================================================
 // make_nblist
 // =====================================================================================================
 // One thread per owned atom scans the 27 cells around its own.  The list is FULL (both directions
@@ -381,7 +282,7 @@ int cells_refresh_ghost_dF(imdb200_sim *s)
 __global__ void __launch_bounds__(128)
 k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__restrict__ cellid,
             const int *__restrict__ cell_start, const int *__restrict__ cell_count,
-            const int *__restrict__ cell_code, const int *__restrict__ gsrc,
+            const int *__restrict__ cell_code, const int *__restrict__ gsrc, const double4 *__restrict__ ghost_raw,
             int *__restrict__ nbl, int *__restrict__ nnb, int max_nb, int L,
             int *flags, int count_only)
 {
@@ -407,7 +308,8 @@ k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__re
           const double4 me = image_pos(xi, inv, g);
           for (int t = 0; t < nj; t++) {
             const int j = j0 + t;
-            const double4 xj = pos[gsrc[j - n_own]];
+            const int src = gsrc[j - n_own];              // the owner's unshifted copy: ours, or as received
+            const double4 xj = src >= 0 ? pos[src] : ghost_raw[j - n_own];
             const double r2 = r2_exact(__dsub_rn(me.x, xj.x), __dsub_rn(me.y, xj.y), __dsub_rn(me.z, xj.z));
             if (r2 < g.cellsz) {
               if (!count_only && cnt < max_nb) nbl[nbl_index(i, cnt, L, max_nb / L)] = j;
@@ -471,21 +373,22 @@ static int read_flags(imdb200_sim *s)
   return 0;
 }
 
-// fix_cells + send_cells + make_nblist, i.e. the `0 == have_valid_nbl` branch of calc_forces
-// (src/imd_forces_nbl.c:304-317)
-int cells_rebuild(imdb200_sim *s)
+// wrap, bin and sort the first n atoms into cell order; atoms of other domains end up behind the
+// owned ones, grouped by leave direction.  h_extra receives cell_start[nall] (= atoms that stay) and
+// the 28 extra bin counts.
+static int bin_and_sort(imdb200_sim *s, long n, int filter, int *h_extra)
 {
-  const long n = s->n_own;
   const Geom &g = s->geom;
   cudaStream_t st = s->stream;
-  if (n <= 0) return imdb_fail(IMDB200_ERR_ARG, "no atoms");
-  // ---- fix_cells: wrap into the box, bin, sort into cell order ------------------------------------
-  CUDA_TRY(cudaMemsetAsync(s->cell_count, 0, (g.nall + 1) * sizeof(int), st));
-  CUDA_TRY(cudaMemsetAsync(s->cell_fill, 0, (g.nall + 1) * sizeof(int), st));
-  CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, FL_COUNT * sizeof(int), st));
+  const int nbins = g.nall + 28;
+  CUDA_TRY(cudaMemsetAsync(s->cell_count, 0, (g.nall + NBIN_EXTRA) * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(s->cell_fill, 0, (g.nall + NBIN_EXTRA) * sizeof(int), st));
+  BinArgs b;
+  for (int d = 0; d < 3; d++) { b.cpu_dim[d] = s->cfg.cpu_dim[d]; b.my_coord[d] = s->cfg.my_coord[d]; }
+  b.filter = filter;
   const int nb = cdiv(n, 256);
-  k_wrap_bin<<<nb, 256, 0, st>>>(s->pos, n, g, s->cellid, s->cell_count, s->d_flags); LAUNCH_CHECK();
-  TRY(scan_exclusive(s, s->cell_count, s->cell_start, g.nall, nullptr));
+  k_wrap_bin<<<nb, 256, 0, st>>>(s->pos, n, g, b, s->cellid, s->cell_count, s->d_flags); LAUNCH_CHECK();
+  TRY(scan_exclusive(s, s->cell_count, s->cell_start, nbins, nullptr));
   k_scatter<<<nb, 256, 0, st>>>(s->cellid, n, s->cell_start, s->cell_fill, s->perm); LAUNCH_CHECK();
   k_sort_cells<<<cdiv(g.nall, 128), 128, 0, st>>>(s->cell_start, s->cell_count, s->perm, s->nummer, g.nall); LAUNCH_CHECK();
   k_gather<<<nb, 256, 0, st>>>(s->perm, n, s->pos, s->mom, s->nummer, s->cellid, s->pos_alt, s->mom_alt,
@@ -495,22 +398,46 @@ int cells_rebuild(imdb200_sim *s)
   { double4 *t = s->mom; s->mom = s->mom_alt; s->mom_alt = t; }
   { int *t = s->nummer; s->nummer = s->nummer_alt; s->nummer_alt = t; }
   { int *t = s->cellid; s->cellid = s->cellid_alt; s->cellid_alt = t; }
-  // ---- buffer cells: images of the boundary cells ---------------------------------------------------
-  CUDA_TRY(cudaMemsetAsync(s->cell_code, 0, (g.nall + 1) * sizeof(int), st));
-  s->n_ghost = 0;
-  if (s->n_gcells) {
-    k_ghost_count<<<cdiv(s->n_gcells, 256), 256, 0, st>>>(s->gcells, s->n_gcells, s->cell_count, s->gcount); LAUNCH_CHECK();
-    TRY(scan_exclusive(s, s->gcount, s->gstart, s->n_gcells, &s->d_flags[FL_NGHOST]));
-    TRY(read_flags(s));
-    if (s->h_flags[FL_LOST]) return imdb_fail(IMDB200_ERR_CELLS, "%d atoms left the local domain (atom migration between ranks failed)", s->h_flags[FL_LOST]);
-    s->n_ghost = s->h_flags[FL_NGHOST];
-    TRY(cells_ensure_capacity(s, n + s->n_ghost));
-    const int nbw = cdiv((long) s->n_gcells * 32, 256);
-    k_ghost_fill<<<nbw, 256, 0, st>>>(s->gcells, s->n_gcells, s->gstart, s->gcount, n, s->cell_start, s->cell_count,
-                                      s->cell_code, s->gsrc); LAUNCH_CHECK();
-    k_ghost_cellid<<<nbw, 256, 0, st>>>(s->gcells, s->n_gcells, s->gstart, s->gcount, s->cellid + n); LAUNCH_CHECK();
-    TRY(cells_refresh_ghost_pos(s));
-  }
+  CUDA_TRY(cudaMemcpyAsync(h_extra, s->cell_start + g.nall, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_extra + 1, s->cell_count + g.nall, 28 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (s->h_flags[FL_LOST]) return imdb_fail(IMDB200_ERR_CELLS, "Atom jumped multiple CPUs (%d atoms)", s->h_flags[FL_LOST]);
+  return 0;
+}
+
+// fix_cells + send_cells + make_nblist, i.e. the `0 == have_valid_nbl` branch of calc_forces
+// (src/imd_forces_nbl.c:304-317)
+int cells_rebuild(imdb200_sim *s)
+{
+  const Geom &g = s->geom;
+  cudaStream_t st = s->stream;
+  if (s->n_own <= 0 && s->nranks == 1) return imdb_fail(IMDB200_ERR_ARG, "no atoms");
+  // ---- fix_cells: wrap into the box, bin, sort into cell order, hand atoms over to their new owners ----
+  CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, FL_COUNT * sizeof(int), st));
+  int *h_extra = s->h_starts;                 // pinned scratch: [0] atoms that stay, [1..28] extra bins
+  TRY(bin_and_sort(s, s->n_own, s->need_filter, h_extra));
+  long n = h_extra[0];
+  s->need_filter = 0;
+  if (s->nranks > 1) {
+    long n_new = n;
+    TRY(comm_migrate(s, h_extra + 1, n, &n_new));             // send_atoms (src/imd_fix_cells_3d.c:331-437)
+    if (n_new != n) {                                           // arrivals were appended behind the sorted atoms
+      TRY(bin_and_sort(s, n_new, 0, h_extra));
+      if (h_extra[0] != n_new) return imdb_fail(IMDB200_ERR_CELLS, "received atoms that are not in this domain");
+      n = n_new;
+    }
+    long long tot = 0;
+    TRY(comm_allgather_ll(s, n, &tot));
+    if (s->natoms_global == 0) s->natoms_global = tot;
+    else if (tot != s->natoms_global) return imdb_fail(IMDB200_ERR_CELLS, "atom count changed from %lld to %lld in fix_cells", s->natoms_global, tot);
+    s->nactive = 3 * s->natoms_global;
+  } else s->natoms_global = n;
+  s->n_own = n;
+  // ---- buffer cells: images of the boundary cells, ours or a neighbour's -----------------------------
+  TRY(comm_setup_ghosts(s));
+  TRY(comm_ghost_pos(s));
+  const int nb = cdiv(n > 0 ? n : 1, 256);
   // ---- make_nblist -------------------------------------------------------------------------------------
   const int L = s->lanes;
   for (int attempt = 0; attempt < 3; attempt++) {
@@ -518,7 +445,7 @@ int cells_rebuild(imdb200_sim *s)
       // size the table from an exact count (estimate_nblist_size, src/imd_forces_nbl.c:74-128)
       CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
       k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
-                                                s->gsrc, nullptr, nullptr, 0, L, s->d_flags, 1); LAUNCH_CHECK();
+                                                s->gsrc, s->ghost_raw, nullptr, nullptr, 0, L, s->d_flags, 1); LAUNCH_CHECK();
       TRY(read_flags(s));
       int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 2;
       TRY(alloc_nbl(s, want > 8 ? want : 8));
@@ -526,7 +453,7 @@ int cells_rebuild(imdb200_sim *s)
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_NBL_OVERFLOW], 0, sizeof(int), st));
     k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
-                                              s->gsrc, s->nbl, s->nnb, s->max_nb, L, s->d_flags, 0); LAUNCH_CHECK();
+                                              s->gsrc, s->ghost_raw, s->nbl, s->nnb, s->max_nb, L, s->d_flags, 0); LAUNCH_CHECK();
     TRY(read_flags(s));
     if (!s->h_flags[FL_NBL_OVERFLOW]) break;
     if (attempt == 2) return imdb_fail(IMDB200_ERR_NBL, "neighbor table full - increase nbl_size");
@@ -534,7 +461,7 @@ int cells_rebuild(imdb200_sim *s)
   // total list length (last_nbl_len, src/imd_forces_nbl.c:270)
   unsigned long long *d_len = (unsigned long long *) (s->d_scal + SC_COUNT - 1);
   CUDA_TRY(cudaMemsetAsync(d_len, 0, sizeof(unsigned long long), st));
-  k_sum_int<<<cdiv(n, 256), 256, 0, st>>>(s->nnb, n, d_len); LAUNCH_CHECK();
+  k_sum_int<<<nb, 256, 0, st>>>(s->nnb, n, d_len); LAUNCH_CHECK();
   // NBL_POS <- ORT (src/imd_forces_nbl.c:142-154)
   k_save_nblpos<<<nb, 256, 0, st>>>(s->pos, n, s->cap_atoms, s->nblpos); LAUNCH_CHECK();
   unsigned long long len = 0;

@@ -93,10 +93,14 @@ __global__ void k_check_nblist(const double4 *pos, const double *nblpos, long ns
 }
 
 // tot_kin_energy and the Nose-Hoover variable (src/imd_integrate.c:1103, 1140-1141)
-__global__ void k_nvt_finish(double *scal, double dt, double nactive, double temperature, double isq_tau_eta)
+// scal: this rank's block, glob: the block summed over ranks (the same pointer on one GPU).  The local
+// share of tot_kin_energy is linear in E_kin_1/2, so it is formed here and summed with the rest; eta is
+// advanced from the GLOBAL E_kin_2 and comes out identical on every rank.
+__global__ void k_nvt_finish(double *scal, const double *glob, double dt, double nactive, double temperature,
+                             double isq_tau_eta)
 {
-  const double e1 = scal[SC_EKIN1], e2 = scal[SC_EKIN2];
-  scal[SC_EKIN] = (e1 + e2) / 4.0;
+  scal[SC_EKIN] = (scal[SC_EKIN1] + scal[SC_EKIN2]) / 4.0;
+  const double e2 = glob[SC_EKIN2];
   const double ttt = nactive * temperature;
   scal[SC_ETA] += dt * (e2 / ttt - 1.0) * isq_tau_eta;
 }
@@ -134,8 +138,8 @@ int integrate_move(imdb200_sim *s)
   if (nvt) {
     const int slots[2] = {SC_EKIN1, SC_EKIN2};
     TRY(reduce_finish(s, nb, 2, slots, 0));
-    // every rank would first all-reduce E_kin_1/2 here (src/imd_integrate.c:1104-1130)
-    k_nvt_finish<<<1, 1, 0, s->stream>>>(s->d_scal, s->cfg.timestep, (double) s->nactive,
+    TRY(comm_sync_scalars(s));    // MPI_Allreduce of E_kin_1/2 (src/imd_integrate.c:1104-1130)
+    k_nvt_finish<<<1, 1, 0, s->stream>>>(s->d_scal, s->d_glob, s->cfg.timestep, (double) s->nactive,
                                          s->cfg.temperature, s->cfg.isq_tau_eta);
     LAUNCH_CHECK();
   } else {

@@ -67,7 +67,20 @@ struct Geom {
 
 // one buffer (ghost) cell of the local grid and where its content comes from
 struct GhostCell { int dst, src; int code; int peer; };
-// code = (sx+1) + 3*(sy+1) + 9*(sz+1), s in {-1,0,1}: image shift in box units
+// code = (sx+1) + 3*(sy+1) + 9*(sz+1), s in {-1,0,1}: image shift in box units; src/peer: the source
+// cell on this rank (peer == own rank) or -1 when the content arrives from another rank
+
+// One of the 26 directions d = (sx+1) + 3*(sy+1) + 9*(sz+1) of the halo.  Receive side: the buffer cells
+// on face/edge/corner d are filled from rank `peer` (possibly this rank: periodic wrap on one GPU).
+// Send side: the owned cells adjacent to face d go to `peer`, where they fill direction 26-d.
+struct DirPlan {
+  int peer;                       // -1: no neighbour (non-periodic edge)
+  int ncells;                     // cells in the region (same count on both sides)
+  int gcell_off;                  // first entry in gcells (receive cells), direction-major
+  int scell_off;                  // first entry in scells (send cells), -1 if peer is self or none
+  int recv_off, recv_cnt;         // ghost atoms [n_own+recv_off, +recv_cnt) after a rebuild
+  int send_off, send_cnt;         // slice of send_idx / the send buffers
+};
 
 struct imdb200_sim {
   imdb200_config cfg;
@@ -80,25 +93,40 @@ struct imdb200_sim {
   cudaStream_t stream; int own_stream;
   // atoms
   long n_own, n_ghost, cap_atoms; // capacity of the per-atom arrays
+  long long natoms_global;        // sum of n_own over all ranks
+  int need_filter;                // set_atoms was given atoms of other domains too: drop them at the first binning
   double4 *pos, *pos_alt, *mom, *mom_alt, *frc;
   int *nummer, *nummer_alt;
   double *rho, *dF, *nblpos, *presstens; // presstens [6][cap] SoA
   double4 *posdf;                 // single-species EAM: x,y,z + 2F'(rho) in .w, the pass-2 gather record
   int *cellid, *cellid_alt, *perm;
-  // cells
+  void *xfer; size_t xfer_bytes;  // staging for set_atoms / get_atoms
+  // cells; cell_count/cell_start have nall + NBIN_EXTRA entries: 27 bins for atoms leaving in direction d
+  // and one for atoms of foreign domains dropped by the first binning
   int *cell_count, *cell_start, *cell_fill, *cell_code;
   GhostCell *gcells; int n_gcells;
   int *gcount, *gstart;
-  int *gsrc; unsigned char *gcode;      // per ghost atom
+  int *gsrc;                      // per ghost atom: source atom on this rank, -1 = arrives from a peer
+  int *ghost_num;                 // per ghost atom: NUMMER (test hook / diagnostics)
+  double4 *ghost_raw;             // per ghost atom: unshifted position as the owner holds it
   int *scan_tmp;
+  // halo plan (comm.cu)
+  DirPlan dir[27];
+  int *scells; int n_scells;      // owned cells to send, direction-major
+  int *scount, *sstart;
+  int *send_idx; long n_send, cap_send;
+  double4 *sendbuf4; double *sendbuf1; int *sendbufi;
+  int *h_starts;                  // pinned: gstart/sstart read back at a rebuild
   // neighbour list
   int *nbl, *nnb; long nbl_cap_rows; int max_nb, lanes; long n_pad;
   int have_valid_nbl, nbl_count; long long nbl_len;
   // restrictions / deformation tables per virtual type
   double *restr; int n_restr;
   // scalars
-  double *d_scal;      // device scalar block, see SC_*
-  double *h_scal;      // pinned mirror
+  double *d_scal;      // device scalar block of this rank, see SC_*
+  double *d_glob;      // the same summed over ranks (== d_scal on one rank)
+  double *d_all;       // [nranks][SC_COUNT] all-gather target
+  double *h_scal;      // pinned mirror of d_glob
   double *d_partial;   // per-block partial sums
   int *d_flags, *h_flags;
   int press_calc, is_short;
@@ -111,9 +139,11 @@ struct imdb200_sim {
   void *nccl_comm; int rank, nranks;
 };
 
+#define NBIN_EXTRA 29   // 27 leave directions + 1 dropped + 1 spare (exclusive-scan total)
+
 enum { SC_EPOT = 0, SC_VIRIAL, SC_EKIN, SC_EKIN2, SC_MAXD2, SC_ETA, SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX,
        SC_PXY, SC_EKIN1, SC_COUNT = 16 };
-enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_COUNT = 8 };
+enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_NSEND, FL_BADTYPE, FL_COUNT = 8 };
 
 // ---- error handling --------------------------------------------------------------------------------
 int imdb_fail(int code, const char *fmt, ...);
@@ -142,9 +172,17 @@ int tables_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2
 int geom_make_box(imdb200_sim *s);           // make_box + init_cells when needed
 int cells_ensure_capacity(imdb200_sim *s, long n_atoms_total);
 int cells_rebuild(imdb200_sim *s);            // fix_cells + ghost images + make_nblist
-int cells_refresh_ghost_pos(imdb200_sim *s);  // send_cells(copy_cell...)
-int cells_refresh_ghost_dF(imdb200_sim *s);   // send_cells(copy_dF...)
 int scan_exclusive(imdb200_sim *s, const int *in, int *out, int n, int *total_dev);
+
+int comm_plan(imdb200_sim *s);                // halo plan for the current cell grid (after init_cells)
+void comm_free(imdb200_sim *s);
+int comm_migrate(imdb200_sim *s, const int *h_counts, long n_stay, long *n_new);  // send_atoms (fix_cells)
+int comm_setup_ghosts(imdb200_sim *s);        // per-cell counts, ghost ranges, send lists (at a rebuild)
+int comm_ghost_pos(imdb200_sim *s);           // send_cells(copy_cell,pack_cell,unpack_cell)
+int comm_ghost_dF(imdb200_sim *s);            // send_cells(copy_dF,pack_dF,unpack_dF)
+int comm_reverse_add(imdb200_sim *s, double *field, int ncomp, long stride);  // send_forces(add_*,...)
+int comm_sync_scalars(imdb200_sim *s);        // the MPI_Allreduce sites
+int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
 
 int forces_pass1(imdb200_sim *s);             // pair + rho + embedding
 int forces_pass2(imdb200_sim *s);             // EAM force pass
@@ -196,6 +234,18 @@ __device__ __forceinline__ void tab_index_fast(double r2, double nbegin_istep, d
 // val = c0 + chi*(c1 + chi*c2); grad = G*(c1 + 2*chi*c2) with G = 2*invstep
 __device__ __forceinline__ double tab_val(double2 ab, double c2, double chi) { return fma(chi, fma(chi, c2, ab.y), ab.x); }
 __device__ __forceinline__ double tab_grad(double2 ab, double c2, double chi, double G) { return G * fma(chi + chi, c2, ab.y); }
+
+// copy_cell (src/imd_comm_force_3d.c:726-778) for all three sweeps at once.  The reference adds
+// the box vectors stage by stage (up/down, then north/south, then east/west; :268-395), so the
+// image position is ((x + sz*box_z) + sy*box_y) + sx*box_x, each add rounded.
+__device__ __forceinline__ double4 image_pos(double4 p, int code, const Geom &g)
+{
+  int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
+  if (sz) { double f = (double) sz; p.x = __dadd_rn(p.x, f * g.box[2][0]); p.y = __dadd_rn(p.y, f * g.box[2][1]); p.z = __dadd_rn(p.z, f * g.box[2][2]); }
+  if (sy) { double f = (double) sy; p.x = __dadd_rn(p.x, f * g.box[1][0]); p.y = __dadd_rn(p.y, f * g.box[1][1]); p.z = __dadd_rn(p.z, f * g.box[1][2]); }
+  if (sx) { double f = (double) sx; p.x = __dadd_rn(p.x, f * g.box[0][0]); p.y = __dadd_rn(p.y, f * g.box[0][1]); p.z = __dadd_rn(p.z, f * g.box[0][2]); }
+  return p;
+}
 
 __device__ __forceinline__ double2 ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 

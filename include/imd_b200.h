@@ -106,11 +106,18 @@ int  imdb200_set_atoms(imdb200_sim *sim, long n, const int *nummer, const int *s
  * torch.cuda.current_stream().cuda_stream, so that the caller's events bracket our launches */
 int  imdb200_set_stream(imdb200_sim *sim, void *cuda_stream);
 
-/* multi-GPU: attach an initialised NCCL communicator (ncclComm_t passed as void*) whose
- * rank order is x-major over cpu_dim like MPI_Cart_create (src/imd_geom_mpi_3d.c:43-62).
- * Alternatively let the library create it from a ncclUniqueId broadcast by the host. */
+/* multi-GPU (replaces: MPI_Init + setup_mpi_topology, src/imd_mpi_util.c:48-63, src/imd_geom_mpi_3d.c:32-90):
+ * one process per GPU and domain.  Rank 0 obtains a ncclUniqueId and the host distributes it (MPI_Bcast,
+ * torch.distributed, a file ...); every rank then joins with its x-major rank over cpu_dim,
+ * rank = (my_coord.x*cpu_dim.y + my_coord.y)*cpu_dim.z + my_coord.z.  Call between imdb200_set_potentials and
+ * imdb200_set_atoms; every later call is collective (all ranks make the same calls in the same order). */
 int  imdb200_comm_unique_id(void *id128);                 /* rank 0: fills 128 bytes        */
 int  imdb200_comm_init(imdb200_sim *sim, const void *id128, int rank, int nranks);
+/* replaces: send_forces(add_forces, pack_forces, unpack_forces) (src/imd_comm_force_3d.c:569-714, 897-1020) for a
+ * caller-owned DEVICE field laid out field[c*stride + i], i < natoms_local + nghost_local, c < ncomp <= 8: what the
+ * images accumulated is added to their owners, across GPUs where the owner lives on another one. */
+int  imdb200_send_forces(imdb200_sim *sim, double *dev_field, int ncomp, long stride);
+long imdb200_nghost_local(imdb200_sim *sim);
 
 /* ---- the step loop ---------------------------------------------------------------------- */
 /* replaces: void calc_forces(int steps)  (src/imd_forces_nbl.c:281-1999; prototypes.h:173) */
@@ -179,6 +186,19 @@ int  imdb200_get_timers(imdb200_sim *sim, double out_ms[8], int reset);
 int  imdb200_read_pot_table(imdb200_pot_table *pt, const char *filename, int ncols, int radial,
                             int ntypes, int default_format, double *cellsz);
 void imdb200_free_pot_table(imdb200_pot_table *pt);
+
+/* replaces: calc_cpu_dim() (src/imd_geom_mpi_3d.c:201-266): factorise num_cpus evenly, largest factor on the
+ * axis with the largest requested cpu_dim */
+void imdb200_calc_cpu_dim(int num_cpus, int cpu_dim[3]);
+/* replaces: MPI_Cart_rank / MPI_Cart_coords on the cpugrid of setup_mpi_topology()
+ * (src/imd_geom_mpi_3d.c:43-53): row-major, z fastest */
+int  imdb200_cart_rank(const int coord[3], const int cpu_dim[3]);
+void imdb200_cart_coords(int rank, const int cpu_dim[3], int coord[3]);
+/* replaces: the neighbour ranks nbeast ... nbdwn of setup_mpi_topology() (src/imd_geom_mpi_3d.c:57-88) and the
+ * periodic shift vectors of send_cells (src/imd_comm_force_3d.c:248-265).  Direction
+ * d = (sx+1) + 3*(sy+1) + 9*(sz+1); peer[d] = -1 behind a free surface; code[d] = image shift, same encoding */
+void imdb200_halo_peers(const int cpu_dim[3], const int my_coord[3], const int pbc_dirs[3], int peer[27],
+                        int code[27]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,56 @@
+"""GPU, N >= 2: spatial domain decomposition (one process per GPU, NCCL halo exchange inside the
+library) against the fixtures of the unmodified single-process reference and against the same run on
+one GPU.  Skipped on a single-GPU box; `gpurun --gpus 2 -- python -m pytest tests -m gpu` runs them."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _run(case, grid, port):
+    n = grid[0] * grid[1] * grid[2]
+    if _ngpus() < n:
+        pytest.skip(f"needs {n} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(common.ROOT, "tests", "mgpu_worker.py"), case] + [str(x) for x in grid]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=common.ROOT)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    print(r.stdout[-1500:])
+
+
+@pytest.mark.parametrize("name", ["cu_long", "nial_nvt", "lj_nve", "cu_slab", "cu_nve"])
+def test_two_domains_match_reference_fixture(built_lib, name):
+    _run("fixture:" + name, (2, 1, 1), 29611)
+
+
+def test_two_domains_split_along_z(built_lib):
+    _run("fixture:cu_long", (1, 1, 2), 29612)
+
+
+def test_atoms_migrate_between_domains(built_lib):
+    _run("migration", (2, 1, 1), 29613)
+
+
+def test_send_forces_reverse_path(built_lib):
+    _run("send_forces", (2, 1, 1), 29614)
+
+
+def test_four_domains(built_lib):
+    _run("fixture:cu_long", (2, 2, 1), 29615)
+    _run("migration", (2, 2, 1), 29616)
+
+
+def test_eight_domains(built_lib):
+    _run("migration", (2, 2, 2), 29617)
+    _run("send_forces", (2, 2, 2), 29618)
