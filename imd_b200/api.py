@@ -49,7 +49,7 @@ EXPORTS = [
     "imdb200_create", "imdb200_destroy", "imdb200_set_potentials", "imdb200_set_restrictions",
     "imdb200_set_atoms", "imdb200_set_stream", "imdb200_comm_unique_id", "imdb200_comm_init", "imdb200_calc_forces",
     "imdb200_move_atoms", "imdb200_check_nblist", "imdb200_fix_cells", "imdb200_make_nblist", "imdb200_run",
-    "imdb200_set_press_calc", "imdb200_invalidate_nblist", "imdb200_set_eta", "imdb200_set_temperature",
+    "imdb200_set_press_calc", "imdb200_set_skin_skip", "imdb200_invalidate_nblist", "imdb200_set_eta", "imdb200_set_temperature",
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
@@ -83,6 +83,7 @@ def load_library():
         getattr(L, "imdb200_" + f).argtypes = [vp]
     L.imdb200_run.argtypes = [vp, C.c_int]
     L.imdb200_set_press_calc.argtypes = [vp, C.c_int]
+    L.imdb200_set_skin_skip.argtypes = [vp, C.c_int]
     L.imdb200_set_eta.argtypes = [vp, C.c_double]
     L.imdb200_set_temperature.argtypes = [vp, C.c_double]
     L.imdb200_lin_deform.argtypes = [vp, vp, vp, vp, C.c_double]
@@ -267,6 +268,10 @@ class IMDB200:
 
     def set_press_calc(self, on=True):
         _chk(self.L.imdb200_set_press_calc(self.h, int(on)))
+
+    def set_skin_skip(self, on=True):
+        """on=False: walk every stored list entry like the reference (test hook; results are bit-identical)."""
+        _chk(self.L.imdb200_set_skin_skip(self.h, int(on)))
 
     def set_eta(self, eta):
         _chk(self.L.imdb200_set_eta(self.h, float(eta)))

@@ -74,6 +74,7 @@ int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
   s->nranks = cfg->cpu_dim[0] * cfg->cpu_dim[1] * cfg->cpu_dim[2];
   s->rank = (cfg->my_coord[0] * cfg->cpu_dim[1] + cfg->my_coord[1]) * cfg->cpu_dim[2] + cfg->my_coord[2];
   s->eta = cfg->eta;
+  s->skin_skip = 1; s->disp2 = -1.0;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   s->own_stream = 1;
   CUDA_TRY(cudaMalloc(&s->d_scal, SC_COUNT * sizeof(double)));
@@ -100,7 +101,7 @@ void imdb200_destroy(imdb200_sim *s)
   void *ptrs[] = {s->posdf, s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF,
                   s->nblpos, s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start,
                   s->cell_fill, s->cell_code, s->gsrc, s->ghost_num, s->ghost_raw, s->scan_tmp, s->nbl, s->nnb,
-                  s->restr, s->d_scal, s->d_partial, s->d_flags, s->xfer};
+                  s->restr, s->d_scal, s->d_partial, s->d_flags, s->xfer, s->nnbc, s->posf};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->h_flags) cudaFreeHost(s->h_flags);
@@ -270,7 +271,9 @@ int imdb200_move_atoms(imdb200_sim *s)
   TRY(ready(s));
   if (s->nbl_count == 0) return imdb_fail(IMDB200_ERR_ARG, "move_atoms before the first calc_forces");
   TRY(integrate_move(s));
-  return fetch_scalars(s);
+  TRY(fetch_scalars(s));
+  s->disp2 = s->h_scal[SC_MAXD2];
+  return 0;
 }
 
 int imdb200_check_nblist(imdb200_sim *s)
@@ -279,6 +282,7 @@ int imdb200_check_nblist(imdb200_sim *s)
   if (s->nbl_count == 0) { s->have_valid_nbl = 0; return 0; }
   TRY(integrate_check_nblist(s));
   TRY(fetch_scalars(s));
+  s->disp2 = s->h_scal[SC_MAXD2];
   apply_check(s);
   return 0;
 }
@@ -286,6 +290,7 @@ int imdb200_check_nblist(imdb200_sim *s)
 int imdb200_fix_cells(imdb200_sim *s) { TRY(ready(s)); s->have_valid_nbl = 0; return cells_rebuild(s); }
 int imdb200_make_nblist(imdb200_sim *s) { TRY(ready(s)); s->have_valid_nbl = 0; return cells_rebuild(s); }
 int imdb200_invalidate_nblist(imdb200_sim *s) { if (!s) return IMDB200_ERR_ARG; s->have_valid_nbl = 0; return 0; }
+int imdb200_set_skin_skip(imdb200_sim *s, int on) { if (!s) return IMDB200_ERR_ARG; s->skin_skip = on ? 1 : 0; return 0; }
 int imdb200_set_press_calc(imdb200_sim *s, int on) { if (!s) return IMDB200_ERR_ARG; s->press_calc = on ? 1 : 0; return 0; }
 
 int imdb200_set_eta(imdb200_sim *s, double eta)
@@ -312,6 +317,7 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     TRY(integrate_move(s));
     cudaEventRecord(s->ev[4], s->stream);
     TRY(fetch_scalars(s));   // one sync per step: the host decides about the rebuild
+    s->disp2 = s->h_scal[SC_MAXD2];
     apply_check(s);
     float ms;
     cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); s->t_ms[rebuild ? 0 : 4] += ms;
@@ -337,6 +343,7 @@ int imdb200_lin_deform(imdb200_sim *s, const double dx[3], const double dy[3], c
 {
   TRY(ready(s));
   TRY(integrate_lin_deform(s, dx, dy, dz, scale));
+  s->skin_all = 1;                 // images move with the box: the displacement bound no longer holds
   // box vectors: box += scale * (D box)  (src/imd_deform.c:71-106)
   Geom &g = s->geom;
   for (int b = 0; b < 3; b++) {
@@ -352,6 +359,7 @@ int imdb200_deform_sample(imdb200_sim *s, double size, const double *shift, cons
                           const double *shear, const double *base)
 {
   TRY(ready(s));
+  s->skin_all = 1;
   return integrate_deform_sample(s, s->cfg.total_types, size, shift, shear_def, shear, base);
 }
 

@@ -105,6 +105,7 @@ int cells_ensure_capacity(imdb200_sim *s, long need)
   TRY(regrow(&s->rho, n, cap)); TRY(regrow(&s->dF, n, cap));
   TRY(regrow(&s->cellid, n, cap)); TRY(regrow(&s->cellid_alt, 0, cap)); TRY(regrow(&s->perm, 0, cap));
   TRY(regrow(&s->gsrc, 0, cap)); TRY(regrow(&s->ghost_num, 0, cap)); TRY(regrow(&s->ghost_raw, 0, cap));
+  TRY(regrow(&s->posf, 0, cap));
   // SoA blocks whose stride is the capacity: contents are rebuilt before use
   if (s->nblpos) cudaFree(s->nblpos);
   if (s->presstens) cudaFree(s->presstens);
@@ -334,6 +335,135 @@ k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__re
   if (!count_only && cnt > max_nb) atomicExch(&flags[FL_NBL_OVERFLOW], 1);
 }
 
+
+// ---- the production build: single-precision pre-filter, exact test on the survivors, entries grouped by skin class ----
+// Phase 1 walks the 27 cells with float positions (a 16-byte broadcast load and ~8 FP32 operations per candidate)
+// against a cut-off widened by the float rounding bound, and queues the ~16 % survivors in shared memory
+// (one column per thread).  Phase 2 repeats the reference's exact FP64 test (operands and rounding as in
+// k_count_nbl above) on the queue only and tags every accepted entry with its skin class.  Phase 3 writes the
+// entries class by class into the warp-blocked list.  The neighbour SET is that of the reference: the float
+// test can only let extra candidates through, never reject a pair the exact test accepts.
+struct ClassT { double t2[NBL_CLASSES]; };       // (rc + q*w)^2, q = 0..NBL_CLASSES-1
+
+__global__ void k_make_posf(const double4 *pos, long n, float4 *posf)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = pos[i];
+  posf[i] = make_float4((float) p.x, (float) p.y, (float) p.z, 0.f);
+}
+
+// one candidate of phase 1: branch-free, so that the loads of an unrolled group are issued back to back
+#define NBL_CAND(PJ, J) do { \
+    const float dx_ = (PJ).x - xf, dy_ = (PJ).y - yf, dz_ = (PJ).z - zf; \
+    const bool pass_ = fmaf(dz_, dz_, fmaf(dy_, dy_, dx_ * dx_)) < cutf; \
+    if (pass_ && qp < qend) *qp = (J) | mirror; \
+    qp += pass_ ? BS : 0; } while (0)
+
+template <int BS>
+__global__ void __launch_bounds__(BS)
+k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, int n_own, Geom g,
+             const int *__restrict__ cellid, const int *__restrict__ cell_start, const int *__restrict__ cell_count,
+             const int *__restrict__ cell_code, const int *__restrict__ gsrc, const double4 *__restrict__ ghost_raw,
+             int *__restrict__ nbl, int *__restrict__ nnb, unsigned long long *__restrict__ nnbc, int max_nb, int L,
+             float cutf, ClassT T, int *flags)
+{
+  extern __shared__ int q[];                                  // [max_nb][BS]
+  const int i = blockIdx.x * BS + threadIdx.x;
+  int cnt = 0;
+  if (i < n_own) {
+    const double4 xi = pos[i];
+    const float xf = (float) xi.x, yf = (float) xi.y, zf = (float) xi.z;
+    const int c1 = cellid[i];
+    const int cz = c1 % g.cdim[2], cy = (c1 / g.cdim[2]) % g.cdim[1], cx = c1 / (g.cdim[2] * g.cdim[1]);
+    int *const q0 = q + threadIdx.x, *const qend = q0 + max_nb * BS;
+    int *qp = q0;
+    // ---- phase 1: every atom of the 27 cells, single precision; the atom itself passes too (r2 = 0) ----
+    for (int l = -1; l <= 1; l++)
+      for (int m = -1; m <= 1; m++) {
+        const int crow = ((cx + l) * g.cdim[1] + (cy + m)) * g.cdim[2] + cz;
+#pragma unroll
+        for (int n = -1; n <= 1; n++) {
+          const int c2 = crow + n;
+          const int nj = cell_count[c2];
+          if (nj == 0) continue;
+          const int j0 = cell_start[c2];
+          const bool upper = (l > 0) || (l == 0 && (m > 0 || (m == 0 && n >= 0)));
+          const int mirror = (j0 >= n_own && !upper) ? (int) 0x80000000 : 0;   // evaluated from the other atom's side
+          const float4 *pj = posf + j0;
+          int t = 0;
+          for (; t + 4 <= nj; t += 4) {
+            const float4 p0 = __ldg(pj + t), p1 = __ldg(pj + t + 1), p2 = __ldg(pj + t + 2), p3 = __ldg(pj + t + 3);
+            NBL_CAND(p0, j0 + t); NBL_CAND(p1, j0 + t + 1); NBL_CAND(p2, j0 + t + 2); NBL_CAND(p3, j0 + t + 3);
+          }
+          for (; t < nj; t++) { const float4 p0 = __ldg(pj + t); NBL_CAND(p0, j0 + t); }
+        }
+      }
+    cnt = (int) (qp - q0) / BS;
+    // ---- phase 2: the reference's FP64 test on the survivors; entries inside the largest cut-off go straight
+    //      to the list, the skin entries are tagged with their class and kept for phase 3 ----
+    const int nq = cnt < max_nb ? cnt : max_nb;
+    const int R = max_nb / L;
+    int *const row0 = nbl + nbl_index(i, 0, L, R);             // L == 1: entry p lives at row0[32 p]
+    int n0 = 0, nk = 0;
+    unsigned long long counts = 0ull;
+    for (int m = 0; m < nq; m++) {
+      const int e = q0[m * BS];
+      const int j = e & 0x7fffffff;
+      double r2;
+      if (e < 0) {
+        const int inv = 26 - cell_code[cellid[j]];           // our image as the buffer cell on the far side holds it
+        const double4 me = image_pos(xi, inv, g);
+        const int src = gsrc[j - n_own];
+        const double4 xj = src >= 0 ? pos[src] : ghost_raw[j - n_own];
+        r2 = r2_exact(__dsub_rn(me.x, xj.x), __dsub_rn(me.y, xj.y), __dsub_rn(me.z, xj.z));
+      } else {
+        const double4 xj = ld_atom(pos + j);
+        r2 = r2_exact(__dsub_rn(xj.x, xi.x), __dsub_rn(xj.y, xi.y), __dsub_rn(xj.z, xi.z));
+      }
+      if (!(r2 < g.cellsz) || j == i) continue;
+      if (r2 <= T.t2[0]) {
+        if (L == 1) row0[n0 * 32] = j; else nbl[nbl_index(i, n0, L, R)] = j;
+        n0++;
+      } else {
+        int c = 1;
+#pragma unroll
+        for (int k = 1; k < NBL_CLASSES; k++) c += r2 > T.t2[k] ? 1 : 0;
+        counts += 1ull << (NBL_CBITS * c);
+        q0[nk * BS] = j | (c << 29);                           // nk <= m: slots already consumed
+        nk++;
+      }
+    }
+    // ---- phase 3: skin entries, class by class behind the core entries ----
+    unsigned long long cum = (unsigned long long) n0, offs = 0ull;
+    {
+      int run = n0;
+#pragma unroll
+      for (int c = 1; c <= NBL_CLASSES; c++) {
+        offs |= (unsigned long long) run << (NBL_CBITS * c);
+        run += (int) ((counts >> (NBL_CBITS * c)) & ((1u << NBL_CBITS) - 1));
+        cum |= (unsigned long long) run << (NBL_CBITS * c);
+      }
+    }
+    for (int m = 0; m < nk; m++) {
+      const unsigned e = (unsigned) q0[m * BS];
+      const int sh = NBL_CBITS * (int) (e >> 29);
+      const int p = (int) ((offs >> sh) & ((1u << NBL_CBITS) - 1));
+      offs += 1ull << sh;
+      const int j = (int) (e & 0x1fffffffu);
+      if (L == 1) row0[p * 32] = j; else nbl[nbl_index(i, p, L, R)] = j;
+    }
+    nnb[i] = n0 + nk;
+    nnbc[i] = cum;
+  }
+  const int wmax = __reduce_max_sync(0xffffffffu, cnt);       // candidates incl. the atom itself and float-only ones
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&flags[FL_MAXNB], wmax);
+    if (wmax > max_nb) atomicExch(&flags[FL_NBL_OVERFLOW], 1);
+  }
+}
+#undef NBL_CAND
+
 __global__ void k_save_nblpos(const double4 *pos, long n, long stride, double *nblpos)
 {
   long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
@@ -356,11 +486,14 @@ static int alloc_nbl(imdb200_sim *s, int max_nb)
   max_nb = ((max_nb + L - 1) / L) * L;
   long n_pad = ((s->cap_atoms + 31) / 32) * 32;
   if (s->nbl && max_nb <= s->max_nb && n_pad == s->n_pad) return 0;
+  if (max_nb >= (1 << NBL_CBITS)) return imdb_fail(IMDB200_ERR_NBL, "more than %d neighbours per atom", (1 << NBL_CBITS) - 1);
   if (s->nbl) cudaFree(s->nbl);
   if (s->nnb) cudaFree(s->nnb);
-  s->nbl = nullptr; s->nnb = nullptr;
+  if (s->nnbc) cudaFree(s->nnbc);
+  s->nbl = nullptr; s->nnb = nullptr; s->nnbc = nullptr;
   CUDA_TRY(cudaMalloc(&s->nbl, (size_t) n_pad * max_nb * sizeof(int)));
   CUDA_TRY(cudaMalloc(&s->nnb, (size_t) n_pad * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->nnbc, (size_t) n_pad * sizeof(unsigned long long)));
   s->max_nb = max_nb;
   s->n_pad = n_pad;
   return 0;
@@ -370,6 +503,46 @@ static int read_flags(imdb200_sim *s)
 {
   CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->d_flags, FL_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// Launch of the production list build.  The float cut-off is the exact one plus a bound on what rounding the
+// coordinates to single precision can do to r^2: |delta r2| <= 2 r |delta d| with |delta d| <= 4 eps maxc per
+// component (two rounded coordinates and the rounded difference), maxc = largest coordinate magnitude.
+static int launch_build(imdb200_sim *s, long n)
+{
+  const Geom &g = s->geom;
+  cudaStream_t st = s->stream;
+  const long ntot = s->n_own + s->n_ghost;
+  if (ntot >= (1L << 29)) return imdb_fail(IMDB200_ERR_ARG, "more than 2^29 atoms and images on one GPU");
+  k_make_posf<<<cdiv(ntot > 0 ? ntot : 1, 256), 256, 0, st>>>(s->pos, ntot, s->posf); LAUNCH_CHECK();
+  double maxc = 0.0;
+  for (int d = 0; d < 3; d++) {
+    double c = 0.0;
+    for (int b = 0; b < 3; b++) c += fabs(g.box[b][d]);
+    if (c > maxc) maxc = c;
+  }
+  maxc *= 2.0;                                                 // images reach one cell beyond the box
+  const double rl = sqrt(g.cellsz);
+  const double slack = 2.0 * rl * 1.7320508 * (4.0 * 1.2e-7 * maxc) + 1e-5 * g.cellsz;
+  const float cutf = (float) ((g.cellsz + slack) * (1.0 + 1e-6));
+  ClassT T;
+  const double rc = sqrt(s->cellsz0), w = s->cfg.nbl_margin / NBL_CLASSES;
+  for (int k = 0; k < NBL_CLASSES; k++) T.t2[k] = (rc + k * w) * (rc + k * w);
+  T.t2[0] = s->cellsz0 * (1.0 + 1e-12);      // the force kernels form r2 with FMAs: an ulp of slack
+  const int max_nb = s->max_nb, L = s->lanes;
+  const size_t per_thread = (size_t) max_nb * sizeof(int);
+#define BUILD(BS) do { \
+    const size_t sm = per_thread * BS; \
+    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_build_nbl2<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm)); \
+    k_build_nbl2<BS><<<cdiv(n > 0 ? n : 1, BS), BS, sm, st>>>(s->pos, s->posf, (int) n, g, s->cellid, s->cell_start, s->cell_count, \
+        s->cell_code, s->gsrc, s->ghost_raw, s->nbl, s->nnb, s->nnbc, max_nb, L, cutf, T, s->d_flags); \
+    LAUNCH_CHECK(); } while (0)
+  if (per_thread * 128 <= 72 * 1024) BUILD(128);
+  else if (per_thread * 64 <= 100 * 1024) BUILD(64);
+  else if (per_thread * 32 <= 200 * 1024) BUILD(32);
+  else return imdb_fail(IMDB200_ERR_NBL, "neighbour table of %d entries per atom does not fit the build queue", max_nb);
+#undef BUILD
   return 0;
 }
 
@@ -447,13 +620,12 @@ int cells_rebuild(imdb200_sim *s)
       k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
                                                 s->gsrc, s->ghost_raw, nullptr, nullptr, 0, L, s->d_flags, 1); LAUNCH_CHECK();
       TRY(read_flags(s));
-      int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 2;
+      int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 4;   // + the atom itself and float-only candidates in the build queue
       TRY(alloc_nbl(s, want > 8 ? want : 8));
     } else TRY(alloc_nbl(s, s->max_nb));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_NBL_OVERFLOW], 0, sizeof(int), st));
-    k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
-                                              s->gsrc, s->ghost_raw, s->nbl, s->nnb, s->max_nb, L, s->d_flags, 0); LAUNCH_CHECK();
+    TRY(launch_build(s, n));
     TRY(read_flags(s));
     if (!s->h_flags[FL_NBL_OVERFLOW]) break;
     if (attempt == 2) return imdb_fail(IMDB200_ERR_NBL, "neighbor table full - increase nbl_size");
@@ -468,6 +640,8 @@ int cells_rebuild(imdb200_sim *s)
   CUDA_TRY(cudaMemcpyAsync(&len, d_len, sizeof(len), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   s->nbl_len = (long long) len;
+  s->disp2 = 0.0;                 // NBL_POS == ORT
+  s->skin_all = 0;
   s->have_valid_nbl = 1;
   s->nbl_count++;
   return 0;

@@ -27,7 +27,9 @@ struct FArgs {
   double4 *posdf;
   double4 *frc;
   double *rho, *dF;
-  const int *nbl, *nnb;
+  const int *nbl;
+  const unsigned long long *nnbc;
+  int cls_shift;                 // NBL_CBITS * (highest skin class to walk)
   long n_own;
   int rows;                      // max_nb / L
   double *presstens; long pstride;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
     if (act) {
       xi = a.pos[i];
       if (MULTI) it = sorte_of(xi.w);
-      const int nn = a.nnb[i];
+      const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
 #pragma unroll 2
       for (int m = sub; m < nn; m += L, row += 32) {
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       const double4 xi = gat[i];
       const int it = MULTI ? sorte_of(xi.w) : 0;
       const double dFi = MULTI ? a.dF[i] : xi.w;
-      const int nn = a.nnb[i];
+      const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
 #pragma unroll 2
       for (int m = sub; m < nn; m += L, row += 32) {
@@ -288,10 +290,23 @@ int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int 
 // ----------------------------------------------------------------------------------------------------
 // launch wrappers: pick the template instance
 // ----------------------------------------------------------------------------------------------------
+// Highest list group a force call has to walk (see NBL_CLASSES in internal.cuh).  Group q >= 1 holds pairs with
+// build distance r_b > rc + (q-1) w; |r - r_b| <= 2 dmax, so they are out of reach while 2 dmax <= (q-1) w.
+static int skin_class(const imdb200_sim *s)
+{
+  if (!s->skin_skip || s->skin_all || s->disp2 < 0.0) return NBL_CLASSES;
+  if (s->disp2 == 0.0) return 0;
+  const double w = s->cfg.nbl_margin / NBL_CLASSES;
+  const double reach = 2.0 * sqrt(s->disp2) * (1.0 + 1e-9) + 1e-12;
+  const int c = (int) floor(reach / w) + 1;
+  return c < NBL_CLASSES ? c : NBL_CLASSES;
+}
+
 static FArgs make_args(imdb200_sim *s)
 {
   FArgs a;
-  a.pos = s->pos; a.posdf = s->posdf; a.frc = s->frc; a.rho = s->rho; a.dF = s->dF; a.nbl = s->nbl; a.nnb = s->nnb;
+  a.pos = s->pos; a.posdf = s->posdf; a.frc = s->frc; a.rho = s->rho; a.dF = s->dF; a.nbl = s->nbl; a.nnbc = s->nnbc;
+  a.cls_shift = NBL_CBITS * skin_class(s);
   a.n_own = s->n_own; a.rows = s->max_nb / s->lanes;
   a.presstens = s->presstens; a.pstride = s->cap_atoms;
   a.partial = s->d_partial; a.flags = s->d_flags;

@@ -119,7 +119,12 @@ struct imdb200_sim {
   int *h_starts;                  // pinned: gstart/sstart read back at a rebuild
   // neighbour list
   int *nbl, *nnb; long nbl_cap_rows; int max_nb, lanes; long n_pad;
+  unsigned long long *nnbc;       // per atom: cumulative entry counts per skin class, 12 bits each (see NBL_CLASSES)
+  float4 *posf;                   // single-precision copy of pos, pre-filter of the list build only
   int have_valid_nbl, nbl_count; long long nbl_len;
+  int skin_skip;                  // 1: the force kernels skip list entries that cannot be inside the cut-off yet
+  int skin_all;                   // box/positions changed outside move_atoms since the build: use every entry
+  double disp2;                   // max squared displacement of the current positions since the build; <0 unknown
   // restrictions / deformation tables per virtual type
   double *restr; int n_restr;
   // scalars
@@ -138,6 +143,13 @@ struct imdb200_sim {
   // comm
   void *nccl_comm; int rank, nranks;
 };
+
+// The list of an atom is stored in NBL_CLASSES+1 groups by the pair distance r_b at build time:
+// group 0: r_b <= rc (largest table cut-off), group q: rc+(q-1)w < r_b <= rc+q*w with w = nbl_margin/NBL_CLASSES.
+// A pair of group q can only be inside the cut-off once 2*max|displacement| > (q-1)*w, so a force call walks the
+// groups 0..cls only (cls from the last skin check); the entries it leaves out would all fail the r2 test.
+#define NBL_CLASSES 4
+#define NBL_CBITS 12
 
 #define NBIN_EXTRA 29   // 27 leave directions + 1 dropped + 1 spare (exclusive-scan total)
 

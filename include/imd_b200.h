@@ -136,6 +136,11 @@ int  imdb200_run(imdb200_sim *sim, int nsteps);
 /* do_press_calc (src/imd_main_3d.c:183-195): accumulate the per-atom stress tensor */
 int  imdb200_set_press_calc(imdb200_sim *sim, int on);
 int  imdb200_invalidate_nblist(imdb200_sim *sim);         /* have_valid_nbl = 0              */
+/* The list of every atom is grouped by build distance; by default a force call leaves out the groups that
+ * cannot have come inside the cut-off given the largest displacement since the build (results are bit-identical
+ * either way -- the entries left out would fail the r2 test of src/imd_forces_nbl.c:493, 588, 1172).
+ * on = 0 walks every stored entry like the reference does (test hook). */
+int  imdb200_set_skin_skip(imdb200_sim *sim, int on);
 int  imdb200_set_eta(imdb200_sim *sim, double eta);
 int  imdb200_set_temperature(imdb200_sim *sim, double temperature);
 

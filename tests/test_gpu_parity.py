@@ -107,6 +107,35 @@ def test_cuda_run_loop_equals_stepwise_calls(api, tmp_path):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("case", ["cu", "nial"])
+def test_skin_skip_is_bit_identical(api, case, tmp_path):
+    """The force kernels leave out list groups that cannot be inside the cut-off yet (2*max displacement bound).
+    Walking every stored entry instead (what the reference does) must give bit-identical trajectories,
+    energies and rebuild steps -- the left-out entries all fail the r2 tests of src/imd_forces_nbl.c:493, 588, 1172."""
+    sims = []
+    for skip in (True, False):
+        if case == "cu":
+            tabs, box, num, typ, m, x, p = _thermal_cu(tmp_path, (12, 12, 12), temp=0.12)
+            s = api.IMDB200(1, box, pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"],
+                            rho=tabs["atomic_e-density_file"], ensemble="nve", timestep=0.001)
+            s.set_atoms(num, typ, m, x, p)
+        else:
+            s = common.make_sim(api.IMDB200, common.load_golden("nial_nvt"), str(tmp_path))
+        s.set_skin_skip(skip)
+        sims.append(s)
+    a, b = sims
+    for chunk in range(6):
+        a.run(8); b.run(8)
+        A, B = a.atoms(), b.atoms()
+        for k in ("ort", "impuls", "kraft", "poteng", "rho", "dF"):
+            assert np.array_equal(A[k], B[k]), (chunk, k)
+        sa, sb = a.scalars(), b.scalars()
+        assert sa["tot_pot_energy"] == sb["tot_pot_energy"] and sa["virial"] == sb["virial"]
+        assert a.nbl_count == b.nbl_count
+    assert a.nbl_count >= 2
+    a.close(); b.close()
+
+
 def test_full_size_properties_4m(api, tmp_path):
     """BASELINE config 2 at full size (100^3 fcc cells = 4 000 000 atoms): size-independent properties."""
     tabs = synth.make_eam_tables(str(tmp_path), "cu")
