@@ -337,28 +337,98 @@ k_build_nbl(const double4 *__restrict__ pos, long n_own, Geom g, const int *__re
 
 
 // ---- the production build: single-precision pre-filter, exact test on the survivors, entries grouped by skin class ----
-// Phase 1 walks the 27 cells with float positions (a 16-byte broadcast load and ~8 FP32 operations per candidate)
-// against a cut-off widened by the float rounding bound, and queues the ~16 % survivors in shared memory
-// (one column per thread).  Phase 2 repeats the reference's exact FP64 test (operands and rounding as in
-// k_count_nbl above) on the queue only and tags every accepted entry with its skin class.  Phase 3 writes the
-// entries class by class into the warp-blocked list.  The neighbour SET is that of the reference: the float
-// test can only let extra candidates through, never reject a pair the exact test accepts.
+// Phase 1 walks the 27 cells with float positions, two candidates per packed FP32 instruction, against a
+// cut-off widened by the float rounding bound, and records the ~16 % survivors as one bit per candidate in
+// shared memory (W 32-bit words per cell and thread: 108 bytes per thread for cells of up to 32 atoms, so a
+// full complement of warps fits beside a large L1).  Phase 2 walks the set bits and repeats the reference's
+// exact FP64 test (operands and rounding as in k_build_nbl above): pairs inside the largest cut-off go
+// straight to the list, pairs outside r_list lose their bit, skin pairs are counted per class.  Phase 3 walks
+// the remaining (skin) bits again and writes them class by class behind the core entries.  The neighbour SET
+// is that of the reference: the float test can only let extra candidates through, never reject a pair the
+// exact test accepts.
 struct ClassT { double t2[NBL_CLASSES]; };       // (rc + q*w)^2, q = 0..NBL_CLASSES-1
 
+// Single-precision positions in packed pairs: record k holds atoms 2k and 2k+1 as (x0,x1) (y0,y1) (z0,z1) (pad),
+// 32 bytes = one 256-bit load, already in the operand layout of the packed FP32 instructions (FADD2/FFMA2).
 __global__ void k_make_posf(const double4 *pos, long n, float4 *posf)
 {
-  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double4 p = pos[i];
-  posf[i] = make_float4((float) p.x, (float) p.y, (float) p.z, 0.f);
+  long k = blockIdx.x * (long) blockDim.x + threadIdx.x;      // pair index
+  if (2 * k >= n) return;
+  const double4 a = pos[2 * k];
+  const double4 b = 2 * k + 1 < n ? pos[2 * k + 1] : a;
+  posf[2 * k] = make_float4((float) a.x, (float) b.x, (float) a.y, (float) b.y);
+  posf[2 * k + 1] = make_float4((float) a.z, (float) b.z, 0.f, 0.f);
 }
 
-// one candidate of phase 1: branch-free, so that the loads of an unrolled group are issued back to back
-#define NBL_CAND(PJ, J) do { \
-    const float dx_ = (PJ).x - xf, dy_ = (PJ).y - yf, dz_ = (PJ).z - zf; \
-    const bool pass_ = fmaf(dz_, dz_, fmaf(dy_, dy_, dx_ * dx_)) < cutf; \
-    if (pass_ && qp < qend) *qp = (J) | mirror; \
-    qp += pass_ ? BS : 0; } while (0)
+struct PairRec { float2 x, y, z, w; };
+__device__ __forceinline__ PairRec ld_pair(const float4 *posf, int k)
+{
+  PairRec r;
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(r.x.x), "=f"(r.x.y), "=f"(r.y.x), "=f"(r.y.y), "=f"(r.z.x), "=f"(r.z.y), "=f"(r.w.x), "=f"(r.w.y)
+      : "l"(posf + 2 * (size_t) k));
+  return r;
+}
+
+// pass bits of the n <= 32 candidates js, js+1, ...; xf, yf, zf hold MINUS the atom's own coordinates twice
+__device__ __forceinline__ unsigned nbl_scan_word(const float4 *__restrict__ posf, int js, int n, float2 xf, float2 yf,
+                                                  float2 zf, float cutf)
+{
+  unsigned word = 0u;
+  int j = js;
+  const int jend = js + n;
+  if (j & 1) {                                                  // odd first atom: upper half of its pair
+    const PairRec p = ld_pair(posf, j >> 1);
+    const float dx = p.x.y + xf.x, dy = p.y.y + yf.x, dz = p.z.y + zf.x;
+    word = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < cutf ? 1u : 0u;
+    j++;
+  }
+  int np = (jend - j) >> 1;                                     // whole pairs
+  int k = j >> 1, sh = j - js;
+#define NBL_PAIR(P, T) do { \
+    const float2 dx_ = __fadd2_rn((P).x, xf), dy_ = __fadd2_rn((P).y, yf), dz_ = __fadd2_rn((P).z, zf); \
+    const float2 r2_ = __ffma2_rn(dz_, dz_, __ffma2_rn(dy_, dy_, __fmul2_rn(dx_, dx_))); \
+    if (r2_.x < cutf) m8 |= 1u << (T); if (r2_.y < cutf) m8 |= 2u << (T); } while (0)
+  for (; np >= 4; np -= 4, k += 4, sh += 8) {
+    const PairRec p0 = ld_pair(posf, k), p1 = ld_pair(posf, k + 1), p2 = ld_pair(posf, k + 2), p3 = ld_pair(posf, k + 3);
+    unsigned m8 = 0u;
+    NBL_PAIR(p0, 0); NBL_PAIR(p1, 2); NBL_PAIR(p2, 4); NBL_PAIR(p3, 6);
+    word |= m8 << sh;
+  }
+  if (np >= 2) {
+    const PairRec p0 = ld_pair(posf, k), p1 = ld_pair(posf, k + 1);
+    unsigned m8 = 0u;
+    NBL_PAIR(p0, 0); NBL_PAIR(p1, 2);
+    word |= m8 << sh;
+    np -= 2; k += 2; sh += 4;
+  }
+  if (np) { const PairRec p0 = ld_pair(posf, k); unsigned m8 = 0u; NBL_PAIR(p0, 0); word |= m8 << sh; k++; sh += 2; }
+#undef NBL_PAIR
+  if (2 * k < jend) {                                           // even last atom: lower half of its pair
+    const PairRec p = ld_pair(posf, k);
+    const float dx = p.x.x + xf.x, dy = p.y.x + yf.x, dz = p.z.x + zf.x;
+    if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < cutf) word |= 1u << sh;
+  }
+  return word;
+}
+
+struct BuildCtx {                 // what the exact test of one candidate needs
+  const double4 *pos, *ghost_raw; const int *cellid, *cell_code, *gsrc;
+  double4 xi; int i, n_own;
+};
+// the reference's own test operands (see k_build_nbl): mirror = the pair is evaluated from the other atom's side
+__device__ __forceinline__ double nbl_exact_r2(const BuildCtx &b, const Geom &g, int j, bool mirror)
+{
+  if (mirror) {
+    const int inv = 26 - b.cell_code[b.cellid[j]];             // our image as the buffer cell on the far side holds it
+    const double4 me = image_pos(b.xi, inv, g);
+    const int src = b.gsrc[j - b.n_own];
+    const double4 xj = src >= 0 ? b.pos[src] : b.ghost_raw[j - b.n_own];
+    return r2_exact(__dsub_rn(me.x, xj.x), __dsub_rn(me.y, xj.y), __dsub_rn(me.z, xj.z));
+  }
+  const double4 xj = ld_atom(b.pos + j);
+  return r2_exact(__dsub_rn(xj.x, b.xi.x), __dsub_rn(xj.y, b.xi.y), __dsub_rn(xj.z, b.xi.z));
+}
 
 template <int BS>
 __global__ void __launch_bounds__(BS)
@@ -366,103 +436,104 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
              const int *__restrict__ cellid, const int *__restrict__ cell_start, const int *__restrict__ cell_count,
              const int *__restrict__ cell_code, const int *__restrict__ gsrc, const double4 *__restrict__ ghost_raw,
              int *__restrict__ nbl, int *__restrict__ nnb, unsigned long long *__restrict__ nnbc, int max_nb, int L,
-             float cutf, ClassT T, int *flags)
+             int W, float cutf, ClassT T, int *flags)
 {
-  extern __shared__ int q[];                                  // [max_nb][BS]
+  extern __shared__ unsigned bits[];                          // [27*W][BS]
   const int i = blockIdx.x * BS + threadIdx.x;
-  int cnt = 0;
+  int total = 0;
   if (i < n_own) {
-    const double4 xi = pos[i];
-    const float xf = (float) xi.x, yf = (float) xi.y, zf = (float) xi.z;
+    BuildCtx b;
+    b.pos = pos; b.ghost_raw = ghost_raw; b.cellid = cellid; b.cell_code = cell_code; b.gsrc = gsrc;
+    b.xi = pos[i]; b.i = i; b.n_own = n_own;
+    const float2 xf = make_float2(-(float) b.xi.x, -(float) b.xi.x), yf = make_float2(-(float) b.xi.y, -(float) b.xi.y),
+                 zf = make_float2(-(float) b.xi.z, -(float) b.xi.z);
     const int c1 = cellid[i];
     const int cz = c1 % g.cdim[2], cy = (c1 / g.cdim[2]) % g.cdim[1], cx = c1 / (g.cdim[2] * g.cdim[1]);
-    int *const q0 = q + threadIdx.x, *const qend = q0 + max_nb * BS;
-    int *qp = q0;
-    // ---- phase 1: every atom of the 27 cells, single precision; the atom itself passes too (r2 = 0) ----
+    unsigned *const my = bits + threadIdx.x;
+    // ---- phase 1 ----
+    int cs = 0;
     for (int l = -1; l <= 1; l++)
       for (int m = -1; m <= 1; m++) {
         const int crow = ((cx + l) * g.cdim[1] + (cy + m)) * g.cdim[2] + cz;
 #pragma unroll
-        for (int n = -1; n <= 1; n++) {
+        for (int n = -1; n <= 1; n++, cs++) {
           const int c2 = crow + n;
           const int nj = cell_count[c2];
-          if (nj == 0) continue;
           const int j0 = cell_start[c2];
-          const bool upper = (l > 0) || (l == 0 && (m > 0 || (m == 0 && n >= 0)));
-          const int mirror = (j0 >= n_own && !upper) ? (int) 0x80000000 : 0;   // evaluated from the other atom's side
-          const float4 *pj = posf + j0;
-          int t = 0;
-          for (; t + 4 <= nj; t += 4) {
-            const float4 p0 = __ldg(pj + t), p1 = __ldg(pj + t + 1), p2 = __ldg(pj + t + 2), p3 = __ldg(pj + t + 3);
-            NBL_CAND(p0, j0 + t); NBL_CAND(p1, j0 + t + 1); NBL_CAND(p2, j0 + t + 2); NBL_CAND(p3, j0 + t + 3);
+          if (nj > 32 * W) atomicMax(&flags[FL_CELLFULL], nj);
+          for (int w = 0; w < W; w++) {
+            const int lo = 32 * w, cntw = min(nj - lo, 32);
+            my[(cs * W + w) * BS] = cntw > 0 ? nbl_scan_word(posf, j0 + lo, cntw, xf, yf, zf, cutf) : 0u;
           }
-          for (; t < nj; t++) { const float4 p0 = __ldg(pj + t); NBL_CAND(p0, j0 + t); }
         }
       }
-    cnt = (int) (qp - q0) / BS;
-    // ---- phase 2: the reference's FP64 test on the survivors; entries inside the largest cut-off go straight
-    //      to the list, the skin entries are tagged with their class and kept for phase 3 ----
-    const int nq = cnt < max_nb ? cnt : max_nb;
-    const int R = max_nb / L;
+    // ---- phases 2 and 3 walk the set bits; j0/mirror of the current cell are refreshed when the word index moves on ----
+    const int R = max_nb / L, nwords = 27 * W;
     int *const row0 = nbl + nbl_index(i, 0, L, R);             // L == 1: entry p lives at row0[32 p]
-    int n0 = 0, nk = 0;
+    int n0 = 0;
     unsigned long long counts = 0ull;
-    for (int m = 0; m < nq; m++) {
-      const int e = q0[m * BS];
-      const int j = e & 0x7fffffff;
-      double r2;
-      if (e < 0) {
-        const int inv = 26 - cell_code[cellid[j]];           // our image as the buffer cell on the far side holds it
-        const double4 me = image_pos(xi, inv, g);
-        const int src = gsrc[j - n_own];
-        const double4 xj = src >= 0 ? pos[src] : ghost_raw[j - n_own];
-        r2 = r2_exact(__dsub_rn(me.x, xj.x), __dsub_rn(me.y, xj.y), __dsub_rn(me.z, xj.z));
-      } else {
-        const double4 xj = ld_atom(pos + j);
-        r2 = r2_exact(__dsub_rn(xj.x, xi.x), __dsub_rn(xj.y, xi.y), __dsub_rn(xj.z, xi.z));
-      }
-      if (!(r2 < g.cellsz) || j == i) continue;
-      if (r2 <= T.t2[0]) {
-        if (L == 1) row0[n0 * 32] = j; else nbl[nbl_index(i, n0, L, R)] = j;
+#define NBL_WALK(BODY) do { \
+      int jb = 0; bool mirror = false; \
+      for (int wi = 0; wi < nwords; wi++) { \
+        unsigned word = my[wi * BS]; \
+        if (!word) continue; \
+        { const int cs_ = wi / W, l_ = cs_ / 9 - 1, m_ = (cs_ / 3) % 3 - 1, n_ = cs_ % 3 - 1; \
+          const int j0_ = cell_start[((cx + l_) * g.cdim[1] + (cy + m_)) * g.cdim[2] + cz + n_]; \
+          const bool upper_ = (l_ > 0) || (l_ == 0 && (m_ > 0 || (m_ == 0 && n_ >= 0))); \
+          mirror = j0_ >= n_own && !upper_; jb = j0_ + 32 * (wi % W); } \
+        unsigned keep = word; \
+        while (word) { \
+          const int t = __ffs(word) - 1; word &= word - 1; \
+          const int j = jb + t; \
+          BODY \
+        } \
+        my[wi * BS] = keep; \
+      } } while (0)
+    NBL_WALK({
+      const double r2 = nbl_exact_r2(b, g, j, mirror);
+      if (!(r2 < g.cellsz) || j == i) keep &= ~(1u << t);
+      else if (r2 <= T.t2[0]) {
+        keep &= ~(1u << t);
+        if (n0 < max_nb) { if (L == 1) row0[n0 * 32] = j; else nbl[nbl_index(i, n0, L, R)] = j; }
         n0++;
       } else {
         int c = 1;
 #pragma unroll
         for (int k = 1; k < NBL_CLASSES; k++) c += r2 > T.t2[k] ? 1 : 0;
         counts += 1ull << (NBL_CBITS * c);
-        q0[nk * BS] = j | (c << 29);                           // nk <= m: slots already consumed
-        nk++;
       }
-    }
-    // ---- phase 3: skin entries, class by class behind the core entries ----
-    unsigned long long cum = (unsigned long long) n0, offs = 0ull;
-    {
-      int run = n0;
+    });
+    unsigned long long cum = (unsigned long long) (n0 < max_nb ? n0 : max_nb), offs = 0ull;
+    int run = n0;
 #pragma unroll
-      for (int c = 1; c <= NBL_CLASSES; c++) {
-        offs |= (unsigned long long) run << (NBL_CBITS * c);
-        run += (int) ((counts >> (NBL_CBITS * c)) & ((1u << NBL_CBITS) - 1));
-        cum |= (unsigned long long) run << (NBL_CBITS * c);
-      }
+    for (int c = 1; c <= NBL_CLASSES; c++) {
+      offs |= (unsigned long long) (run & ((1 << NBL_CBITS) - 1)) << (NBL_CBITS * c);
+      run += (int) ((counts >> (NBL_CBITS * c)) & ((1u << NBL_CBITS) - 1));
+      cum |= (unsigned long long) ((run < max_nb ? run : max_nb) & ((1 << NBL_CBITS) - 1)) << (NBL_CBITS * c);
     }
-    for (int m = 0; m < nk; m++) {
-      const unsigned e = (unsigned) q0[m * BS];
-      const int sh = NBL_CBITS * (int) (e >> 29);
-      const int p = (int) ((offs >> sh) & ((1u << NBL_CBITS) - 1));
-      offs += 1ull << sh;
-      const int j = (int) (e & 0x1fffffffu);
-      if (L == 1) row0[p * 32] = j; else nbl[nbl_index(i, p, L, R)] = j;
+    total = run;
+    if (total <= max_nb && total > n0) {
+      NBL_WALK({
+        const double r2 = nbl_exact_r2(b, g, j, mirror);
+        int c = 1;
+#pragma unroll
+        for (int k = 1; k < NBL_CLASSES; k++) c += r2 > T.t2[k] ? 1 : 0;
+        const int sh = NBL_CBITS * c;
+        const int p = (int) ((offs >> sh) & ((1u << NBL_CBITS) - 1));
+        offs += 1ull << sh;
+        if (L == 1) row0[p * 32] = j; else nbl[nbl_index(i, p, L, R)] = j;
+      });
     }
-    nnb[i] = n0 + nk;
+#undef NBL_WALK
+    nnb[i] = total < max_nb ? total : max_nb;
     nnbc[i] = cum;
   }
-  const int wmax = __reduce_max_sync(0xffffffffu, cnt);       // candidates incl. the atom itself and float-only ones
+  const int wmax = __reduce_max_sync(0xffffffffu, total);
   if ((threadIdx.x & 31) == 0) {
     atomicMax(&flags[FL_MAXNB], wmax);
     if (wmax > max_nb) atomicExch(&flags[FL_NBL_OVERFLOW], 1);
   }
 }
-#undef NBL_CAND
 
 __global__ void k_save_nblpos(const double4 *pos, long n, long stride, double *nblpos)
 {
@@ -515,7 +586,7 @@ static int launch_build(imdb200_sim *s, long n)
   cudaStream_t st = s->stream;
   const long ntot = s->n_own + s->n_ghost;
   if (ntot >= (1L << 29)) return imdb_fail(IMDB200_ERR_ARG, "more than 2^29 atoms and images on one GPU");
-  k_make_posf<<<cdiv(ntot > 0 ? ntot : 1, 256), 256, 0, st>>>(s->pos, ntot, s->posf); LAUNCH_CHECK();
+  k_make_posf<<<cdiv(ntot / 2 + 1, 256), 256, 0, st>>>(s->pos, ntot, s->posf); LAUNCH_CHECK();
   double maxc = 0.0;
   for (int d = 0; d < 3; d++) {
     double c = 0.0;
@@ -531,17 +602,18 @@ static int launch_build(imdb200_sim *s, long n)
   for (int k = 0; k < NBL_CLASSES; k++) T.t2[k] = (rc + k * w) * (rc + k * w);
   T.t2[0] = s->cellsz0 * (1.0 + 1e-12);      // the force kernels form r2 with FMAs: an ulp of slack
   const int max_nb = s->max_nb, L = s->lanes;
-  const size_t per_thread = (size_t) max_nb * sizeof(int);
+  if (s->cell_words < 1) s->cell_words = 1;
+  const int W = s->cell_words;
+  const size_t per_thread = (size_t) 27 * W * sizeof(unsigned);
 #define BUILD(BS) do { \
     const size_t sm = per_thread * BS; \
     if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_build_nbl2<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm)); \
     k_build_nbl2<BS><<<cdiv(n > 0 ? n : 1, BS), BS, sm, st>>>(s->pos, s->posf, (int) n, g, s->cellid, s->cell_start, s->cell_count, \
-        s->cell_code, s->gsrc, s->ghost_raw, s->nbl, s->nnb, s->nnbc, max_nb, L, cutf, T, s->d_flags); \
+        s->cell_code, s->gsrc, s->ghost_raw, s->nbl, s->nnb, s->nnbc, max_nb, L, W, cutf, T, s->d_flags); \
     LAUNCH_CHECK(); } while (0)
-  if (per_thread * 128 <= 72 * 1024) BUILD(128);
-  else if (per_thread * 64 <= 100 * 1024) BUILD(64);
+  if (per_thread * 128 <= 64 * 1024) BUILD(128);
   else if (per_thread * 32 <= 200 * 1024) BUILD(32);
-  else return imdb_fail(IMDB200_ERR_NBL, "neighbour table of %d entries per atom does not fit the build queue", max_nb);
+  else return imdb_fail(IMDB200_ERR_CELLS, "cells of more than %d atoms do not fit the list build", 32 * W);
 #undef BUILD
   return 0;
 }
@@ -620,13 +692,19 @@ int cells_rebuild(imdb200_sim *s)
       k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
                                                 s->gsrc, s->ghost_raw, nullptr, nullptr, 0, L, s->d_flags, 1); LAUNCH_CHECK();
       TRY(read_flags(s));
-      int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 4;   // + the atom itself and float-only candidates in the build queue
+      int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 2;
       TRY(alloc_nbl(s, want > 8 ? want : 8));
     } else TRY(alloc_nbl(s, s->max_nb));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_NBL_OVERFLOW], 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_CELLFULL], 0, sizeof(int), st));
     TRY(launch_build(s, n));
     TRY(read_flags(s));
+    if (s->h_flags[FL_CELLFULL]) {               // a cell holds more atoms than the candidate bit words cover
+      s->cell_words = (s->h_flags[FL_CELLFULL] + 31) / 32;
+      attempt--;
+      continue;
+    }
     if (!s->h_flags[FL_NBL_OVERFLOW]) break;
     if (attempt == 2) return imdb_fail(IMDB200_ERR_NBL, "neighbor table full - increase nbl_size");
   }

@@ -122,6 +122,7 @@ struct imdb200_sim {
   unsigned long long *nnbc;       // per atom: cumulative entry counts per skin class, 12 bits each (see NBL_CLASSES)
   float4 *posf;                   // single-precision copy of pos, pre-filter of the list build only
   int have_valid_nbl, nbl_count; long long nbl_len;
+  int cell_words;                 // 32-bit candidate words per cell in the list build (cells of up to 32*cell_words atoms)
   int skin_skip;                  // 1: the force kernels skip list entries that cannot be inside the cut-off yet
   int skin_all;                   // box/positions changed outside move_atoms since the build: use every entry
   double disp2;                   // max squared displacement of the current positions since the build; <0 unknown
@@ -155,7 +156,7 @@ struct imdb200_sim {
 
 enum { SC_EPOT = 0, SC_VIRIAL, SC_EKIN, SC_EKIN2, SC_MAXD2, SC_ETA, SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX,
        SC_PXY, SC_EKIN1, SC_COUNT = 16 };
-enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_NSEND, FL_BADTYPE, FL_COUNT = 8 };
+enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_NSEND, FL_BADTYPE, FL_CELLFULL, FL_COUNT = 8 };
 
 // ---- error handling --------------------------------------------------------------------------------
 int imdb_fail(int code, const char *fmt, ...);
