@@ -430,15 +430,16 @@ __device__ __forceinline__ double nbl_exact_r2(const BuildCtx &b, const Geom &g,
   return r2_exact(__dsub_rn(xj.x, b.xi.x), __dsub_rn(xj.y, b.xi.y), __dsub_rn(xj.z, b.xi.z));
 }
 
-template <int BS>
+template <int BS, bool W1>
 __global__ void __launch_bounds__(BS)
 k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, int n_own, Geom g,
              const int *__restrict__ cellid, const int *__restrict__ cell_start, const int *__restrict__ cell_count,
              const int *__restrict__ cell_code, const int *__restrict__ gsrc, const double4 *__restrict__ ghost_raw,
              int *__restrict__ nbl, int *__restrict__ nnb, unsigned long long *__restrict__ nnbc, int max_nb, int L,
-             int W, float cutf, ClassT T, int *flags)
+             int Wrt, float cutf, ClassT T, int *flags)
 {
   extern __shared__ unsigned bits[];                          // [27*W][BS]
+  const int W = W1 ? 1 : Wrt;                                 // the common case (cells of <= 32 atoms) without divisions
   const int i = blockIdx.x * BS + threadIdx.x;
   int total = 0;
   if (i < n_own) {
@@ -473,21 +474,20 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
     int n0 = 0;
     unsigned long long counts = 0ull;
 #define NBL_WALK(BODY) do { \
-      int jb = 0; bool mirror = false; \
-      for (int wi = 0; wi < nwords; wi++) { \
-        unsigned word = my[wi * BS]; \
-        if (!word) continue; \
-        { const int cs_ = wi / W, l_ = cs_ / 9 - 1, m_ = (cs_ / 3) % 3 - 1, n_ = cs_ % 3 - 1; \
+      int wi = -1, jb = 0; bool mirror = false; unsigned word = 0u, keep = 0u; \
+      for (;;) { \
+        if (word == 0u) {                       /* this lane moves on to its next non-empty word */ \
+          if (wi >= 0) my[wi * BS] = keep; \
+          for (++wi; wi < nwords; ++wi) { word = my[wi * BS]; if (word) break; } \
+          if (wi >= nwords) break; \
+          const int cs_ = wi / W, l_ = cs_ / 9 - 1, m_ = (cs_ / 3) % 3 - 1, n_ = cs_ % 3 - 1; \
           const int j0_ = cell_start[((cx + l_) * g.cdim[1] + (cy + m_)) * g.cdim[2] + cz + n_]; \
           const bool upper_ = (l_ > 0) || (l_ == 0 && (m_ > 0 || (m_ == 0 && n_ >= 0))); \
-          mirror = j0_ >= n_own && !upper_; jb = j0_ + 32 * (wi % W); } \
-        unsigned keep = word; \
-        while (word) { \
-          const int t = __ffs(word) - 1; word &= word - 1; \
-          const int j = jb + t; \
-          BODY \
+          mirror = j0_ >= n_own && !upper_; jb = j0_ + 32 * (wi % W); keep = word; \
         } \
-        my[wi * BS] = keep; \
+        const int t = __ffs(word) - 1; word &= word - 1; \
+        const int j = jb + t; \
+        BODY \
       } } while (0)
     NBL_WALK({
       const double r2 = nbl_exact_r2(b, g, j, mirror);
@@ -605,14 +605,15 @@ static int launch_build(imdb200_sim *s, long n)
   if (s->cell_words < 1) s->cell_words = 1;
   const int W = s->cell_words;
   const size_t per_thread = (size_t) 27 * W * sizeof(unsigned);
-#define BUILD(BS) do { \
+#define BUILD(BS, W1) do { \
     const size_t sm = per_thread * BS; \
-    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_build_nbl2<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm)); \
-    k_build_nbl2<BS><<<cdiv(n > 0 ? n : 1, BS), BS, sm, st>>>(s->pos, s->posf, (int) n, g, s->cellid, s->cell_start, s->cell_count, \
+    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_build_nbl2<BS, W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm)); \
+    k_build_nbl2<BS, W1><<<cdiv(n > 0 ? n : 1, BS), BS, sm, st>>>(s->pos, s->posf, (int) n, g, s->cellid, s->cell_start, s->cell_count, \
         s->cell_code, s->gsrc, s->ghost_raw, s->nbl, s->nnb, s->nnbc, max_nb, L, W, cutf, T, s->d_flags); \
     LAUNCH_CHECK(); } while (0)
-  if (per_thread * 128 <= 64 * 1024) BUILD(128);
-  else if (per_thread * 32 <= 200 * 1024) BUILD(32);
+  if (W == 1) BUILD(128, true);
+  else if (per_thread * 128 <= 64 * 1024) BUILD(128, false);
+  else if (per_thread * 32 <= 200 * 1024) BUILD(32, false);
   else return imdb_fail(IMDB200_ERR_CELLS, "cells of more than %d atoms do not fit the list build", 32 * W);
 #undef BUILD
   return 0;
