@@ -22,6 +22,15 @@
 // takes list entries l, l+L, ... and the partial sums are combined with xor shuffles.
 #include "internal.cuh"
 
+// entries per block of the software-pipelined list walk, and threads per CTA (one persistent CTA per SM)
+#ifndef IMDB_DEPTH
+#define IMDB_DEPTH 4
+#endif
+#ifndef IMDB_NT
+#define IMDB_NT 640
+#endif
+#define FDEPTH IMDB_DEPTH
+
 struct FArgs {
   const double4 *pos;
   double4 *posdf;
@@ -97,10 +106,23 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
       if (MULTI) it = sorte_of(xi.w);
       const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
-#pragma unroll 2
-      for (int m = sub; m < nn; m += L, row += 32) {
-        const int j = __ldcs(row);
-        const double4 xj = ld_atom(a.pos + j);
+      // Software pipeline over the list: the D entries of a block are in registers when the block starts (they
+      // were loaded during the previous block), their D position gathers are issued together, the next block's
+      // entries are requested, and only then the arithmetic of the block runs.  The list stream comes from HBM
+      // (~1 us) and the gathers from L1/L2: without this every warp sits out both latencies once per entry.
+      int jq[FDEPTH];
+#pragma unroll
+      for (int d = 0; d < FDEPTH; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
+      for (int m = sub; m < nn; m += FDEPTH * L, row += FDEPTH * 32) {
+        double4 xq[FDEPTH];
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) xq[d] = ld_atom(a.pos + (jq[d] >= 0 ? jq[d] : (int) i));
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) jq[d] = (m + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) {
+        if (m + d * L >= nn) break;
+        const double4 xj = xq[d];
         const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         const int col = MULTI ? it * nt + sorte_of(xj.w) : 0;
@@ -117,7 +139,11 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         }
         if (inp) {
           const int e = MULTI ? k * T.pair.ncols + col : k;
+#if defined(IMDB_ABL) && (IMDB_ABL & 2)   /* experiment only: no table lookups */
+          const double2 ab = make_double2(chi, 1.0 + k); const double c2 = r2;
+#else
           const double2 ab = pAB[e]; const double c2 = pC[e];
+#endif
           const double pot = tab_val(ab, c2, chi);
           const double grad = tab_grad(ab, c2, chi, pis + pis);
           fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
@@ -129,7 +155,12 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         }
         if (inr) {
           const int e = MULTI ? kr * T.rho.ncols + col : kr;
+#if defined(IMDB_ABL) && (IMDB_ABL & 2)
+          rh += tab_val(make_double2(chir, 2.0 + e), r2, chir);
+#else
           rh += tab_val(rAB[e], rC[e], chir);
+#endif
+        }
         }
       }
     }
@@ -201,10 +232,25 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       const double dFi = MULTI ? a.dF[i] : xi.w;
       const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
-#pragma unroll 2
-      for (int m = sub; m < nn; m += L, row += 32) {
-        const int j = __ldcs(row);
-        const double4 xj = ld_atom(gat + j);
+      int jq[FDEPTH];                                    // software pipeline as in pass 1
+#pragma unroll
+      for (int d = 0; d < FDEPTH; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
+      for (int m = sub; m < nn; m += FDEPTH * L, row += FDEPTH * 32) {
+        double4 xq[FDEPTH];
+        int jc[MULTI ? FDEPTH : 1];
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) {
+          const int j = jq[d] >= 0 ? jq[d] : (int) i;
+          xq[d] = ld_atom(gat + j);
+          if (MULTI) jc[d] = j;
+        }
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) jq[d] = (m + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) {
+        if (m + d * L >= nn) break;
+        const double4 xj = xq[d];
+        const int j = MULTI ? jc[d] : 0;
         const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         double grad;
@@ -212,7 +258,11 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           if (!(r2 < r_end0)) continue;                    // :1172
           int k; double chi;
           tab_index_fast(r2, r_nb0, r_is0, k, chi, is_short);
+#if defined(IMDB_ABL) && (IMDB_ABL & 2)
+          const double2 h = make_double2(chi, 1.0 + k);
+#else
           const double2 h = rH[k];
+#endif
           grad = (dFi + xj.w) * fma(chi, h.y, h.x);        // 0.5*(dF_i+dF_j)*rho' (:1203), col1 == col2
         } else {
           const int jt = sorte_of(xj.w);
@@ -236,6 +286,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
         if (STRESS) { const double gx = dx * grad, gy = dy * grad, gz = dz * grad;
                       s0 = fma(dx, gx, s0); s1 = fma(dy, gy, s1); s2 = fma(dz, gz, s2);
                       s3 = fma(dy, gz, s3); s4 = fma(dz, gx, s4); s5 = fma(dx, gy, s5); }
+        }
       }
     }
     if (L > 1) {
@@ -334,8 +385,8 @@ template <typename K> static int launch_k(K kern, imdb200_sim *s, const FArgs &a
 #define P1(L, EAM, MULTI, SHARED) \
   (s->press_calc ? (ts ? launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, true>, s, a, 512, sm) \
                        : launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, false>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass1<1024, L, EAM, MULTI, SHARED, false, true>, s, a, 1024, sm) \
-                       : launch_k(k_pass1<1024, L, EAM, MULTI, SHARED, false, false>, s, a, 1024, 0)))
+                 : (ts ? launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, true>, s, a, IMDB_NT, sm) \
+                       : launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, false>, s, a, IMDB_NT, 0)))
 
 template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 {
@@ -349,8 +400,8 @@ template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 #define P2(L, MULTI) \
   (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true>, s, a, 512, sm) \
                        : launch_k(k_pass2<512, L, MULTI, true, false>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass2<1024, L, MULTI, false, true>, s, a, 1024, sm) \
-                       : launch_k(k_pass2<1024, L, MULTI, false, false>, s, a, 1024, 0)))
+                 : (ts ? launch_k(k_pass2<IMDB_NT, L, MULTI, false, true>, s, a, IMDB_NT, sm) \
+                       : launch_k(k_pass2<IMDB_NT, L, MULTI, false, false>, s, a, IMDB_NT, 0)))
 
 template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a)
 {
@@ -372,7 +423,7 @@ int forces_pass1(imdb200_sim *s)
     default: return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
   }
   const int slots[2] = {SC_EPOT, SC_VIRIAL};
-  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : 1024), 2, slots, 0);
+  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 2, slots, 0);
 }
 
 int forces_pass2(imdb200_sim *s)
@@ -388,5 +439,5 @@ int forces_pass2(imdb200_sim *s)
     default: return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
   }
   const int slots[1] = {SC_VIRIAL};
-  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : 1024), 1, slots, 1);
+  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 1, slots, 1);
 }
