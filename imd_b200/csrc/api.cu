@@ -245,7 +245,7 @@ static int calc_forces_async(imdb200_sim *s)
   TRY(forces_pass1(s));
   if (s->tabs.have_eam) {
     TRY(comm_ghost_dF(s));                             // send_cells(copy_dF,...) (:1115)
-    TRY(forces_pass2(s));
+    TRY(forces_pass2(s, 0));
   }
   return 0;
 }
@@ -312,9 +312,11 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     cudaEventRecord(s->ev[1], s->stream);
     TRY(forces_pass1(s));
     cudaEventRecord(s->ev[2], s->stream);
-    if (s->tabs.have_eam) { TRY(comm_ghost_dF(s)); TRY(forces_pass2(s)); }
+    // single-species EAM: move_atoms + check_nblist ride in the tail of pass 2 (bit-identical, one kernel less)
+    const int fuse = forces_can_fuse_move(s);
+    if (s->tabs.have_eam) { TRY(comm_ghost_dF(s)); TRY(forces_pass2(s, fuse)); }
     cudaEventRecord(s->ev[3], s->stream);
-    TRY(integrate_move(s));
+    if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
     cudaEventRecord(s->ev[4], s->stream);
     TRY(fetch_scalars(s));   // one sync per step: the host decides about the rebuild
     s->disp2 = s->h_scal[SC_MAXD2];

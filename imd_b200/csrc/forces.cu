@@ -44,6 +44,12 @@ struct FArgs {
   double *presstens; long pstride;
   double *partial;
   int *flags;
+  // fused move_atoms + check_nblist in the tail of pass 2 (single-species EAM: pass 2 gathers posdf, never pos)
+  double4 *pos_rw, *mom;
+  const double *nblpos; long nstride;
+  const double *scal;
+  unsigned long long *maxd2;
+  double dt; int nvt;
 };
 
 template <int L> __device__ __forceinline__ double lanes_sum(double v)
@@ -71,7 +77,13 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const double2 *pAB = T.pairAB, *rAB = T.rhoAB;
   const double *pC = T.pairC, *rC = T.rhoC;
-  if (TSMEM) {
+  constexpr bool FUSED = EAM && !MULTI && SHARED;          // one 48-byte record per interval, see DevTables::fused
+  const double2 *fT = T.fused;
+  if (TSMEM && FUSED) {
+    stage(smem_raw, T.fused, T.fused_rows * 48);
+    __syncthreads();
+    fT = reinterpret_cast<const double2 *>(smem_raw);
+  } else if (TSMEM) {
     // [phi (c0,c1)] [rho (c0,c1)] [phi c2] [rho c2]
     const int np = T.pair.nrows * T.pair.ncols, nr = EAM ? T.rho.nrows * T.rho.ncols : 0;
     const int npe = (np + 1) & ~1, nre = (nr + 1) & ~1;                // c2 arrays are padded to even length
@@ -137,13 +149,11 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
           else if (inr) { const double ris = MULTI ? T.rho.invstep[col] : r_is0;
                           tab_index_fast(r2, MULTI ? -T.rho.begin[col] * ris : r_nb0, ris, kr, chir, is_short); }
         }
+        double2 fmid = make_double2(0.0, 0.0);
+        if (FUSED) fmid = fT[3 * k + 1];                     // (phi c2, rho c2)
         if (inp) {
           const int e = MULTI ? k * T.pair.ncols + col : k;
-#if defined(IMDB_ABL) && (IMDB_ABL & 2)   /* experiment only: no table lookups */
-          const double2 ab = make_double2(chi, 1.0 + k); const double c2 = r2;
-#else
-          const double2 ab = pAB[e]; const double c2 = pC[e];
-#endif
+          const double2 ab = FUSED ? fT[3 * k] : pAB[e]; const double c2 = FUSED ? fmid.x : pC[e];
           const double pot = tab_val(ab, c2, chi);
           const double grad = tab_grad(ab, c2, chi, pis + pis);
           fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
@@ -155,11 +165,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         }
         if (inr) {
           const int e = MULTI ? kr * T.rho.ncols + col : kr;
-#if defined(IMDB_ABL) && (IMDB_ABL & 2)
-          rh += tab_val(make_double2(chir, 2.0 + e), r2, chir);
-#else
-          rh += tab_val(rAB[e], rC[e], chir);
-#endif
+          rh += FUSED ? tab_val(fT[3 * kr + 2], fmid.y, chir) : tab_val(rAB[e], rC[e], chir);
         }
         }
       }
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 // ----------------------------------------------------------------------------------------------------
 // pass 2: EAM forces (src/imd_forces_nbl.c:1117-1322)
 // ----------------------------------------------------------------------------------------------------
-template <int NT, int L, bool MULTI, bool STRESS, bool TSMEM>
+template <int NT, int L, bool MULTI, bool STRESS, bool TSMEM, bool FUSE>
 __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -218,7 +224,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   const long total = ((a.n_own * L + 31) / 32) * 32;
   const long per = ((total + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
   const long s_end = min(total, (long) (blockIdx.x + 1) * per);
-  double red[1] = {0.0};
+  double red[3] = {0.0, 0.0, 0.0};                  // virial, and with FUSE the two kinetic-energy sums
+  double d2max = 0.0;
   int is_short = 0;
   for (long slot = (long) blockIdx.x * per + threadIdx.x; slot < s_end; slot += NT) {
     const long i = slot / L;
@@ -258,11 +265,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           if (!(r2 < r_end0)) continue;                    // :1172
           int k; double chi;
           tab_index_fast(r2, r_nb0, r_is0, k, chi, is_short);
-#if defined(IMDB_ABL) && (IMDB_ABL & 2)
-          const double2 h = make_double2(chi, 1.0 + k);
-#else
           const double2 h = rH[k];
-#endif
           grad = (dFi + xj.w) * fma(chi, h.y, h.x);        // 0.5*(dF_i+dF_j)*rho' (:1203), col1 == col2
         } else {
           const int jt = sorte_of(xj.w);
@@ -298,6 +301,20 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       double4 f = a.frc[i];
       f.x += fx; f.y += fy; f.z += fz;
       a.frc[i] = f;
+      if (FUSE) {                                        // move_atoms + check_nblist of this atom, see integrate_atom()
+        const double4 xo = gat[i];
+        double4 x = xo, p = a.mom[i];
+        double rk[2];
+        const double nx = a.nblpos[i], ny = a.nblpos[a.nstride + i], nz = a.nblpos[2 * a.nstride + i];
+        const double d2 = a.nvt ? integrate_atom<true>(x, p, f, a.dt, a.scal[SC_ETA], 1.0, 1.0, 1.0, nx, ny, nz, rk)
+                                : integrate_atom<false>(x, p, f, a.dt, 0.0, 1.0, 1.0, 1.0, nx, ny, nz, rk);
+        a.mom[i] = p;
+        double *xw = reinterpret_cast<double *>(a.pos_rw + i);   // .w (the types) stays as it is
+        *reinterpret_cast<double2 *>(xw) = make_double2(x.x, x.y);
+        xw[2] = x.z;
+        red[1] += rk[0]; red[2] += rk[1];
+        d2max = fmax(d2max, d2);
+      }
       if (STRESS) {
         double *p = a.presstens + i;
         p[0] -= 0.5 * s0; p[a.pstride] -= 0.5 * s1; p[2 * a.pstride] -= 0.5 * s2;
@@ -307,7 +324,15 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
     }
   }
   if (is_short) atomicExch(&a.flags[FL_SHORT], 1);
-  block_sum_store<1>(red, a.partial);
+  if (FUSE) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2max = fmax(d2max, __shfl_xor_sync(0xffffffffu, d2max, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(a.maxd2, (unsigned long long) __double_as_longlong(d2max));
+    block_sum_store<3>(red, a.partial);
+  } else {
+    double r1[1] = {red[0]};
+    block_sum_store<1>(r1, a.partial);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -315,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 // (replaces the MPI_Allreduce operand build-up of src/imd_forces_nbl.c:1975-1994 on one rank)
 // ----------------------------------------------------------------------------------------------------
 struct Slots { int s[8]; };
-__global__ void k_reduce_partials(const double *partial, int nblocks, int nv, double *scal, Slots slots, int accumulate)
+__global__ void k_reduce_partials(const double *partial, int nblocks, int nv, double *scal, Slots slots, int accumulate_mask)
 {
   __shared__ double sm[256];
   for (int v = 0; v < nv; v++) {
@@ -324,16 +349,16 @@ __global__ void k_reduce_partials(const double *partial, int nblocks, int nv, do
     sm[threadIdx.x] = x;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) { if (accumulate) scal[slots.s[v]] += sm[0]; else scal[slots.s[v]] = sm[0]; }
+    if (threadIdx.x == 0) { if ((accumulate_mask >> v) & 1) scal[slots.s[v]] += sm[0]; else scal[slots.s[v]] = sm[0]; }
     __syncthreads();
   }
 }
 
-int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate)
+int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask)
 {
   Slots sl;
   for (int i = 0; i < 8; i++) sl.s[i] = i < nvals ? slots[i] : 0;
-  k_reduce_partials<<<1, 256, 0, s->stream>>>(s->d_partial, nblocks, nvals, s->d_scal, sl, accumulate);
+  k_reduce_partials<<<1, 256, 0, s->stream>>>(s->d_partial, nblocks, nvals, s->d_scal, sl, accumulate_mask);
   LAUNCH_CHECK();
   return 0;
 }
@@ -361,6 +386,9 @@ static FArgs make_args(imdb200_sim *s)
   a.n_own = s->n_own; a.rows = s->max_nb / s->lanes;
   a.presstens = s->presstens; a.pstride = s->cap_atoms;
   a.partial = s->d_partial; a.flags = s->d_flags;
+  a.pos_rw = s->pos; a.mom = s->mom; a.nblpos = s->nblpos; a.nstride = s->cap_atoms; a.scal = s->d_scal;
+  a.maxd2 = (unsigned long long *) (s->d_scal + SC_MAXD2);
+  a.dt = s->cfg.timestep; a.nvt = s->cfg.ensemble == IMDB200_ENS_NVT;
   return a;
 }
 
@@ -397,18 +425,24 @@ template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
   return multi ? P1(L, true, true, false) : P1(L, true, false, false);
 }
 
-#define P2(L, MULTI) \
-  (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true>, s, a, 512, sm) \
-                       : launch_k(k_pass2<512, L, MULTI, true, false>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass2<IMDB_NT, L, MULTI, false, true>, s, a, IMDB_NT, sm) \
-                       : launch_k(k_pass2<IMDB_NT, L, MULTI, false, false>, s, a, IMDB_NT, 0)))
+#define P2(L, MULTI, FUSE) \
+  (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true, false>, s, a, 512, sm) \
+                       : launch_k(k_pass2<512, L, MULTI, true, false, false>, s, a, 512, 0)) \
+                 : (ts ? launch_k(k_pass2<IMDB_NT, L, MULTI, false, true, FUSE>, s, a, IMDB_NT, sm) \
+                       : launch_k(k_pass2<IMDB_NT, L, MULTI, false, false, FUSE>, s, a, IMDB_NT, 0)))
 
-template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a)
+template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
 {
   const bool multi = s->tabs.ntypes > 1, ts = s->tabs.smem2 > 0;
   const int sm = s->tabs.smem2;
-  return multi ? P2(L, true) : P2(L, false);
+  if (multi) return P2(L, true, false);
+  return fuse ? P2(L, false, true) : P2(L, false, false);
 }
+
+// move_atoms can ride in the tail of pass 2 when pass 2 does not gather from pos (single species) and neither
+// the per-atom stress nor restriction vectors are in play
+int forces_can_fuse_move(const imdb200_sim *s)
+{ return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0; }
 
 int forces_pass1(imdb200_sim *s)
 {
@@ -426,18 +460,26 @@ int forces_pass1(imdb200_sim *s)
   return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 2, slots, 0);
 }
 
-int forces_pass2(imdb200_sim *s)
+int forces_pass2(imdb200_sim *s, int fuse)
 {
   FArgs a = make_args(s);
+  if (fuse && !forces_can_fuse_move(s)) return imdb_fail(IMDB200_ERR_ARG, "fused move_atoms is not available in this configuration");
+  if (fuse) CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
   switch (s->lanes) {
-    case 1: TRY(launch2_L<1>(s, a)); break;
-    case 2: TRY(launch2_L<2>(s, a)); break;
-    case 4: TRY(launch2_L<4>(s, a)); break;
-    case 8: TRY(launch2_L<8>(s, a)); break;
-    case 16: TRY(launch2_L<16>(s, a)); break;
-    case 32: TRY(launch2_L<32>(s, a)); break;
+    case 1: TRY(launch2_L<1>(s, a, fuse)); break;
+    case 2: TRY(launch2_L<2>(s, a, fuse)); break;
+    case 4: TRY(launch2_L<4>(s, a, fuse)); break;
+    case 8: TRY(launch2_L<8>(s, a, fuse)); break;
+    case 16: TRY(launch2_L<16>(s, a, fuse)); break;
+    case 32: TRY(launch2_L<32>(s, a, fuse)); break;
     default: return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
   }
+  const int nb = grid_for(s, s->press_calc ? 512 : IMDB_NT);
+  if (fuse) {
+    const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT;
+    const int slots[3] = {SC_VIRIAL, nvt ? SC_EKIN1 : SC_EKIN, SC_EKIN2};
+    return reduce_finish(s, nb, 3, slots, 1);            // the virial adds to pass 1's, the kinetic sums replace
+  }
   const int slots[1] = {SC_VIRIAL};
-  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 1, slots, 1);
+  return reduce_finish(s, nb, 1, slots, 1);
 }

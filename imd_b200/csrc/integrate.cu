@@ -47,23 +47,9 @@ __global__ void __launch_bounds__(IBLOCK) k_move_atoms(IArgs a)
       f.x *= rx; f.y *= ry; f.z *= rz;                                // :192-197
       a.frc[i] = f;
     }
-    if (!NVT) {
-      const double k1 = p.x * p.x + p.y * p.y + p.z * p.z;
-      p.x += dt * f.x; p.y += dt * f.y; p.z += dt * f.z;              // :213-217
-      const double k2 = p.x * p.x + p.y * p.y + p.z * p.z;
-      red[0] = (k1 + k2) / (4 * m);                                   // :329-335
-    } else {
-      const double eta = a.scal[SC_ETA];
-      const double reibung = 1.0 - eta * dt / 2.0;                    // :907
-      const double eins_d_reib = 1.0 / (1.0 + eta * dt / 2.0);        // :908
-      red[0] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;               // E_kin_1 :951
-      p.x = (p.x * reibung + dt * f.x) * eins_d_reib * rx;            // :1020-1027
-      p.y = (p.y * reibung + dt * f.y) * eins_d_reib * ry;
-      p.z = (p.z * reibung + dt * f.z) * eins_d_reib * rz;
-      red[1] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;               // E_kin_2
-    }
-    const double tmp = dt / m;                                         // :353-358
-    x.x += tmp * p.x; x.y += tmp * p.y; x.z += tmp * p.z;
+    const double eta = NVT ? a.scal[SC_ETA] : 0.0;
+    const double nx = a.nblpos[i], ny = a.nblpos[a.nstride + i], nz = a.nblpos[2 * a.nstride + i];
+    d2 = integrate_atom<NVT>(x, p, f, dt, eta, rx, ry, rz, nx, ny, nz, red);
     a.mom[i] = p;
     a.pos[i] = x;
     if (STRESS) {                                                      // :410-433
@@ -71,9 +57,6 @@ __global__ void __launch_bounds__(IBLOCK) k_move_atoms(IArgs a)
       s[0] += p.x * p.x / m; s[a.pstride] += p.y * p.y / m; s[2 * a.pstride] += p.z * p.z / m;
       s[3 * a.pstride] += p.y * p.z / m; s[4 * a.pstride] += p.z * p.x / m; s[5 * a.pstride] += p.x * p.y / m;
     }
-    // check_nblist: same operands and rounding as the reference (exact -> identical rebuild steps)
-    const double ex = x.x - a.nblpos[i], ey = x.y - a.nblpos[a.nstride + i], ez = x.z - a.nblpos[2 * a.nstride + i];
-    d2 = r2_exact(ex, ey, ez);
   }
   d2 = block_max(d2);
   if (threadIdx.x == 0) atomicMax(a.maxd2, (unsigned long long) __double_as_longlong(d2));
@@ -135,21 +118,28 @@ int integrate_move(imdb200_sim *s)
              else    { if (re) GO(false, false, true); else GO(false, false, false); } }
 #undef GO
   LAUNCH_CHECK();
+  return integrate_finish(s, nb);
+}
+
+// what follows the per-atom part: kinetic-energy sums, Nose-Hoover update, stress totals
+int integrate_finish(imdb200_sim *s, int nb)
+{
+  const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT, st = s->press_calc != 0;
   if (nvt) {
-    const int slots[2] = {SC_EKIN1, SC_EKIN2};
-    TRY(reduce_finish(s, nb, 2, slots, 0));
+    if (nb > 0) { const int slots[2] = {SC_EKIN1, SC_EKIN2}; TRY(reduce_finish(s, nb, 2, slots, 0)); }
     TRY(comm_sync_scalars(s));    // MPI_Allreduce of E_kin_1/2 (src/imd_integrate.c:1104-1130)
     k_nvt_finish<<<1, 1, 0, s->stream>>>(s->d_scal, s->d_glob, s->cfg.timestep, (double) s->nactive,
                                          s->cfg.temperature, s->cfg.isq_tau_eta);
     LAUNCH_CHECK();
-  } else {
+  } else if (nb > 0) {
     const int slots[2] = {SC_EKIN, SC_EKIN2};
     TRY(reduce_finish(s, nb, 2, slots, 0));
   }
   if (st) {
-    k_sum_presstens<<<nb, IBLOCK, 0, s->stream>>>(s->presstens, s->cap_atoms, s->n_own, s->d_partial); LAUNCH_CHECK();
+    const int nbp = cdiv(s->n_own, IBLOCK);
+    k_sum_presstens<<<nbp, IBLOCK, 0, s->stream>>>(s->presstens, s->cap_atoms, s->n_own, s->d_partial); LAUNCH_CHECK();
     const int slots[6] = {SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX, SC_PXY};
-    TRY(reduce_finish(s, nb, 6, slots, 0));
+    TRY(reduce_finish(s, nbp, 6, slots, 0));
   }
   return 0;
 }

@@ -49,6 +49,9 @@ struct DevTables {
   const double  *rhoC;    // [nrows][ncols]  c2 of rho
   const double2 *rhoH;    // [nrows][ncols]  (h1,h2): rho'/2 = h1+chi*h2 (pass 2; the 0.5 of :1203 folded in)
   const double  *embedVG; // [nrows][ntypes][6]  c0 c1 c2 g1 g2 -     value+grad of F (once per atom)
+  const double2 *fused;   // single species, phi and rho on one r^2 grid: [nrows][3] = (phi c0,c1) (phi c2, rho c2) (rho c0,c1),
+                          // one 48-byte record per interval = three 16-byte loads per pair in pass 1
+  int fused_rows;
   int have_eam, shared_grid, ntypes;
   int smem1, smem2;       // dynamic shared memory (bytes) to stage the pass-1 / pass-2 tables; 0 = leave in HBM/L1
 };
@@ -198,9 +201,11 @@ int comm_sync_scalars(imdb200_sim *s);        // the MPI_Allreduce sites
 int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
 
 int forces_pass1(imdb200_sim *s);             // pair + rho + embedding
-int forces_pass2(imdb200_sim *s);             // EAM force pass
+int forces_pass2(imdb200_sim *s, int fuse_move);   // EAM force pass; fuse_move: move_atoms + check_nblist in its tail
+int forces_can_fuse_move(const imdb200_sim *s);
+int integrate_finish(imdb200_sim *s, int nblocks_move);   // reductions + Nose-Hoover update after the per-atom part
 int integrate_move(imdb200_sim *s);           // move_atoms_nve/nvt + check_nblist fused
-int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate);
+int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask);
 
 // ---- device helpers ------------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -275,6 +280,37 @@ __device__ __forceinline__ double warp_sum(double v)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// One atom of move_atoms_nve / move_atoms_nvt (src/imd_integrate.c:192-217, 328-358, 907-908, 1020-1027) and of
+// check_nblist (src/imd_forces_nbl.c:2007-2037).  Shared by k_move_atoms and by the fused tail of k_pass2 so that
+// imdb200_run and the separate calls produce bit-identical trajectories.  f is the (restricted) force, rx..rz the
+// restriction vector of the atom's virtual type, red[0..1] the kinetic-energy partial sums, returns |x - nbl_pos|^2.
+template <bool NVT>
+__device__ __forceinline__ double integrate_atom(double4 &x, double4 &p, const double4 &f, double dt, double eta,
+                                                 double rx, double ry, double rz, double nx, double ny, double nz,
+                                                 double (&red)[2])
+{
+  const double m = p.w;
+  if (!NVT) {
+    const double k1 = p.x * p.x + p.y * p.y + p.z * p.z;
+    p.x += dt * f.x; p.y += dt * f.y; p.z += dt * f.z;              // :213-217
+    const double k2 = p.x * p.x + p.y * p.y + p.z * p.z;
+    red[0] = (k1 + k2) / (4 * m);                                   // :329-335
+    red[1] = 0.0;
+  } else {
+    const double reibung = 1.0 - eta * dt / 2.0;                    // :907
+    const double eins_d_reib = 1.0 / (1.0 + eta * dt / 2.0);        // :908
+    red[0] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;               // E_kin_1 :951
+    p.x = (p.x * reibung + dt * f.x) * eins_d_reib * rx;            // :1020-1027
+    p.y = (p.y * reibung + dt * f.y) * eins_d_reib * ry;
+    p.z = (p.z * reibung + dt * f.z) * eins_d_reib * rz;
+    red[1] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;               // E_kin_2
+  }
+  const double tmp = dt / m;                                         // :353-358
+  x.x += tmp * p.x; x.y += tmp * p.y; x.z += tmp * p.z;
+  // check_nblist: same operands and rounding as the reference (exact -> identical rebuild steps)
+  return r2_exact(x.x - nx, x.y - ny, x.z - nz);
 }
 
 // Block-wide sum of NV values; thread 0 of the block writes them to partial[blockIdx.x*NV + v].

@@ -111,6 +111,22 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
     for (int col = 0; col < pair->ncols; col++)
       if (pair->begin[col] != rho->begin[col] || pair->invstep[col] != rho->invstep[col]) T.shared_grid = 0;
   }
+  if (rho && nt == 1 && T.shared_grid) {
+    const int nr = pair->maxsteps > rho->maxsteps ? pair->maxsteps : rho->maxsteps;
+    std::vector<double2> f((size_t) nr * 3, make_double2(0.0, 0.0));
+    double c5[5];
+    for (int k = 0; k < nr; k++) {
+      double pc[3] = {0, 0, 0}, rc[3] = {0, 0, 0};
+      if (k < pair->maxsteps) { coef(pair, k, 0, c5); pc[0] = c5[0]; pc[1] = c5[1]; pc[2] = c5[2]; }
+      if (k < rho->maxsteps) { coef(rho, k, 0, c5); rc[0] = c5[0]; rc[1] = c5[1]; rc[2] = c5[2]; }
+      f[3 * (size_t) k] = make_double2(pc[0], pc[1]);
+      f[3 * (size_t) k + 1] = make_double2(pc[2], rc[2]);
+      f[3 * (size_t) k + 2] = make_double2(rc[0], rc[1]);
+    }
+    TRY(upload(s, 6, f, &T.fused));
+    T.fused_rows = nr;
+    bytes1 = (size_t) nr * 48;
+  }
   // Tables are staged in shared memory when they leave at least ~100 KB of the 228 KB SM array to L1
   // (the position gathers live there); otherwise they stay in HBM and are served by L1/L2.
   const size_t limit = 128 * 1024;
