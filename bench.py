@@ -17,7 +17,8 @@ Printed JSON (one line, rank 0):
              forces, all inside the timed region
   roofline   dominant kernel (pass 1: pair + density + embedding) against the measured HBM peak
   cpu_baseline  the reference's own serial Verlet-list build (oracle/_ref) on a bounded sample
---impl reference: the reference's own CPU implementation on all host threads (its OpenMP build).
+--impl reference: the reference's own CPU implementation on all host threads: IMD's MPI build on
+oracle/shmpi (shared-memory MPI subset, one rank per host thread); its OpenMP build as fallback.
 """
 from __future__ import annotations
 
@@ -133,45 +134,102 @@ print(json.dumps(dict(value=n * k / dt, steps=k, natoms=n, seconds=dt)))
         return {"value": None, "unit": "atom-steps/s", "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
 
 
+def balanced_grid(n):
+    """(px, py, pz) with px*py*pz == n and the smallest surface; None if n has no factorisation with
+    max/min <= 4 (prime rank counts would give slabs thinner than the interaction range)."""
+    best = None
+    for a in range(1, n + 1):
+        if n % a:
+            continue
+        for b in range(a, n // a + 1):
+            if (n // a) % b:
+                continue
+            c = n // a // b
+            if c < b:
+                continue
+            if c <= 4 * a and (best is None or c - a < best[2] - best[0]):
+                best = (a, b, c)
+    return best
+
+
 def reference_arm(args):
-    """--impl reference: IMD's own OpenMP CPU build (cell-pair algorithm, src/imd_main_risc_3d.c +
-    src/imd_forces_eam2.c) on all host threads; each 'step' is one MD step of a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads.
+    First choice is IMD's MPI build (imd_mpi_nve_nvt_eam_nbl: the same Verlet-list code path, spatial domain
+    decomposition, one rank per host thread) running on oracle/shmpi, our shared-memory subset of MPI --
+    there is no MPI installation in this image; tests/test_ref_mpi.py checks it against the serial build.
+    Fallback: IMD's OpenMP build (cell-pair algorithm).  Each 'step' is one MD step of a bounded sample."""
     from imd_b200 import synth
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    exe = os.path.join(ROOT, "oracle", "_ref", "imd_ref_omp_eam")
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     tmp = tempfile.mkdtemp(prefix="imdref_")
     tabs = synth.make_eam_tables(tmp, "cu")
-    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-    nc = 24
+    mpi_exe = os.path.join(ROOT, "oracle", "_ref", "imd_ref_mpi_eam")
+    omp_exe = os.path.join(ROOT, "oracle", "_ref", "imd_ref_omp_eam")
+    ranks, grid = 1, (1, 1, 1)
+    for n in range(cores, 0, -1):
+        g = balanced_grid(n)
+        if g:
+            ranks, grid = n, g
+            break
 
-    def run(nsteps):
-        p = synth.cu_param(tmp, ncell=(nc, nc, nc), name=f"omp{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs)
+    def run(kind, nc, nsteps):
+        if kind == "mpi":
+            box = [nc * g for g in grid]
+            p = synth.cu_param(tmp, ncell=box, name=f"mpi{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs,
+                               extra=dict(cpu_dim=list(grid)))
+            exe, env = mpi_exe, dict(os.environ, SHMPI_NP=str(ranks))
+        else:
+            p = synth.cu_param(tmp, ncell=(nc, nc, nc), name=f"omp{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs)
+            exe, env = omp_exe, dict(os.environ, OMP_NUM_THREADS=str(cores))
+        t0 = time.perf_counter()
         r = subprocess.run([exe, "-p", p], capture_output=True, text=True, cwd=tmp, env=env, timeout=3000)
+        wall = time.perf_counter() - t0
         m = re.search(r"([0-9.eE+-]+) seconds excluding setup time", r.stdout)
-        if not m:
+        if r.returncode != 0 or not m:
             raise RuntimeError("reference run failed:\n" + r.stdout[-1500:] + r.stderr[-1500:])
-        return float(m.group(1))
+        # IMD's timer is CPU time of rank 0 (= wall time of the main loop: ranks spin-wait, never sleep)
+        return min(float(m.group(1)), wall)
 
-    # size the bounded sample from a 4-step probe so that the two runs below take about 100 s in total
-    rate = 4 * nc ** 3 * 4 / max(run(4), 1e-6)
-    total_steps = 2 * args.warmup + args.steps
-    nc = int(min(100, max(16, round((rate * 100.0 / total_steps / 4) ** (1.0 / 3.0)))))
-    natoms = 4 * nc ** 3
-    t_w = run(args.warmup) if args.warmup > 0 else 0.0
-    t_all = run(args.warmup + args.steps)
-    dt = max(t_all - t_w, 1e-9)
+    def measure(kind):
+        # size the bounded sample from a 4-step probe so that the two runs below take about 100 s in total
+        nc0 = 12 if kind == "mpi" else 24
+        units = ranks if kind == "mpi" else 1
+        rate = 4 * nc0 ** 3 * units * 4 / max(run(kind, nc0, 4), 1e-6)
+        total_steps = 2 * args.warmup + args.steps
+        cap = int((32e6 / 4 / units) ** (1.0 / 3.0))     # at most 32 M atoms (about 12 GB of host memory) in the sample
+        nc = int(min(100, cap, max(10 if kind == "mpi" else 16, round((rate * 100.0 / total_steps / 4 / units) ** (1.0 / 3.0)))))
+        natoms = 4 * nc ** 3 * units
+        t_w = run(kind, nc, args.warmup) if args.warmup > 0 else 0.0
+        t_all = run(kind, nc, args.warmup + args.steps)
+        return natoms, max(t_all - t_w, 1e-9)
+
+    kind, note = "mpi", None
+    try:
+        if not os.path.exists(mpi_exe):
+            raise RuntimeError("oracle/_ref/imd_ref_mpi_eam missing")
+        natoms, dt = measure("mpi")
+    except Exception as e:                                 # keep the arm alive: fall back to the OpenMP build
+        kind, note = "omp", f"MPI build unavailable ({str(e)[:200]})"
+        natoms, dt = measure("omp")
     v = natoms * args.steps / dt
+    if kind == "mpi":
+        par, used = "mpi%d (cpu_dim %d %d %d, oracle/shmpi shared-memory MPI)" % ((ranks,) + grid), ranks
+        sample = (f"IMD MPI build imd_mpi_nve_nvt_eam_nbl (Verlet lists, -O3 -march=x86-64-v3) on {ranks} ranks, "
+                  f"{natoms} atoms ({natoms // ranks} per rank) x {args.steps} steps after {args.warmup} warm-up steps, "
+                  "main-loop time of rank 0")
+    else:
+        par, used = f"omp{cores}", cores
+        sample = (f"IMD OpenMP build imd_omp_nve_eam (cell-pair algorithm), {natoms} atoms x {args.steps} steps after "
+                  f"{args.warmup} warm-up steps, main-loop wall time" + (f"; {note}" if note else ""))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "atom-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "EAM Cu fcc NVE, Verlet-skin parameters, synthetic Cu tables (IMD format 2)",
-                       "sample_atoms": natoms, "parallelism": f"omp{cores}"},
-            "cpu_baseline": {"value": v, "unit": "atom-steps/s", "cores": cores, "kind": "reference",
-                             "sample": f"IMD OpenMP build imd_omp_nve_eam (cell-pair algorithm), {natoms} atoms x "
-                                       f"{args.steps} steps after {args.warmup} warm-up steps, main-loop wall time"},
+            "config": {"workload": "EAM Cu fcc NVE, Verlet nbl + skin 0.4, synthetic Cu tables 2001/4001 rows (IMD format 2), "
+                                   "T0=0.05, dt=1fs; bounded sample of the 4M-atom job",
+                       "sample_atoms": natoms, "parallelism": par, "host_threads": cores},
+            "cpu_baseline": {"value": v, "unit": "atom-steps/s", "cores": used, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
