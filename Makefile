@@ -7,7 +7,7 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-
 CFLAGS   := -O2 -fPIC -Wall -std=c99 -D_POSIX_C_SOURCE=200809L
 CU       := $(wildcard imd_b200/csrc/*.cu)
 HC       := $(wildcard imd_b200/host/*.c)
-OBJ      := $(CU:imd_b200/csrc/%.cu=build/%.o) $(HC:imd_b200/host/%.c=build/host_%.o)
+OBJ      := $(CU:imd_b200/csrc/%.cu=build/%.o) build/forces_cubic.o $(HC:imd_b200/host/%.c=build/host_%.o)
 LIB      := imd_b200/libimd_b200.so
 
 all: $(LIB)
@@ -15,6 +15,11 @@ all: $(LIB)
 build/%.o: imd_b200/csrc/%.cu imd_b200/csrc/internal.cuh include/imd_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+# the force kernels once more for the cubic table interpolations (4point / spline), see forces.cu
+build/forces_cubic.o: imd_b200/csrc/forces.cu imd_b200/csrc/internal.cuh include/imd_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -DIMDB_CUBIC=1 -c $< -o $@ 2> build/forces_cubic.ptxas.log || (cat build/forces_cubic.ptxas.log; false)
 
 build/host_%.o: imd_b200/host/%.c include/imd_b200.h
 	@mkdir -p build

@@ -32,7 +32,8 @@ class Config(C.Structure):
                 ("pbc_dirs", C.c_int * 3), ("cpu_dim", C.c_int * 3), ("my_coord", C.c_int * 3),
                 ("nbl_margin", C.c_double), ("nbl_size", C.c_double), ("timestep", C.c_double),
                 ("ensemble", C.c_int), ("temperature", C.c_double), ("eta", C.c_double),
-                ("isq_tau_eta", C.c_double), ("device", C.c_int), ("lanes_per_atom", C.c_int)]
+                ("isq_tau_eta", C.c_double), ("device", C.c_int), ("lanes_per_atom", C.c_int),
+                ("interpolation", C.c_int)]
 
 
 class Scalars(C.Structure):
@@ -178,13 +179,17 @@ def comm_unique_id():
     return buf.raw
 
 
+# table interpolation (IMDB200_INTERP_*): what IMD's `4point` / `spline` make targets select at compile time
+INTERP = {"3point": 0, "4point": 1, "spline": 2}
+
+
 class IMDB200:
     """One simulation domain on one B200."""
 
     def __init__(self, ntypes, box, pbc=(1, 1, 1), nbl_margin=0.4, nbl_size=1.1, pair=None, embed=None,
                  rho=None, default_fmt=None, ensemble="nve", timestep=0.001, temperature=0.0, eta=0.0,
                  isq_tau_eta=0.0, device=-1, lanes_per_atom=0, total_types=None, cpu_dim=(1, 1, 1),
-                 my_coord=(0, 0, 0)):
+                 my_coord=(0, 0, 0), interp="3point"):
         L = load_library()
         self.L = L
         cfg = Config()
@@ -199,6 +204,7 @@ class IMDB200:
         cfg.ensemble = NVT if str(ensemble).lower() == "nvt" else NVE
         cfg.temperature = temperature; cfg.eta = eta; cfg.isq_tau_eta = isq_tau_eta
         cfg.device = device; cfg.lanes_per_atom = lanes_per_atom
+        cfg.interpolation = INTERP[interp] if isinstance(interp, str) else int(interp)
         self.h = C.c_void_p()
         _chk(L.imdb200_create(C.byref(cfg), C.byref(self.h)))
         self.ntypes = int(ntypes)

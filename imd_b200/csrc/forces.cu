@@ -30,6 +30,18 @@
 #define IMDB_NT 640
 #endif
 #define FDEPTH IMDB_DEPTH
+// This file is compiled twice (Makefile): IMDB_CUBIC=0 holds the quadratic (PAIR_INT2) kernels and everything the
+// two builds share, IMDB_CUBIC=1 the same kernels for the cubic table modes (PAIR_INT3 / PAIR_INT_SP, one more
+// coefficient per lookup).  The kernels carry the flag as a template argument so that their symbols differ.
+#ifndef IMDB_CUBIC
+#define IMDB_CUBIC 0
+#endif
+#if IMDB_CUBIC
+#define IMPL(name) name##_cubic
+#else
+#define IMPL(name) name##_quad
+#endif
+static constexpr bool CUBIC = IMDB_CUBIC != 0;
 
 struct FArgs {
   const double4 *pos;
@@ -71,18 +83,28 @@ __device__ __forceinline__ void stage(void *dst, const void *src, int bytes)
 // pass 1: pair potential + host electron density (src/imd_forces_nbl.c:422-981), then the embedding
 // energy F(rho_i) and 2F'(rho_i) (:1079-1095)
 // ----------------------------------------------------------------------------------------------------
-template <int NT, int L, bool EAM, bool MULTI, bool SHARED, bool STRESS, bool TSMEM>
+template <int NT, int L, bool EAM, bool MULTI, bool SHARED, bool STRESS, bool TSMEM, bool CUB>
 __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const double2 *pAB = T.pairAB, *rAB = T.rhoAB;
   const double *pC = T.pairC, *rC = T.rhoC;
-  constexpr bool FUSED = EAM && !MULTI && SHARED;          // one 48-byte record per interval, see DevTables::fused
+  const double2 *pCD = T.pairCD, *rCD = T.rhoCD;           // cubic modes: (c2,c3)
+  constexpr bool FUSED = EAM && !MULTI && SHARED && !CUB;  // one 48-byte record per interval, see DevTables::fused
   const double2 *fT = T.fused;
   if (TSMEM && FUSED) {
     stage(smem_raw, T.fused, T.fused_rows * 48);
     __syncthreads();
     fT = reinterpret_cast<const double2 *>(smem_raw);
+  } else if (TSMEM && CUB) {
+    // [phi (c0,c1)] [rho (c0,c1)] [phi (c2,c3)] [rho (c2,c3)]
+    const int np = T.pair.nrows * T.pair.ncols, nr = EAM ? T.rho.nrows * T.rho.ncols : 0;
+    double2 *sAB = reinterpret_cast<double2 *>(smem_raw);
+    stage(sAB, T.pairAB, np * 16);
+    stage(sAB + np + nr, T.pairCD, np * 16);
+    if (EAM) { stage(sAB + np, T.rhoAB, nr * 16); stage(sAB + 2 * np + nr, T.rhoCD, nr * 16); }
+    __syncthreads();
+    pAB = sAB; rAB = sAB + np; pCD = sAB + np + nr; rCD = sAB + 2 * np + nr;
   } else if (TSMEM) {
     // [phi (c0,c1)] [rho (c0,c1)] [phi c2] [rho c2]
     const int np = T.pair.nrows * T.pair.ncols, nr = EAM ? T.rho.nrows * T.rho.ncols : 0;
@@ -153,9 +175,10 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         if (FUSED) fmid = fT[3 * k + 1];                     // (phi c2, rho c2)
         if (inp) {
           const int e = MULTI ? k * T.pair.ncols + col : k;
-          const double2 ab = FUSED ? fT[3 * k] : pAB[e]; const double c2 = FUSED ? fmid.x : pC[e];
-          const double pot = tab_val(ab, c2, chi);
-          const double grad = tab_grad(ab, c2, chi, pis + pis);
+          const double2 ab = FUSED ? fT[3 * k] : pAB[e];
+          double pot, grad;
+          if (CUB) { const double2 cd = pCD[e]; pot = tab_val3(ab, cd, chi); grad = tab_grad3(ab, cd, chi, pis + pis); }
+          else { const double c2 = FUSED ? fmid.x : pC[e]; pot = tab_val(ab, c2, chi); grad = tab_grad(ab, c2, chi, pis + pis); }
           fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
           ee += pot;
           vir = fma(r2, grad, vir);
@@ -165,7 +188,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         }
         if (inr) {
           const int e = MULTI ? kr * T.rho.ncols + col : kr;
-          rh += FUSED ? tab_val(fT[3 * kr + 2], fmid.y, chir) : tab_val(rAB[e], rC[e], chir);
+          if (CUB) rh += tab_val3(rAB[e], rCD[e], chir);
+          else rh += FUSED ? tab_val(fT[3 * kr + 2], fmid.y, chir) : tab_val(rAB[e], rC[e], chir);
         }
         }
       }
@@ -182,10 +206,16 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
       if (EAM) {
         int k, dummy = 0; double chi;                     // PAIR_INT(pot, EAM_DF, embed_pot, ...) :1086
         tab_index(rh, T.embed.begin[it], T.embed.end[it], T.embed.invstep[it], k, chi, dummy);
-        const double *e = T.embedVG + ((size_t) k * T.embed.ncols + it) * 6;
+        const double *e = T.embedVG + ((size_t) k * T.embed.ncols + it) * 8;   // c0 c1 | c2 c3 | g1 g2 | g3 -
         const double2 e0 = ld2(e), e1 = ld2(e + 2), e2 = ld2(e + 4);
-        epot += fma(chi, fma(chi, e1.x, e0.y), e0.x);
-        const double dF = fma(chi, e2.x, e1.y);
+        double dF;
+        if (CUB) {
+          epot += tab_val3(e0, e1, chi);
+          dF = fma(chi, fma(chi, __ldg(e + 6), e2.y), e2.x);
+        } else {
+          epot += fma(chi, fma(chi, e1.x, e0.y), e0.x);
+          dF = fma(chi, e2.y, e2.x);
+        }
         a.rho[i] = rh;
         a.dF[i] = dF;
         if (!MULTI) a.posdf[i] = make_double4(xi.x, xi.y, xi.z, dF);
@@ -207,16 +237,19 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 // ----------------------------------------------------------------------------------------------------
 // pass 2: EAM forces (src/imd_forces_nbl.c:1117-1322)
 // ----------------------------------------------------------------------------------------------------
-template <int NT, int L, bool MULTI, bool STRESS, bool TSMEM, bool FUSE>
+template <int NT, int L, bool MULTI, bool STRESS, bool TSMEM, bool FUSE, bool CUB>
 __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const double2 *rH = T.rhoH;
+  const double *rH3 = T.rhoH3;                       // cubic modes: rho'/2 = h1 + chi*(h2 + chi*h3)
   if (TSMEM) {
     const int nr = T.rho.nrows * T.rho.ncols;
     stage(smem_raw, T.rhoH, nr * 16);
+    if (CUB) stage(smem_raw + (size_t) nr * 16, T.rhoH3, ((nr + 1) & ~1) * 8);
     __syncthreads();
     rH = reinterpret_cast<const double2 *>(smem_raw);
+    rH3 = reinterpret_cast<const double *>(smem_raw + (size_t) nr * 16);
   }
   const int nt = T.ntypes;
   const double r_end0 = T.rho.end[0], r_is0 = T.rho.invstep[0], r_nb0 = -T.rho.begin[0] * T.rho.invstep[0];
@@ -266,7 +299,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           int k; double chi;
           tab_index_fast(r2, r_nb0, r_is0, k, chi, is_short);
           const double2 h = rH[k];
-          grad = (dFi + xj.w) * fma(chi, h.y, h.x);        // 0.5*(dF_i+dF_j)*rho' (:1203), col1 == col2
+          const double hs = CUB ? fma(chi, rH3[k], h.y) : h.y;
+          grad = (dFi + xj.w) * fma(chi, hs, h.x);         // 0.5*(dF_i+dF_j)*rho' (:1203), col1 == col2
         } else {
           const int jt = sorte_of(xj.w);
           const int col1 = jt * nt + it, col2 = it * nt + jt;
@@ -275,12 +309,12 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           // rho_i' from column col1, rho_j' from col2; both evaluated with the clamp, as DERIV_FUNC does
           tab_index(r2, T.rho.begin[col1], T.rho.end[col1], T.rho.invstep[col1], k, chi, is_short);
           double2 h = rH[k * T.rho.ncols + col1];
-          const double rho_i_strich = fma(chi, h.y, h.x);
+          const double rho_i_strich = fma(chi, CUB ? fma(chi, rH3[k * T.rho.ncols + col1], h.y) : h.y, h.x);
           double rho_j_strich = rho_i_strich;
           if (col1 != col2) {
             tab_index(r2, T.rho.begin[col2], T.rho.end[col2], T.rho.invstep[col2], k, chi, is_short);
             h = rH[k * T.rho.ncols + col2];
-            rho_j_strich = fma(chi, h.y, h.x);
+            rho_j_strich = fma(chi, CUB ? fma(chi, rH3[k * T.rho.ncols + col2], h.y) : h.y, h.x);
           }
           grad = dFi * rho_j_strich + __ldg(a.dF + j) * rho_i_strich;
         }
@@ -335,6 +369,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   }
 }
 
+#if !IMDB_CUBIC
 // ----------------------------------------------------------------------------------------------------
 // deterministic second reduction stage: one block sums the per-block partials in a fixed order
 // (replaces the MPI_Allreduce operand build-up of src/imd_forces_nbl.c:1975-1994 on one rank)
@@ -362,6 +397,8 @@ int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int 
   LAUNCH_CHECK();
   return 0;
 }
+
+#endif  // !IMDB_CUBIC
 
 // ----------------------------------------------------------------------------------------------------
 // launch wrappers: pick the template instance
@@ -411,10 +448,10 @@ template <typename K> static int launch_k(K kern, imdb200_sim *s, const FArgs &a
 
 // the per-atom stress variant needs twelve more accumulator registers: half the threads, twice the registers
 #define P1(L, EAM, MULTI, SHARED) \
-  (s->press_calc ? (ts ? launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, true>, s, a, 512, sm) \
-                       : launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, false>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, true>, s, a, IMDB_NT, sm) \
-                       : launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, false>, s, a, IMDB_NT, 0)))
+  (s->press_calc ? (ts ? launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, true, CUBIC>, s, a, 512, sm) \
+                       : launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, false, CUBIC>, s, a, 512, 0)) \
+                 : (ts ? launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, true, CUBIC>, s, a, IMDB_NT, sm) \
+                       : launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, false, CUBIC>, s, a, IMDB_NT, 0)))
 
 template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 {
@@ -426,10 +463,10 @@ template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 }
 
 #define P2(L, MULTI, FUSE) \
-  (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true, false>, s, a, 512, sm) \
-                       : launch_k(k_pass2<512, L, MULTI, true, false, false>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass2<IMDB_NT, L, MULTI, false, true, FUSE>, s, a, IMDB_NT, sm) \
-                       : launch_k(k_pass2<IMDB_NT, L, MULTI, false, false, FUSE>, s, a, IMDB_NT, 0)))
+  (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true, false, CUBIC>, s, a, 512, sm) \
+                       : launch_k(k_pass2<512, L, MULTI, true, false, false, CUBIC>, s, a, 512, 0)) \
+                 : (ts ? launch_k(k_pass2<IMDB_NT, L, MULTI, false, true, FUSE, CUBIC>, s, a, IMDB_NT, sm) \
+                       : launch_k(k_pass2<IMDB_NT, L, MULTI, false, false, FUSE, CUBIC>, s, a, IMDB_NT, 0)))
 
 template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
 {
@@ -439,12 +476,19 @@ template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
   return fuse ? P2(L, false, true) : P2(L, false, false);
 }
 
+#if !IMDB_CUBIC
 // move_atoms can ride in the tail of pass 2 when pass 2 does not gather from pos (single species) and neither
 // the per-atom stress nor restriction vectors are in play
 int forces_can_fuse_move(const imdb200_sim *s)
 { return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0; }
 
-int forces_pass1(imdb200_sim *s)
+int forces_pass1_cubic(imdb200_sim *s);
+int forces_pass2_cubic(imdb200_sim *s, int fuse);
+int forces_pass1(imdb200_sim *s) { return s->tabs.cubic ? forces_pass1_cubic(s) : forces_pass1_quad(s); }
+int forces_pass2(imdb200_sim *s, int fuse) { return s->tabs.cubic ? forces_pass2_cubic(s, fuse) : forces_pass2_quad(s, fuse); }
+#endif
+
+int IMPL(forces_pass1)(imdb200_sim *s)
 {
   FArgs a = make_args(s);
   switch (s->lanes) {
@@ -460,7 +504,7 @@ int forces_pass1(imdb200_sim *s)
   return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 2, slots, 0);
 }
 
-int forces_pass2(imdb200_sim *s, int fuse)
+int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
 {
   FArgs a = make_args(s);
   if (fuse && !forces_can_fuse_move(s)) return imdb_fail(IMDB200_ERR_ARG, "fused move_atoms is not available in this configuration");

@@ -48,7 +48,12 @@ struct DevTables {
   const double2 *rhoAB;   // [nrows][ncols]  (c0,c1) of rho           (pass 1)
   const double  *rhoC;    // [nrows][ncols]  c2 of rho
   const double2 *rhoH;    // [nrows][ncols]  (h1,h2): rho'/2 = h1+chi*h2 (pass 2; the 0.5 of :1203 folded in)
-  const double  *embedVG; // [nrows][ntypes][6]  c0 c1 c2 g1 g2 -     value+grad of F (once per atom)
+  const double  *embedVG; // [nrows][ntypes][8]  c0 c1 c2 c3 g1 g2 g3 -  value+grad of F (once per atom)
+  // cubic interpolation (IMDB200_INTERP_4POINT / _SPLINE): val = c0+chi*(c1+chi*(c2+chi*c3)); pairC/rhoC unused
+  const double2 *pairCD;  // [nrows][ncols]  (c2,c3) of phi
+  const double2 *rhoCD;   // [nrows][ncols]  (c2,c3) of rho
+  const double  *rhoH3;   // [nrows][ncols]  h3: rho'/2 = h1+chi*(h2+chi*h3)
+  int cubic;
   const double2 *fused;   // single species, phi and rho on one r^2 grid: [nrows][3] = (phi c0,c1) (phi c2, rho c2) (rho c0,c1),
                           // one 48-byte record per interval = three 16-byte loads per pair in pass 1
   int fused_rows;
@@ -91,7 +96,7 @@ struct imdb200_sim {
   double height[3], min_height[3], max_height[3], volume, volume_init;
   double cellsz0;                 // max table end (r^2) before the margin is added
   DevTables tabs;
-  void *tab_mem[8];
+  void *tab_mem[8];               // device allocations behind DevTables
   int have_tabs;
   cudaStream_t stream; int own_stream;
   // atoms
@@ -203,6 +208,10 @@ int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
 int forces_pass1(imdb200_sim *s);             // pair + rho + embedding
 int forces_pass2(imdb200_sim *s, int fuse_move);   // EAM force pass; fuse_move: move_atoms + check_nblist in its tail
 int forces_can_fuse_move(const imdb200_sim *s);
+int forces_pass1_quad(imdb200_sim *s);        // forces.cu is compiled once per interpolation order (quadratic / cubic)
+int forces_pass2_quad(imdb200_sim *s, int fuse_move);
+int forces_pass1_cubic(imdb200_sim *s);
+int forces_pass2_cubic(imdb200_sim *s, int fuse_move);
 int integrate_finish(imdb200_sim *s, int nblocks_move);   // reductions + Nose-Hoover update after the per-atom part
 int integrate_move(imdb200_sim *s);           // move_atoms_nve/nvt + check_nblist fused
 int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask);
@@ -252,6 +261,11 @@ __device__ __forceinline__ void tab_index_fast(double r2, double nbegin_istep, d
 // val = c0 + chi*(c1 + chi*c2); grad = G*(c1 + 2*chi*c2) with G = 2*invstep
 __device__ __forceinline__ double tab_val(double2 ab, double c2, double chi) { return fma(chi, fma(chi, c2, ab.y), ab.x); }
 __device__ __forceinline__ double tab_grad(double2 ab, double c2, double chi, double G) { return G * fma(chi + chi, c2, ab.y); }
+// cubic modes: val = c0 + chi*(c1 + chi*(c2 + chi*c3)); grad = G*(c1 + chi*(2*c2 + 3*c3*chi))
+__device__ __forceinline__ double tab_val3(double2 ab, double2 cd, double chi)
+{ return fma(chi, fma(chi, fma(chi, cd.y, cd.x), ab.y), ab.x); }
+__device__ __forceinline__ double tab_grad3(double2 ab, double2 cd, double chi, double G)
+{ return G * fma(chi, fma(3.0 * chi, cd.y, cd.x + cd.x), ab.y); }
 
 // copy_cell (src/imd_comm_force_3d.c:726-778) for all three sweeps at once.  The reference adds
 // the box vectors stage by stage (up/down, then north/south, then east/west; :268-395), so the

@@ -13,19 +13,98 @@ static int fill_meta(TabMeta &m, const imdb200_pot_table *pt)
   return 0;
 }
 
-// c0 c1 c2 g1 g2 of interval k, column col -- same dv/d2v expressions as PAIR_INT2
-// (src/potaccess.h:345-349), evaluated here once in double instead of once per pair.
-static inline void coef(const imdb200_pot_table *pt, int k, int col, double out[5])
+// ---- host-side preparation -------------------------------------------------------------------------------
+// A private copy of one pot_table_t with the pad rows (and the spline's second derivatives) recomputed for
+// the interpolation in use: init_threepoint / init_fourpoint / init_spline, src/imd_potential.c:1171-1272.
+struct HostTab {
+  const imdb200_pot_table *pt;
+  std::vector<double> y, y2;     // [(maxsteps+2)][ncols]
+  int mode;
+};
+
+static void prepare(HostTab &h, const imdb200_pot_table *pt, int mode, int radial)
 {
   const int nc = pt->ncols;
-  const double *t = pt->table + (size_t) k * nc + col;
-  const double p0 = t[0], p1 = t[nc], p2 = t[2 * nc];
-  const double dv = p1 - p0, d2v = p2 - 2 * p1 + p0, istep = pt->invstep[col];
-  out[0] = p0;
-  out[1] = dv - 0.5 * d2v;
-  out[2] = 0.5 * d2v;
-  out[3] = 2 * istep * out[1];
-  out[4] = 4 * istep * out[2];
+  const size_t rows = (size_t) pt->maxsteps + 2;
+  h.pt = pt; h.mode = mode;
+  h.y.assign(pt->table, pt->table + rows * nc);
+  h.y2.assign(mode == IMDB200_INTERP_SPLINE ? rows * nc : 0, 0.0);
+  for (int col = 0; col < nc; col++) {
+    double *y = h.y.data() + col;
+    const long n = pt->len[col];
+    if (mode == IMDB200_INTERP_4POINT) {
+      if (n < 4) continue;
+      y[n * nc]       =  4 * y[(n - 1) * nc] -  6 * y[(n - 2) * nc] +  4 * y[(n - 3) * nc] -     y[(n - 4) * nc];
+      y[(n + 1) * nc] = 10 * y[(n - 1) * nc] - 20 * y[(n - 2) * nc] + 15 * y[(n - 3) * nc] - 4 * y[(n - 4) * nc];
+    } else if (mode == IMDB200_INTERP_SPLINE) {
+      if (n < 3) continue;
+      double *y2 = h.y2.data() + col;
+      const double step = pt->step[col];
+      std::vector<double> u(rows, 0.0);
+      y2[0] = u[0] = 0;                                   // natural spline at the left end
+      for (long i = 1; i < n - 1; i++) {
+        const double p = 0.5 * y2[(i - 1) * nc] + 2.0;
+        y2[i * nc] = -0.5 / p;
+        u[i] = (y[(i + 1) * nc] - 2 * y[i * nc] + y[(i - 1) * nc]) / step;
+        u[i] = (6.0 * u[i] / (2 * step) - 0.5 * u[i - 1]) / p;
+      }
+      double qn = 0.0, un = 0.0;                          // radial functions: zero slope at the right end
+      if (radial) { qn = 0.5; un = (3.0 / step) * (y[(n - 2) * nc] - y[(n - 1) * nc]) / step; }
+      y2[(n - 1) * nc] = (un - qn * u[n - 2]) / (qn * y2[(n - 2) * nc] + 1.0);
+      for (long k = n - 2; k >= 0; k--) y2[k * nc] = y2[k * nc] * y2[(k + 1) * nc] + u[k];
+      y[n * nc] = 2 * y[(n - 1) * nc] - y[(n - 2) * nc] + step * step * y2[(n - 1) * nc];
+      y2[n * nc] = 2 * y2[(n - 1) * nc] - y2[(n - 2) * nc];
+    } else {
+      if (n < 3) continue;
+      y[n * nc]       = 3 * y[(n - 1) * nc] - 3 * y[(n - 2) * nc] + y[(n - 3) * nc];
+      y[(n + 1) * nc] = 6 * y[(n - 1) * nc] - 8 * y[(n - 2) * nc] + 3 * y[(n - 3) * nc];
+    }
+  }
+}
+
+// Polynomial coefficients of interval k = (int)((r2-begin)*invstep), chi = (r2-begin)*invstep - k in [0,1):
+//   val = c0 + chi*(c1 + chi*(c2 + chi*c3)),  grad = 2*istep*(c1 + chi*(2*c2 + 3*c3*chi))
+// 3-point: the dv/d2v expressions of PAIR_INT2 (src/potaccess.h:345-349), c3 = 0.
+// 4-point: the Lagrange cubic of PAIR_INT3 (:385-405) through samples k-1..k+2 collected by powers of chi; the
+//          reference uses k = MAX(k,1), i.e. interval 0 evaluates the cubic of interval 1 at chi-1 -- that
+//          polynomial is re-expanded around chi here so that the device indexes every mode the same way.
+// spline : PAIR_INT_SP (:438-456) with a = 1-b collected by powers of b.
+static void coef(const HostTab &h, int k, int col, double c[4])
+{
+  const imdb200_pot_table *pt = h.pt;
+  const int nc = pt->ncols;
+  if (h.mode == IMDB200_INTERP_4POINT) {
+    const int kk = k < 1 ? 1 : k;
+    const double *t = h.y.data() + (size_t) (kk - 1) * nc + col;
+    const double p0 = t[0], p1 = t[nc], p2 = t[2 * nc], p3 = t[3 * nc];
+    c[0] = p1;
+    c[1] = -p0 / 3.0 - 0.5 * p1 + p2 - p3 / 6.0;
+    c[2] = 0.5 * p0 - p1 + 0.5 * p2;
+    c[3] = (p3 - p0) / 6.0 + 0.5 * (p1 - p2);
+    if (k < 1) {                                            // P(chi - 1)
+      const double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+      c[0] = a0 - a1 + a2 - a3;
+      c[1] = a1 - 2 * a2 + 3 * a3;
+      c[2] = a2 - 3 * a3;
+      c[3] = a3;
+    }
+  } else if (h.mode == IMDB200_INTERP_SPLINE) {
+    const double *t = h.y.data() + (size_t) k * nc + col, *t2 = h.y2.data() + (size_t) k * nc + col;
+    const double p1 = t[0], p2 = t[nc], d21 = t2[0], d22 = t2[nc];
+    const double s6 = pt->step[col] * pt->step[col] / 6.0;
+    c[0] = p1;
+    c[1] = (p2 - p1) - s6 * (2 * d21 + d22);
+    c[2] = 3 * s6 * d21;
+    c[3] = s6 * (d22 - d21);
+  } else {
+    const double *t = h.y.data() + (size_t) k * nc + col;
+    const double p0 = t[0], p1 = t[nc], p2 = t[2 * nc];
+    const double dv = p1 - p0, d2v = p2 - 2 * p1 + p0;
+    c[0] = p0;
+    c[1] = dv - 0.5 * d2v;
+    c[2] = 0.5 * d2v;
+    c[3] = 0.0;
+  }
 }
 
 template <typename T> static int upload(imdb200_sim *s, int slot, const std::vector<T> &h, const T **dev)
@@ -44,17 +123,20 @@ void tables_free(imdb200_sim *s)
   s->have_tabs = 0;
 }
 
-// (c0,c1) and c2 arrays of one table
-static void split_coefs(const imdb200_pot_table *pt, std::vector<double2> &ab, std::vector<double> &c)
+// (c0,c1), c2 and (cubic modes) (c2,c3) arrays of one table
+static void split_coefs(const HostTab &h, std::vector<double2> &ab, std::vector<double> &c, std::vector<double2> &cd)
 {
-  double c5[5];
+  const imdb200_pot_table *pt = h.pt;
+  double c4[4];
   ab.assign((size_t) pt->maxsteps * pt->ncols, make_double2(0.0, 0.0));
+  cd.assign((size_t) pt->maxsteps * pt->ncols, make_double2(0.0, 0.0));
   c.assign((((size_t) pt->maxsteps * pt->ncols + 1) / 2) * 2, 0.0);   // even length: staged 16 bytes at a time
   for (int k = 0; k < pt->maxsteps; k++)
     for (int col = 0; col < pt->ncols; col++) {
-      coef(pt, k, col, c5);
-      ab[(size_t) k * pt->ncols + col] = make_double2(c5[0], c5[1]);
-      c[(size_t) k * pt->ncols + col] = c5[2];
+      coef(h, k, col, c4);
+      ab[(size_t) k * pt->ncols + col] = make_double2(c4[0], c4[1]);
+      cd[(size_t) k * pt->ncols + col] = make_double2(c4[2], c4[3]);
+      c[(size_t) k * pt->ncols + col] = c4[2];
     }
 }
 
@@ -63,20 +145,26 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
 {
   if (!pair) return imdb_fail(IMDB200_ERR_ARG, "pair potential table is required");
   if ((embed == nullptr) != (rho == nullptr)) return imdb_fail(IMDB200_ERR_ARG, "EAM needs both embed and rho tables");
-  const int nt = s->cfg.ntypes;
+  const int nt = s->cfg.ntypes, mode = s->cfg.interpolation;
+  if (mode < IMDB200_INTERP_3POINT || mode > IMDB200_INTERP_SPLINE) return imdb_fail(IMDB200_ERR_ARG, "unknown interpolation %d", mode);
+  const bool cubic = mode != IMDB200_INTERP_3POINT;
   if (pair->ncols != nt * nt) return imdb_fail(IMDB200_ERR_ARG, "pair table has %d columns, need %d", pair->ncols, nt * nt);
   if (rho && (rho->ncols != nt * nt || embed->ncols != nt)) return imdb_fail(IMDB200_ERR_ARG, "EAM table column count mismatch");
   tables_free(s);
   DevTables &T = s->tabs;
   memset(&T, 0, sizeof(T));
   T.ntypes = nt;
+  T.cubic = cubic;
   T.have_eam = rho != nullptr;
   TRY(fill_meta(T.pair, pair));
-  std::vector<double2> ab; std::vector<double> c;
-  split_coefs(pair, ab, c);
+  HostTab hp, he, hr;
+  prepare(hp, pair, mode, 1);
+  std::vector<double2> ab, cd; std::vector<double> c;
+  split_coefs(hp, ab, c, cd);
   TRY(upload(s, 0, ab, &T.pairAB));
-  TRY(upload(s, 1, c, &T.pairC));
-  size_t bytes1 = (size_t) pair->maxsteps * pair->ncols * 24 + 8, bytes2 = 0;
+  if (cubic) TRY(upload(s, 1, cd, &T.pairCD)); else TRY(upload(s, 1, c, &T.pairC));
+  const size_t per1 = cubic ? 32 : 24;
+  size_t bytes1 = (size_t) pair->maxsteps * pair->ncols * per1 + 8, bytes2 = 0;
   // cellsz = max end of the radial tables (src/imd_potential.c:364, 406)
   double cz = 0.0;
   for (int col = 0; col < pair->ncols; col++) cz = cz > pair->end[col] ? cz : pair->end[col];
@@ -84,26 +172,38 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
     for (int col = 0; col < rho->ncols; col++) cz = cz > rho->end[col] ? cz : rho->end[col];
     TRY(fill_meta(T.embed, embed));
     TRY(fill_meta(T.rho, rho));
+    prepare(he, embed, mode, 0);
+    prepare(hr, rho, mode, 1);
     {
-      double c5[5];
-      std::vector<double> h((size_t) embed->maxsteps * embed->ncols * 6, 0.0);
+      // per (k, type): c0 c1 c2 c3 | g1 g2 g3 -  with F' = g1 + chi*(g2 + chi*g3)
+      double c4[4];
+      std::vector<double> h((size_t) embed->maxsteps * embed->ncols * 8, 0.0);
       for (int k = 0; k < embed->maxsteps; k++)
-        for (int col = 0; col < embed->ncols; col++) { coef(embed, k, col, c5); memcpy(&h[((size_t) k * embed->ncols + col) * 6], c5, 5 * sizeof(double)); }
+        for (int col = 0; col < embed->ncols; col++) {
+          coef(he, k, col, c4);
+          double *o = &h[((size_t) k * embed->ncols + col) * 8];
+          const double is2 = 2 * embed->invstep[col];
+          o[0] = c4[0]; o[1] = c4[1]; o[2] = c4[2]; o[3] = c4[3];
+          o[4] = is2 * c4[1]; o[5] = 2 * is2 * c4[2]; o[6] = 3 * is2 * c4[3];
+        }
       TRY(upload(s, 2, h, &T.embedVG));
     }
-    split_coefs(rho, ab, c);
+    split_coefs(hr, ab, c, cd);
     TRY(upload(s, 3, ab, &T.rhoAB));
-    TRY(upload(s, 4, c, &T.rhoC));
+    if (cubic) TRY(upload(s, 4, cd, &T.rhoCD)); else TRY(upload(s, 4, c, &T.rhoC));
     std::vector<double2> hh(ab.size());
+    std::vector<double> h3((ab.size() + 1) / 2 * 2, 0.0);
     for (int k = 0; k < rho->maxsteps; k++)
       for (int col = 0; col < rho->ncols; col++) {
         const size_t e = (size_t) k * rho->ncols + col;
-        // rho'/2 = istep*(c1 + 2*chi*c2): exact scalings of the products the reference forms
-        hh[e] = make_double2(rho->invstep[col] * ab[e].y, 2 * rho->invstep[col] * c[e]);
+        // rho'/2 = istep*(c1 + 2*chi*c2 + 3*chi^2*c3): exact scalings of the products the reference forms
+        hh[e] = make_double2(rho->invstep[col] * ab[e].y, 2 * rho->invstep[col] * cd[e].x);
+        h3[e] = 3 * rho->invstep[col] * cd[e].y;
       }
     TRY(upload(s, 5, hh, &T.rhoH));
-    bytes1 += (size_t) rho->maxsteps * rho->ncols * 24 + 8;
-    bytes2 = (size_t) rho->maxsteps * rho->ncols * 16;
+    if (cubic) TRY(upload(s, 7, h3, &T.rhoH3));
+    bytes1 += (size_t) rho->maxsteps * rho->ncols * per1 + 8;
+    bytes2 = (size_t) rho->maxsteps * rho->ncols * (cubic ? 24 : 16) + 8;
     // Shared grid: phi and rho use the same begin/invstep in every column, so one (k,chi)
     // serves both lookups of a pair in pass 1.  Inside `r2 <= end` / `r2 < end` the MIN(r2,end)
     // clamp of PAIR_INT2 is inactive, so differing ends do not matter.
@@ -111,14 +211,15 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
     for (int col = 0; col < pair->ncols; col++)
       if (pair->begin[col] != rho->begin[col] || pair->invstep[col] != rho->invstep[col]) T.shared_grid = 0;
   }
-  if (rho && nt == 1 && T.shared_grid) {
+  if (rho && nt == 1 && T.shared_grid && !cubic) {
+    // (the cubic modes need 4+4 coefficients = four 16-byte loads with or without fusing: they use the split arrays)
     const int nr = pair->maxsteps > rho->maxsteps ? pair->maxsteps : rho->maxsteps;
     std::vector<double2> f((size_t) nr * 3, make_double2(0.0, 0.0));
-    double c5[5];
+    double c4[4];
     for (int k = 0; k < nr; k++) {
       double pc[3] = {0, 0, 0}, rc[3] = {0, 0, 0};
-      if (k < pair->maxsteps) { coef(pair, k, 0, c5); pc[0] = c5[0]; pc[1] = c5[1]; pc[2] = c5[2]; }
-      if (k < rho->maxsteps) { coef(rho, k, 0, c5); rc[0] = c5[0]; rc[1] = c5[1]; rc[2] = c5[2]; }
+      if (k < pair->maxsteps) { coef(hp, k, 0, c4); pc[0] = c4[0]; pc[1] = c4[1]; pc[2] = c4[2]; }
+      if (k < rho->maxsteps) { coef(hr, k, 0, c4); rc[0] = c4[0]; rc[1] = c4[1]; rc[2] = c4[2]; }
       f[3 * (size_t) k] = make_double2(pc[0], pc[1]);
       f[3 * (size_t) k + 1] = make_double2(pc[2], rc[2]);
       f[3 * (size_t) k + 2] = make_double2(rc[0], rc[1]);
@@ -147,9 +248,15 @@ __global__ void k_pair_int(DevTables T, int which, int col, long n, const double
   tab_index(r2[i], m.begin[col], m.end[col], m.invstep[col], k, chi, sh);
   const size_t e = (size_t) k * m.ncols + col;
   if (which == TAB_EMBED) {
-    const double *v = T.embedVG + e * 6;
-    pot[i] = fma(chi, fma(chi, v[2], v[1]), v[0]);
-    grad[i] = fma(chi, v[4], v[3]);
+    const double *v = T.embedVG + e * 8;
+    pot[i] = fma(chi, fma(chi, fma(chi, v[3], v[2]), v[1]), v[0]);
+    grad[i] = fma(chi, fma(chi, v[6], v[5]), v[4]);
+  } else if (T.cubic) {
+    const double2 ab = which == TAB_PAIR ? T.pairAB[e] : T.rhoAB[e];
+    const double2 cd = which == TAB_PAIR ? T.pairCD[e] : T.rhoCD[e];
+    pot[i] = tab_val3(ab, cd, chi);
+    grad[i] = which == TAB_PAIR ? tab_grad3(ab, cd, chi, 2.0 * m.invstep[col])
+                                : 2.0 * fma(chi, fma(chi, T.rhoH3[e], T.rhoH[e].y), T.rhoH[e].x);
   } else {
     const double2 ab = which == TAB_PAIR ? T.pairAB[e] : T.rhoAB[e];
     const double c2 = which == TAB_PAIR ? T.pairC[e] : T.rhoC[e];

@@ -40,11 +40,20 @@ enum {
 
 enum { IMDB200_ENS_NVE = 0, IMDB200_ENS_NVT = 1 }; /* ensemble keyword, src/imd_param.c:377-444 */
 
+/* Table interpolation.  The reference fixes it at compile time (src/potaccess.h:24-36; make targets with
+ * `4point` or `spline` in their name, src/Makefile:1694-1701); here it is a run-time field of the config.
+ *   3POINT  PAIR_INT2   quadratic through samples k..k+2            (src/potaccess.h:323-354), the default
+ *   4POINT  PAIR_INT3   cubic through samples k-1..k+2, k >= 1      (src/potaccess.h:365-407)
+ *   SPLINE  PAIR_INT_SP cubic spline on table + second derivatives  (src/potaccess.h:418-457) */
+enum { IMDB200_INTERP_3POINT = 0, IMDB200_INTERP_4POINT = 1, IMDB200_INTERP_SPLINE = 2 };
+
 typedef struct imdb200_sim imdb200_sim;
 
 /* Mirrors pot_table_t (src/types.h:416-428): ncols columns interleaved row by row,
- * table[k*ncols+col], (maxsteps+2) rows allocated, the two pad rows already filled by
- * init_threepoint (src/imd_potential.c:1256-1272). */
+ * table[k*ncols+col], (maxsteps+2) rows allocated.  The pad rows behind len[col] (and, for splines, the
+ * second-derivative table) depend on the interpolation: imdb200_set_potentials recomputes them from the
+ * samples the way init_threepoint / init_fourpoint / init_spline do (src/imd_potential.c:1171-1272), so a
+ * table padded by any of them is accepted. */
 typedef struct {
   double *begin, *end, *step, *invstep;
   int *len;
@@ -70,6 +79,7 @@ typedef struct {
   double isq_tau_eta;      /* 1/tau_eta^2                                                  */
   int device;              /* CUDA device ordinal, -1: current device                      */
   int lanes_per_atom;      /* 0 = choose; else 1,2,4,8,16,32 lanes cooperate on one atom   */
+  int interpolation;       /* IMDB200_INTERP_*; what a `4point` / `spline` build of IMD selects */
 } imdb200_config;
 
 void        imdb200_default_config(imdb200_config *cfg);

@@ -146,6 +146,12 @@ static void b200_init(void)
   cfg.ensemble = (ensemble == ENS_NVT) ? IMDB200_ENS_NVT : IMDB200_ENS_NVE;
   if (ensemble != ENS_NVE && ensemble != ENS_NVT) error("imd_b200 supports ensemble nve and nvt");
   cfg.temperature = temperature; cfg.eta = eta; cfg.isq_tau_eta = isq_tau_eta;
+  /* `4point` / `spline` make targets (src/Makefile:1694-1701, src/potaccess.h:24-36) */
+#if defined(FOURPOINT)
+  cfg.interpolation = IMDB200_INTERP_4POINT;
+#elif defined(SPLINE)
+  cfg.interpolation = IMDB200_INTERP_SPLINE;
+#endif
   b200_check(imdb200_create(&cfg, &b200));
   /* pot_table_t (src/types.h:416-428) and imdb200_pot_table have the same layout */
 #ifdef EAM2

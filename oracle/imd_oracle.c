@@ -27,6 +27,7 @@ typedef struct { /* pot_table_t, src/types.h:416-428 */
   double *begin, *end, *step, *invstep;
   int *len, ncols, maxsteps;
   double *table;
+  double *table2;      /* second derivatives, SPLINE only (pot_table_t.table2, src/types.h:416-428) */
   int loaded;
 } ptab;
 
@@ -41,6 +42,7 @@ struct orc_sim {
   int margin_added;
   ptab tab[3];
   int default_fmt;
+  int interp;          /* ORC_INTERP_*: which PAIR_INT the build selects, src/potaccess.h:24-36 */
   /* atoms: [0,n) real, [n, n+ng) buffer-cell copies */
   long n, ng, cap;
   int *nummer, *sorte, *vsorte;
@@ -78,6 +80,51 @@ static void init_threepoint(ptab *pt)
     y[n * nc]       = 3 * y[(n - 1) * nc] - 3 * y[(n - 2) * nc] + y[(n - 3) * nc];
     y[(n + 1) * nc] = 6 * y[(n - 1) * nc] - 8 * y[(n - 2) * nc] + 3 * y[(n - 3) * nc];
   }
+}
+
+/* init_fourpoint, src/imd_potential.c:1171-1189 */
+static void init_fourpoint(ptab *pt)
+{
+  int col, nc = pt->ncols;
+  for (col = 0; col < nc; col++) {
+    double *y = pt->table + col;
+    int n = pt->len[col];
+    y[n * nc]       =  4 * y[(n - 1) * nc] -  6 * y[(n - 2) * nc] +  4 * y[(n - 3) * nc] -     y[(n - 4) * nc];
+    y[(n + 1) * nc] = 10 * y[(n - 1) * nc] - 20 * y[(n - 2) * nc] + 15 * y[(n - 3) * nc] - 4 * y[(n - 4) * nc];
+  }
+}
+
+/* init_spline, src/imd_potential.c:1197-1246 */
+static void init_spline(ptab *pt, int radial)
+{
+  int ncols = pt->ncols, size = pt->maxsteps + 2, col, n, i, k;
+  double p, qn, un, step, *u, *y, *y2;
+  pt->table2 = (double *) calloc((size_t) ncols * size, sizeof(double));
+  u = (double *) calloc((size_t) size, sizeof(double));
+  for (col = 0; col < ncols; col++) {
+    y2 = pt->table2 + col;
+    y = pt->table + col;
+    n = pt->len[col];
+    step = pt->step[col];
+    y2[0] = u[0] = 0;
+    for (i = 1; i < n - 1; i++) {
+      p = 0.5 * y2[(i - 1) * ncols] + 2.0;
+      y2[i * ncols] = -0.5 / p;
+      u[i] = (y[(i + 1) * ncols] - 2 * y[i * ncols] + y[(i - 1) * ncols]) / step;
+      u[i] = (6.0 * u[i] / (2 * step) - 0.5 * u[i - 1]) / p;
+    }
+    if (radial) {
+      qn = 0.5;
+      un = (3.0 / step) * (y[(n - 2) * ncols] - y[(n - 1) * ncols]) / step;
+    } else {
+      qn = un = 0.0;
+    }
+    y2[(n - 1) * ncols] = (un - qn * u[n - 2]) / (qn * y2[(n - 2) * ncols] + 1.0);
+    for (k = n - 2; k >= 0; k--) y2[k * ncols] = y2[k * ncols] * y2[(k + 1) * ncols] + u[k];
+    y[n * ncols] = 2 * y[(n - 1) * ncols] - y[(n - 2) * ncols] + step * step * y2[(n - 1) * ncols];
+    y2[n * ncols] = 2 * y2[(n - 1) * ncols] - y2[(n - 2) * ncols];
+  }
+  free(u);
 }
 
 /* read_pot_table1, src/imd_potential.c:297-376 */
@@ -183,7 +230,10 @@ int orc_read_table(orc_sim *s, int which, const char *path)
   rc = (format == 1) ? read_table1(s, pt, f, radial) : read_table2(s, pt, f, radial);
   fclose(f);
   if (rc) return -8;
-  init_threepoint(pt);
+  /* src/imd_potential.c:270-277 */
+  if (s->interp == ORC_INTERP_4POINT) init_fourpoint(pt);
+  else if (s->interp == ORC_INTERP_SPLINE) init_spline(pt, radial);
+  else init_threepoint(pt);
   pt->loaded = 1;
   return 0;
 }
@@ -212,11 +262,81 @@ static inline void pair_int2(const ptab *pt, int col, int inc, double r2, double
   *grad = 2 * istep * (dv + (chi - 0.5) * d2v);
 }
 
+/* PAIR_INT3, src/potaccess.h:365-407: cubic through the four samples k-1 .. k+2 */
+static inline void pair_int3(const ptab *pt, int col, int inc, double r2, double *pot, double *grad, int *is_short)
+{
+  double r2a, istep, chi, p0, p1, p2, p3;
+  double fac0, fac1, fac2, fac3, dfac0, dfac1, dfac2, dfac3;
+  const double *ptr;
+  int k;
+  r2a = MINV(r2, pt->end[col]);
+  r2a = r2a - pt->begin[col];
+  if (r2a < 0) { r2a = 0; *is_short = 1; }
+  istep = pt->invstep[col];
+  r2a = r2a * istep;
+  k = (int) (r2a);
+  if (k < 1) k = 1;
+  chi = r2a - k;
+  fac0 = -(1.0 / 6.0) * chi * (chi - 1.0) * (chi - 2.0);
+  fac1 = 0.5 * (chi * chi - 1.0) * (chi - 2.0);
+  fac2 = -0.5 * chi * (chi + 1.0) * (chi - 2.0);
+  fac3 = (1.0 / 6.0) * chi * (chi * chi - 1.0);
+  dfac0 = -(1.0 / 6.0) * ((3.0 * chi - 6.0) * chi + 2.0);
+  dfac1 = 0.5 * ((3.0 * chi - 4.0) * chi - 1.0);
+  dfac2 = -0.5 * ((3.0 * chi - 2.0) * chi - 2.0);
+  dfac3 = 1.0 / 6.0 * (3.0 * chi * chi - 1.0);
+  ptr = pt->table + (size_t) (k - 1) * inc + col;
+  p0 = *ptr; ptr += inc;
+  p1 = *ptr; ptr += inc;
+  p2 = *ptr; ptr += inc;
+  p3 = *ptr;
+  *pot = fac0 * p0 + fac1 * p1 + fac2 * p2 + fac3 * p3;
+  *grad = 2 * istep * (dfac0 * p0 + dfac1 * p1 + dfac2 * p2 + dfac3 * p3);
+}
+
+/* PAIR_INT_SP, src/potaccess.h:418-457: cubic spline on (table, table2) */
+static inline void pair_int_sp(const ptab *pt, int col, int inc, double r2, double *pot, double *grad, int *is_short)
+{
+  double r2a, a, b, a2, b2, istep, step, st6, p1, p2, d21, d22;
+  int k;
+  r2a = MINV(r2, pt->end[col]);
+  r2a = r2a - pt->begin[col];
+  if (r2a < 0) { r2a = 0; *is_short = 1; }
+  istep = pt->invstep[col];
+  step = pt->step[col];
+  r2a = r2a * istep;
+  k = (int) (r2a);
+  b = r2a - k;
+  a = 1.0 - b;
+  k = k * inc + col;
+  p1 = pt->table[k];
+  d21 = pt->table2[k];
+  k += inc;
+  p2 = pt->table[k];
+  d22 = pt->table2[k];
+  a2 = a * a - 1;
+  b2 = b * b - 1;
+  st6 = step / 6;
+  *pot = a * p1 + b * p2 + (a * a2 * d21 + b * b2 * d22) * st6 * step;
+  *grad = 2 * ((p2 - p1) * istep + ((3 * b2 + 2) * d22 - (3 * a2 + 2) * d21) * st6);
+}
+
+/* PAIR_INT as the build selects it (src/potaccess.h:24-36) */
+static inline void pair_int(const orc_sim *s, const ptab *pt, int col, int inc, double r2, double *pot, double *grad,
+                            int *is_short)
+{
+  if (s->interp == ORC_INTERP_4POINT) pair_int3(pt, col, inc, r2, pot, grad, is_short);
+  else if (s->interp == ORC_INTERP_SPLINE) pair_int_sp(pt, col, inc, r2, pot, grad, is_short);
+  else pair_int2(pt, col, inc, r2, pot, grad, is_short);
+}
+
 void orc_pair_int(const orc_sim *s, int which, int col, double r2, double *pot, double *grad, int *is_short)
 {
   int dummy = 0;
-  pair_int2(&s->tab[which], col, s->tab[which].ncols, r2, pot, grad, is_short ? is_short : &dummy);
+  pair_int(s, &s->tab[which], col, s->tab[which].ncols, r2, pot, grad, is_short ? is_short : &dummy);
 }
+
+void orc_set_interpolation(orc_sim *s, int mode) { s->interp = mode; }
 
 int orc_table_info(const orc_sim *s, int which, int col, double *begin, double *end, double *step, int *len)
 {
@@ -603,7 +723,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
         double pot, grad, rho_h = 0.0, fx, fy, fz;
         int jt = s->sorte[ja], col = it * nt + jt, col2 = jt * nt + it;
         if (r2 <= pair_pot->end[col]) { /* :493 */
-          pair_int2(pair_pot, col, inc, r2, &pot, &grad, &is_short);
+          pair_int(s, pair_pot, col, inc, r2, &pot, &grad, &is_short);
           s->tot_pot_energy += pot;
           fx = dx * grad; fy = dy * grad; fz = dz * grad;
           s->kraft[3 * ja] -= fx; s->kraft[3 * ja + 1] -= fy; s->kraft[3 * ja + 2] -= fz;
@@ -624,14 +744,14 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
         if (eam) { /* :586-611 */
           double dummy;
           if (r2 < rho_h_tab->end[col]) {
-            pair_int2(rho_h_tab, col, inc, r2, &rho_h, &dummy, &is_short);
+            pair_int(s, rho_h_tab, col, inc, r2, &rho_h, &dummy, &is_short);
             eam_r += rho_h;
           }
           if (it == jt) {
             if (r2 < rho_h_tab->end[col]) s->rho[ja] += rho_h;
           } else {
             if (r2 < rho_h_tab->end[col2]) {
-              pair_int2(rho_h_tab, col2, inc, r2, &rho_h, &dummy, &is_short);
+              pair_int(s, rho_h_tab, col2, inc, r2, &rho_h, &dummy, &is_short);
               s->rho[ja] += rho_h;
             }
           }
@@ -652,7 +772,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
       cellist *p = &s->cells[s->cnp[c]];
       for (i = 0; i < p->n; i++) {
         long ia = p->idx[i]; double pot;
-        pair_int2(embed_pot, s->sorte[ia], nt, s->rho[ia], &pot, &s->dF[ia], &idummy);
+        pair_int(s, embed_pot, s->sorte[ia], nt, s->rho[ia], &pot, &s->dF[ia], &idummy);
         s->poteng[ia] += pot;
         s->tot_pot_energy += pot;
       }
@@ -675,9 +795,9 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
           int jt = s->sorte[ja], col1 = jt * nt + it, col2 = it * nt + jt;
           if ((r2 < rho_h_tab->end[col1]) || (r2 < rho_h_tab->end[col2])) { /* :1172 */
             double dummy, rho_i_strich, rho_j_strich, grad, fx, fy, fz;
-            pair_int2(rho_h_tab, col1, inc, r2, &dummy, &rho_i_strich, &is_short);
+            pair_int(s, rho_h_tab, col1, inc, r2, &dummy, &rho_i_strich, &is_short);
             if (col1 == col2) rho_j_strich = rho_i_strich;
-            else pair_int2(rho_h_tab, col2, inc, r2, &dummy, &rho_j_strich, &is_short);
+            else pair_int(s, rho_h_tab, col2, inc, r2, &dummy, &rho_j_strich, &is_short);
             grad = 0.5 * (s->dF[ia] * rho_j_strich + s->dF[ja] * rho_i_strich); /* :1203 */
             fx = dx * grad; fy = dy * grad; fz = dz * grad;
             s->kraft[3 * ja] -= fx; s->kraft[3 * ja + 1] -= fy; s->kraft[3 * ja + 2] -= fz;
@@ -825,7 +945,7 @@ void orc_destroy(orc_sim *s)
   if (!s) return;
   for (w = 0; w < 3; w++) {
     free(s->tab[w].begin); free(s->tab[w].end); free(s->tab[w].step); free(s->tab[w].invstep);
-    free(s->tab[w].len); free(s->tab[w].table);
+    free(s->tab[w].len); free(s->tab[w].table); free(s->tab[w].table2);
   }
   free_cells(s);
   free(s->nummer); free(s->sorte); free(s->vsorte); free(s->masse); free(s->ort); free(s->impuls);

@@ -19,10 +19,16 @@ typedef struct orc_sim orc_sim;
 /* which table: 0 = pair_pot (radial), 1 = embed_pot (not radial), 2 = rho_h_tab (radial) */
 enum { ORC_PAIR = 0, ORC_EMBED = 1, ORC_RHO = 2 };
 enum { ORC_NVE = 0, ORC_NVT = 1 };
+/* table interpolation a reference build selects at compile time (src/potaccess.h:24-36, src/Makefile:1694-1701) */
+enum { ORC_INTERP_3POINT = 0, ORC_INTERP_4POINT = 1, ORC_INTERP_SPLINE = 2 };
 
 orc_sim *orc_create(int ntypes, const double box[9], const int pbc[3], double nbl_margin);
 void     orc_destroy(orc_sim *s);
 
+/* PAIR_INT2 (default), PAIR_INT3 (`4point` builds) or PAIR_INT_SP (`spline` builds); call before orc_read_table:
+ * the pad rows / second-derivative table depend on it (init_threepoint / init_fourpoint / init_spline,
+ * src/imd_potential.c:1171-1272) */
+void orc_set_interpolation(orc_sim *s, int mode);
 /* read_pot_table (src/imd_potential.c:161-282); returns 0 on success */
 int  orc_read_table(orc_sim *s, int which, const char *path);
 /* PAIR_INT2 / VAL_FUNC2 / DERIV_FUNC2 (src/potaccess.h:323-354, 465-495, 591-621) */

@@ -68,18 +68,24 @@ def lib():
         L.orc_get_nbl_pairs.restype = C.c_long
         L.orc_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.orc_tot_presstens.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_interpolation.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
 
+# table interpolation of the reference build being mirrored (src/potaccess.h:24-36)
+INTERP = {"3point": 0, "4point": 1, "spline": 2}
+
+
 class OracleIMD:
     def __init__(self, ntypes, box, pbc=(1, 1, 1), nbl_margin=0.4, pair=None, embed=None, rho=None,
-                 default_fmt=1):
+                 default_fmt=1, interp="3point"):
         L = lib()
         b = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(9))
         p = np.ascontiguousarray(np.asarray(pbc, dtype=np.int32))
         self.h = L.orc_create(int(ntypes), _p(b, C.c_double), _p(p, C.c_int), float(nbl_margin))
         self.press = False
+        L.orc_set_interpolation(self.h, INTERP[interp] if isinstance(interp, str) else int(interp))
         for which, path in ((PAIR, pair), (EMBED, embed), (RHO, rho)):
             if path:
                 rc = L.orc_read_table(self.h, which, os.fspath(path).encode())

@@ -42,6 +42,8 @@ def make_sim(factory, g, tabdir, **kw):
     ens = str(g["ensemble"])
     common = dict(pbc=tuple(int(x) for x in g["pbc"]), nbl_margin=0.4, pair=paths["pair"],
                   embed=paths.get("embed"), rho=paths.get("rho"))
+    if "interp" in g and str(g["interp"]) != "3point":     # fixture of a `4point` / `spline` reference build
+        common["interp"] = str(g["interp"])
     integ = dict(ensemble=ens, timestep=float(g["timestep"]), temperature=float(g["temperature"]),
                  eta=float(g["eta0"]), isq_tau_eta=float(g["isq_tau_eta"]))
     try:

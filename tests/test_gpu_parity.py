@@ -9,6 +9,8 @@ from imd_b200 import synth
 pytestmark = pytest.mark.gpu
 
 CASES = ["cu_nve", "nial_nvt", "lj_nve", "cu_slab", "cu_long"]
+# fixtures of the reference's `4point` and `spline` builds (cubic table interpolation)
+CUBIC_CASES = ["cu_4point", "cu_spline", "nial_spline"]
 
 
 @pytest.fixture(scope="module")
@@ -32,11 +34,39 @@ def test_cuda_matches_reference_fixture(api, name, lanes, tmp_path):
     sim.close()
 
 
-def test_cuda_potaccess_known_answers(api, tmp_path):
-    """Device table lookup against PAIR_INT2 known answers from the reference macro."""
-    g = common.load_golden("potaccess")
+@pytest.mark.parametrize("lanes", [1, 8])
+@pytest.mark.parametrize("name", CUBIC_CASES)
+def test_cuda_cubic_interpolation_matches_reference_fixture(api, name, lanes, tmp_path):
+    """IMDB200_INTERP_4POINT / _SPLINE against the reference's `4point` / `spline` builds (PAIR_INT3, PAIR_INT_SP,
+    src/potaccess.h:365-457; pad rows and spline second derivatives recomputed in tables.cu)."""
+    g = common.load_golden(name)
+    sim = common.make_sim(api.IMDB200, g, str(tmp_path), lanes_per_atom=lanes)
+    out = common.run_protocol(sim, g)
+    errs = common.compare(out, g, full_list=True, rtol=1e-10, traj_rtol=1e-8)
+    print(name, lanes, {k: f"{v:.1e}" for k, v in errs.items()})
+    sim.close()
+
+
+def test_cuda_cubic_run_loop_equals_stepwise_calls(api, tmp_path):
+    """imdb200_run (fused integrator) and the separate calls stay bit-identical in the cubic kernels too."""
+    g = common.load_golden("cu_spline")
+    sims = [common.make_sim(api.IMDB200, g, str(tmp_path / n)) for n in ("a", "b")]
+    sims[0].run(12)
+    for s in range(12):
+        sims[1].calc_forces(s); sims[1].move_atoms(); sims[1].check_nblist()
+    a, b = sims[0].atoms(), sims[1].atoms()
+    assert np.array_equal(a["ort"], b["ort"]) and np.array_equal(a["impuls"], b["impuls"])
+    for s_ in sims:
+        s_.close()
+
+
+@pytest.mark.parametrize("name", ["potaccess", "potaccess_4point", "potaccess_spline"])
+def test_cuda_potaccess_known_answers(api, name, tmp_path):
+    """Device table lookup against PAIR_INT2 / PAIR_INT3 / PAIR_INT_SP known answers from the reference macros."""
+    g = common.load_golden(name)
     paths = common.write_tables(g, str(tmp_path))
-    sim = api.IMDB200(2, np.eye(3) * 20.0, pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
+    sim = api.IMDB200(2, np.eye(3) * 20.0, pair=paths["pair"], embed=paths["embed"], rho=paths["rho"],
+                      interp=str(g["interp"]) if "interp" in g else "3point")
     for key in g:
         if not key.startswith("x:"):
             continue

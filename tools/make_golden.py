@@ -41,6 +41,13 @@ CASES = {
     "cu_slab": dict(kind="cu", ncell=(5, 5, 4), ensemble="nve", starttemp=0.05, warm=20, nsteps=8,
                     record=[0, 7], press=False, variant="eam", extra=dict(pbc_dirs=[1, 1, 0])),
     # non-cubic box, more cells, longer run with several rebuilds
+    # `4point` / `spline` reference builds (cubic table interpolation, src/potaccess.h:365-457)
+    "cu_4point": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=40, nsteps=16,
+                      record=[0, 15], press=True, variant="eam_4point", interp="4point"),
+    "nial_spline": dict(kind="nial", ncell=(5, 5, 5), ensemble="nvt", starttemp=0.06, warm=40, nsteps=16,
+                        record=[0, 15], press=True, variant="eam_spline", interp="spline"),
+    "cu_spline": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=40, nsteps=16,
+                      record=[0, 15], press=False, variant="eam_spline", interp="spline"),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
 }
@@ -77,6 +84,7 @@ def make_case(name, c):
     g = dict(table_arrays(tabs))
     g["ntypes"] = ntypes
     g["ensemble"] = c["ensemble"]
+    g["interp"] = c.get("interp", "3point")
     g["press"] = int(c["press"])
     g["nsteps"] = c["nsteps"]
     g["record"] = np.array(c["record"])
@@ -114,8 +122,9 @@ def make_case(name, c):
           f"{out['nbl_count']} list builds, {os.path.getsize(path) / 1024:.0f} kB")
 
 
-def make_potaccess():
-    """Known answers of PAIR_INT2 through the reference's own macro (src/potaccess.h:323-354)."""
+def make_potaccess(variant="eam", name="potaccess"):
+    """Known answers of PAIR_INT2 / PAIR_INT3 / PAIR_INT_SP through the reference's own macros
+    (src/potaccess.h:323-457), as selected by the build."""
     tmp = tempfile.mkdtemp(prefix="gold_pot")
     tabs = synth.make_eam_tables(tmp, "nial", nr=601, nrho=801)
     p = synth.nial_param(tmp, ncell=(5, 5, 5), tables=tabs)
@@ -124,7 +133,7 @@ def make_potaccess():
 import sys, pickle, numpy as np
 sys.path.insert(0, {ROOT!r})
 from oracle import ref_driver as rd
-sim = rd.RefIMD('eam', {p!r})
+sim = rd.RefIMD({variant!r}, {p!r})
 rng = np.random.default_rng(7)
 out = {{}}
 for which, ncol, lo, hi in ((0, 4, 0.5, 31.0), (2, 4, 0.5, 31.0), (1, 2, -1.0, 45.0)):
@@ -138,16 +147,18 @@ pickle.dump(out, open({os.path.join(tmp, 'pa.pkl')!r}, 'wb'))
     out = pickle.load(open(os.path.join(tmp, "pa.pkl"), "rb"))
     g = dict(table_arrays(tabs))
     g["ntypes"] = 2
+    g["interp"] = {"eam": "3point", "eam_4point": "4point", "eam_spline": "spline"}[variant]
     for (which, col), (x, v, gr) in out.items():
         g[f"x:{which}:{col}"] = x; g[f"v:{which}:{col}"] = v; g[f"g:{which}:{col}"] = gr
-    np.savez_compressed(os.path.join(GOLD, "potaccess.npz"), **g)
-    print("potaccess: done")
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **g)
+    print(name + ": done")
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES) + ["potaccess"]
+    POT = {"potaccess": "eam", "potaccess_4point": "eam_4point", "potaccess_spline": "eam_spline"}
+    names = sys.argv[1:] or list(CASES) + list(POT)
     for n in names:
-        if n == "potaccess":
-            make_potaccess()
+        if n in POT:
+            make_potaccess(POT[n], n)
         else:
             make_case(n, CASES[n])
