@@ -26,6 +26,7 @@
 #include <nccl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 // ---- NCCL binding ----------------------------------------------------------------------------------------
@@ -125,35 +126,70 @@ int comm_plan(imdb200_sim *s)
   for (int d = 0; d < 27; d++) {
     DirPlan &D = s->dir[d];
     memset(&D, 0, sizeof(D));
-    D.peer = -1; D.scell_off = -1;
-    if (d == 13 || peers[d] < 0) continue;
-    const int sg[3] = {d % 3 - 1, (d / 3) % 3 - 1, d / 9 - 1};
-    D.peer = peers[d];
-    const int code = codes[d];
-    const bool self = D.peer == s->rank;
-    int lo[3], hi[3];
-    for (int a = 0; a < 3; a++) axis_range(sg[a], g.cdim[a], &lo[a], &hi[a]);
-    D.gcell_off = (int) gc.size();
-    if (!self) D.scell_off = (int) sc.size();
-    for (int i = lo[0]; i <= hi[0]; i++)
-      for (int j = lo[1]; j <= hi[1]; j++)
-        for (int k = lo[2]; k <= hi[2]; k++) {
-          const int c[3] = {i, j, k};
-          int src[3], snd[3];
-          for (int a = 0; a < 3; a++) {
-            // receive cell -> its source on the neighbour; owned cell sent towards d
-            src[a] = sg[a] == 0 ? c[a] : (sg[a] < 0 ? g.cdim[a] - 2 : 1);
-            snd[a] = sg[a] == 0 ? c[a] : (sg[a] < 0 ? 1 : g.cdim[a] - 2);
+    D.peer = (d == 13) ? -1 : peers[d];
+    D.scell_off = -1;
+  }
+  // Receive and send regions are laid out PEER-major so that everything exchanged with one neighbour rank is one
+  // contiguous slice = one message per peer and exchange (up to 26 directions share 1..7 peers on small process
+  // grids; a message costs ~6 us whatever its size).  Within a peer the receive regions follow ascending
+  // direction and the send regions descending direction: what is sent towards d arrives as direction 26-d.
+  std::vector<int> rorder, sorder;
+  for (int d = 0; d < 27; d++) if (s->dir[d].peer >= 0) { rorder.push_back(d); sorder.push_back(d); }
+  std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) {
+    return s->dir[a].peer != s->dir[b].peer ? s->dir[a].peer < s->dir[b].peer : a < b; });
+  std::stable_sort(sorder.begin(), sorder.end(), [&](int a, int b) {
+    return s->dir[a].peer != s->dir[b].peer ? s->dir[a].peer < s->dir[b].peer : a > b; });
+  for (int pass = 0; pass < 2; pass++) {
+    for (int d : (pass == 0 ? rorder : sorder)) {
+      DirPlan &D = s->dir[d];
+      const int sg[3] = {d % 3 - 1, (d / 3) % 3 - 1, d / 9 - 1};
+      const int code = codes[d];
+      const bool self = D.peer == s->rank;
+      if (pass == 1 && self) continue;
+      int lo[3], hi[3];
+      for (int a = 0; a < 3; a++) axis_range(sg[a], g.cdim[a], &lo[a], &hi[a]);
+      if (pass == 0) D.gcell_off = (int) gc.size(); else D.scell_off = (int) sc.size();
+      for (int i = lo[0]; i <= hi[0]; i++)
+        for (int j = lo[1]; j <= hi[1]; j++)
+          for (int k = lo[2]; k <= hi[2]; k++) {
+            const int c[3] = {i, j, k};
+            int src[3], snd[3];
+            for (int a = 0; a < 3; a++) {
+              // receive cell -> its source on the neighbour; owned cell sent towards d
+              src[a] = sg[a] == 0 ? c[a] : (sg[a] < 0 ? g.cdim[a] - 2 : 1);
+              snd[a] = sg[a] == 0 ? c[a] : (sg[a] < 0 ? 1 : g.cdim[a] - 2);
+            }
+            if (pass == 0) {
+              GhostCell x;
+              x.dst = (i * g.cdim[1] + j) * g.cdim[2] + k;
+              x.src = self ? (src[0] * g.cdim[1] + src[1]) * g.cdim[2] + src[2] : -1;
+              x.code = code;
+              x.peer = D.peer;
+              gc.push_back(x);
+            } else {
+              sc.push_back((snd[0] * g.cdim[1] + snd[1]) * g.cdim[2] + snd[2]);
+            }
           }
-          GhostCell x;
-          x.dst = (i * g.cdim[1] + j) * g.cdim[2] + k;
-          x.src = self ? (src[0] * g.cdim[1] + src[1]) * g.cdim[2] + src[2] : -1;
-          x.code = code;
-          x.peer = D.peer;
-          gc.push_back(x);
-          if (!self) sc.push_back((snd[0] * g.cdim[1] + snd[1]) * g.cdim[2] + snd[2]);
-        }
-    D.ncells = (int) gc.size() - D.gcell_off;
+      if (pass == 0) D.ncells = (int) gc.size() - D.gcell_off;
+    }
+  }
+  // one PeerPlan per neighbour rank: the cell slices are fixed by the grid, the atom slices are set at every rebuild
+  s->n_peers = 0;
+  for (int d : rorder) {
+    const DirPlan &D = s->dir[d];
+    if (D.peer == s->rank) continue;
+    if (s->n_peers == 0 || s->peers[s->n_peers - 1].peer != D.peer) {
+      PeerPlan &P = s->peers[s->n_peers++];
+      memset(&P, 0, sizeof(P));
+      P.peer = D.peer; P.gcell_off = D.gcell_off; P.scell_off = -1;
+    }
+    s->peers[s->n_peers - 1].ncells += D.ncells;
+  }
+  for (int d : sorder) {
+    const DirPlan &D = s->dir[d];
+    if (D.peer == s->rank) continue;
+    for (int q = 0; q < s->n_peers; q++)
+      if (s->peers[q].peer == D.peer && s->peers[q].scell_off < 0) s->peers[q].scell_off = D.scell_off;
   }
   void *old[] = {s->gcells, s->gcount, s->gstart, s->scells, s->scount, s->sstart};
   for (void *p : old) if (p) cudaFree(p);
@@ -266,22 +302,16 @@ __global__ void k_reverse_unpack(double *field, int ncomp, long stride, const in
 }
 
 // ---- exchanges ----------------------------------------------------------------------------------------------
-// forward: owner -> images.  One group: sends in ascending direction, receives in descending direction,
-// so that between any two ranks the k-th send meets the k-th receive (direction d arrives as 26-d).
+// forward: owner -> images.  One group, one send and one receive per neighbour rank (see comm_plan).
 template <typename T>
 static int exchange_forward(imdb200_sim *s, const T *sendbuf, T *recv_base, ncclDataType_t ty, int per_elem)
 {
   ncclComm_t c = (ncclComm_t) s->nccl_comm;
   NCCL_TRY(g_nccl.GroupStart());
-  for (int d = 0; d < 27; d++) {
-    const DirPlan &D = s->dir[d];
-    if (D.peer < 0 || D.peer == s->rank || D.send_cnt == 0) continue;
-    NCCL_TRY(g_nccl.Send(sendbuf + (size_t) D.send_off * per_elem, (size_t) D.send_cnt * per_elem, ty, D.peer, c, s->stream));
-  }
-  for (int d = 26; d >= 0; d--) {
-    const DirPlan &D = s->dir[d];
-    if (D.peer < 0 || D.peer == s->rank || D.recv_cnt == 0) continue;
-    NCCL_TRY(g_nccl.Recv(recv_base + (size_t) D.recv_off * per_elem, (size_t) D.recv_cnt * per_elem, ty, D.peer, c, s->stream));
+  for (int q = 0; q < s->n_peers; q++) {
+    const PeerPlan &P = s->peers[q];
+    if (P.send_cnt) NCCL_TRY(g_nccl.Send(sendbuf + (size_t) P.send_off * per_elem, (size_t) P.send_cnt * per_elem, ty, P.peer, c, s->stream));
+    if (P.recv_cnt) NCCL_TRY(g_nccl.Recv(recv_base + (size_t) P.recv_off * per_elem, (size_t) P.recv_cnt * per_elem, ty, P.peer, c, s->stream));
   }
   NCCL_TRY(g_nccl.GroupEnd());
   return 0;
@@ -312,6 +342,7 @@ int comm_setup_ghosts(imdb200_sim *s)
   CUDA_TRY(cudaMemsetAsync(s->cell_code, 0, (g.nall + NBIN_EXTRA) * sizeof(int), st));
   s->n_ghost = 0; s->n_send = 0;
   for (int d = 0; d < 27; d++) { s->dir[d].recv_off = s->dir[d].recv_cnt = s->dir[d].send_off = s->dir[d].send_cnt = 0; }
+  for (int q = 0; q < s->n_peers; q++) { s->peers[q].recv_off = s->peers[q].recv_cnt = s->peers[q].send_off = s->peers[q].send_cnt = 0; }
   if (!s->n_gcells) return 0;
   const int ng = s->n_gcells, ns = s->n_scells;
   CUDA_TRY(cudaMemsetAsync(s->gcount, 0, (ng + 1) * sizeof(int), st));
@@ -322,15 +353,10 @@ int comm_setup_ghosts(imdb200_sim *s)
     k_cell_counts<<<cdiv(ns, 256), 256, 0, st>>>(s->scells, ns, s->cell_count, s->scount); LAUNCH_CHECK();
     ncclComm_t c = (ncclComm_t) s->nccl_comm;
     NCCL_TRY(g_nccl.GroupStart());
-    for (int d = 0; d < 27; d++) {
-      const DirPlan &D = s->dir[d];
-      if (D.peer < 0 || D.peer == s->rank) continue;
-      NCCL_TRY(g_nccl.Send(s->scount + D.scell_off, D.ncells, ncclInt32, D.peer, c, st));
-    }
-    for (int d = 26; d >= 0; d--) {
-      const DirPlan &D = s->dir[d];
-      if (D.peer < 0 || D.peer == s->rank) continue;
-      NCCL_TRY(g_nccl.Recv(s->gcount + D.gcell_off, D.ncells, ncclInt32, D.peer, c, st));
+    for (int q = 0; q < s->n_peers; q++) {
+      const PeerPlan &P = s->peers[q];
+      NCCL_TRY(g_nccl.Send(s->scount + P.scell_off, P.ncells, ncclInt32, P.peer, c, st));
+      NCCL_TRY(g_nccl.Recv(s->gcount + P.gcell_off, P.ncells, ncclInt32, P.peer, c, st));
     }
     NCCL_TRY(g_nccl.GroupEnd());
     TRY(scan_exclusive(s, s->scount, s->sstart, ns + 1, nullptr));
@@ -348,6 +374,11 @@ int comm_setup_ghosts(imdb200_sim *s)
     D.recv_off = h_g[D.gcell_off];
     D.recv_cnt = h_g[D.gcell_off + D.ncells] - D.recv_off;
     if (D.scell_off >= 0) { D.send_off = h_s[D.scell_off]; D.send_cnt = h_s[D.scell_off + D.ncells] - D.send_off; }
+  }
+  for (int q = 0; q < s->n_peers; q++) {
+    PeerPlan &P = s->peers[q];
+    P.recv_off = h_g[P.gcell_off]; P.recv_cnt = h_g[P.gcell_off + P.ncells] - P.recv_off;
+    P.send_off = h_s[P.scell_off]; P.send_cnt = h_s[P.scell_off + P.ncells] - P.send_off;
   }
   TRY(cells_ensure_capacity(s, n + s->n_ghost + 1));
   TRY(ensure_send_capacity(s, s->n_send));
@@ -409,15 +440,10 @@ int comm_reverse_add(imdb200_sim *s, double *field, int ncomp, long stride)
     // the roles swap: every receive slice of the forward exchange is now sent, component by component
     NCCL_TRY(g_nccl.GroupStart());
     for (int comp = 0; comp < ncomp; comp++) {
-      for (int d = 0; d < 27; d++) {
-        const DirPlan &D = s->dir[d];
-        if (D.peer < 0 || D.peer == s->rank || D.recv_cnt == 0) continue;
-        NCCL_TRY(g_nccl.Send(field + comp * stride + s->n_own + D.recv_off, D.recv_cnt, ncclFloat64, D.peer, c, st));
-      }
-      for (int d = 26; d >= 0; d--) {
-        const DirPlan &D = s->dir[d];
-        if (D.peer < 0 || D.peer == s->rank || D.send_cnt == 0) continue;
-        NCCL_TRY(g_nccl.Recv(s->sendbuf1 + comp * s->n_send + D.send_off, D.send_cnt, ncclFloat64, D.peer, c, st));
+      for (int q = 0; q < s->n_peers; q++) {
+        const PeerPlan &P = s->peers[q];
+        if (P.recv_cnt) NCCL_TRY(g_nccl.Send(field + comp * stride + s->n_own + P.recv_off, P.recv_cnt, ncclFloat64, P.peer, c, st));
+        if (P.send_cnt) NCCL_TRY(g_nccl.Recv(s->sendbuf1 + comp * s->n_send + P.send_off, P.send_cnt, ncclFloat64, P.peer, c, st));
       }
     }
     NCCL_TRY(g_nccl.GroupEnd());

@@ -90,6 +90,15 @@ struct DirPlan {
   int send_off, send_cnt;         // slice of send_idx / the send buffers
 };
 
+// Everything exchanged with one neighbour rank: the regions of all directions that lead to it are adjacent
+// (comm_plan), so each exchange is one message per peer.
+struct PeerPlan {
+  int peer;
+  int ncells, gcell_off, scell_off;   // slices of gcells / scells (fixed by the cell grid)
+  int recv_off, recv_cnt;             // ghost atoms [n_own+recv_off, +recv_cnt) after a rebuild
+  int send_off, send_cnt;             // slice of send_idx / the send buffers
+};
+
 struct imdb200_sim {
   imdb200_config cfg;
   Geom geom;
@@ -120,6 +129,7 @@ struct imdb200_sim {
   int *scan_tmp;
   // halo plan (comm.cu)
   DirPlan dir[27];
+  PeerPlan peers[26]; int n_peers;
   int *scells; int n_scells;      // owned cells to send, direction-major
   int *scount, *sstart;
   int *send_idx; long n_send, cap_send;
