@@ -273,7 +273,8 @@ def ours(args):
     num = num + rank * n
     box = box1 * np.array(grid)[:, None]
     kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"],
-              rho=tabs["atomic_e-density_file"], ensemble="nve", timestep=0.001, device=local, nbl_size=1.2)
+              rho=tabs["atomic_e-density_file"], ensemble="nve", timestep=0.001, device=local, nbl_size=1.2,
+              lanes_per_atom=args.lanes)
     if world > 1:
         sim = idist.create(1, box, cpu_dim=grid, **kw)      # halo exchange: NCCL p2p inside the library
     else:
@@ -383,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ncell", type=int, default=100, help="fcc unit cells per edge per GPU (100 -> 4M atoms)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes_per_atom of the force kernels (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

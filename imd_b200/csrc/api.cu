@@ -98,6 +98,7 @@ void imdb200_destroy(imdb200_sim *s)
   cudaStreamSynchronize(s->stream);
   tables_free(s);
   comm_free(s);
+  forces_free_textures(s);
   void *ptrs[] = {s->posdf, s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF,
                   s->nblpos, s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start,
                   s->cell_fill, s->cell_code, s->gsrc, s->ghost_num, s->ghost_raw, s->scan_tmp, s->nbl, s->nnb,

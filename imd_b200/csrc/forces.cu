@@ -21,6 +21,8 @@
 // Thread mapping: L lanes cooperate on one atom (L = 1 for big systems, up to 32 for small ones); lane l
 // takes list entries l, l+L, ... and the partial sums are combined with xor shuffles.
 #include "internal.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 // entries per block of the software-pipelined list walk, and threads per CTA (one persistent CTA per SM)
 #ifndef IMDB_DEPTH
@@ -30,6 +32,27 @@
 #define IMDB_NT 640
 #endif
 #define FDEPTH IMDB_DEPTH
+// pass 2 has its own block depth and CTA size
+#ifndef IMDB_DEPTH2
+#define IMDB_DEPTH2 4
+#endif
+#ifndef IMDB_NT2
+#define IMDB_NT2 640
+#endif
+#define FDEPTH2 IMDB_DEPTH2
+// Entries per block whose position gather goes through the TEX front end of the L1 (tex1Dfetch on a linear int4
+// texture over the same records) instead of the LSU one (ld.global).  The L1 data stage has one pipe per front end;
+// pass 1 keeps the LSU pipe busy with the table look-ups in shared memory, so all its gathers go through TEX
+// (1.62 -> 1.33 ms at 4 M atoms), pass 2 has little table traffic and splits its gathers between the two pipes.
+#ifndef IMDB_TEX1
+#define IMDB_TEX1 4
+#endif
+#ifndef IMDB_TEX2
+#define IMDB_TEX2 2
+#endif
+#ifndef IMDB_TEX1_SKIP
+#define IMDB_TEX1_SKIP 4
+#endif
 // This file is compiled twice (Makefile): IMDB_CUBIC=0 holds the quadratic (PAIR_INT2) kernels and everything the
 // two builds share, IMDB_CUBIC=1 the same kernels for the cubic table modes (PAIR_INT3 / PAIR_INT_SP, one more
 // coefficient per lookup).  The kernels carry the flag as a template argument so that their symbols differ.
@@ -49,6 +72,8 @@ struct FArgs {
   double4 *frc;
   double *rho, *dF;
   const int *nbl;
+  cudaTextureObject_t tpos, tposdf;   // the same atom records as linear int4 textures (two texels per atom)
+  int use_tex;                        // 0: the atom arrays exceed the 1-D linear texture limit, every gather on the LSU path
   const unsigned long long *nnbc;
   int cls_shift;                 // NBL_CBITS * (highest skin class to walk)
   long n_own;
@@ -63,6 +88,12 @@ struct FArgs {
   unsigned long long *maxd2;
   double dt; int nvt;
 };
+
+__device__ __forceinline__ double4 ld_atom_tex(cudaTextureObject_t t, int j)
+{
+  const int4 a = tex1Dfetch<int4>(t, 2 * j), b = tex1Dfetch<int4>(t, 2 * j + 1);
+  return make_double4(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(b.y, b.x), __hiloint2double(b.w, b.z));
+}
 
 template <int L> __device__ __forceinline__ double lanes_sum(double v)
 {
@@ -150,7 +181,10 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
       for (int m = sub; m < nn; m += FDEPTH * L, row += FDEPTH * 32) {
         double4 xq[FDEPTH];
 #pragma unroll
-        for (int d = 0; d < FDEPTH; d++) xq[d] = ld_atom(a.pos + (jq[d] >= 0 ? jq[d] : (int) i));
+        for (int d = 0; d < FDEPTH; d++) {
+          const int j = jq[d] >= 0 ? jq[d] : (int) i;
+          xq[d] = (d < IMDB_TEX1 && a.use_tex) ? ld_atom_tex(a.tpos, j) : ld_atom(a.pos + j);
+        }
 #pragma unroll
         for (int d = 0; d < FDEPTH; d++) jq[d] = (m + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
 #pragma unroll
@@ -272,22 +306,22 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       const double dFi = MULTI ? a.dF[i] : xi.w;
       const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
-      int jq[FDEPTH];                                    // software pipeline as in pass 1
+      int jq[FDEPTH2];                                    // software pipeline as in pass 1
 #pragma unroll
-      for (int d = 0; d < FDEPTH; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
-      for (int m = sub; m < nn; m += FDEPTH * L, row += FDEPTH * 32) {
-        double4 xq[FDEPTH];
-        int jc[MULTI ? FDEPTH : 1];
+      for (int d = 0; d < FDEPTH2; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
+      for (int m = sub; m < nn; m += FDEPTH2 * L, row += FDEPTH2 * 32) {
+        double4 xq[FDEPTH2];
+        int jc[MULTI ? FDEPTH2 : 1];
 #pragma unroll
-        for (int d = 0; d < FDEPTH; d++) {
+        for (int d = 0; d < FDEPTH2; d++) {
           const int j = jq[d] >= 0 ? jq[d] : (int) i;
-          xq[d] = ld_atom(gat + j);
+          xq[d] = (d < IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j);
           if (MULTI) jc[d] = j;
         }
 #pragma unroll
-        for (int d = 0; d < FDEPTH; d++) jq[d] = (m + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
+        for (int d = 0; d < FDEPTH2; d++) jq[d] = (m + (FDEPTH2 + d) * L < nn) ? __ldcs(row + (FDEPTH2 + d) * 32) : -1;
 #pragma unroll
-        for (int d = 0; d < FDEPTH; d++) {
+        for (int d = 0; d < FDEPTH2; d++) {
         if (m + d * L >= nn) break;
         const double4 xj = xq[d];
         const int j = MULTI ? jc[d] : 0;
@@ -415,9 +449,49 @@ static int skin_class(const imdb200_sim *s)
   return c < NBL_CLASSES ? c : NBL_CLASSES;
 }
 
+#if !IMDB_CUBIC
+// The atom records as linear textures.  The L1 of an SM has two front ends, LSU (ld.global, shared memory) and TEX;
+// the force passes saturate the LSU data pipe with table look-ups + gathers while TEX idles, so a fixed share of
+// the gathers of every block goes through TEX instead (profiles/README.md, "two pipes").
+static int tex_make(cudaTextureObject_t *t, const void **cur, const void *ptr, size_t bytes, size_t *cur_bytes)
+{
+  if (*cur == ptr && *cur_bytes == bytes) return 0;
+  if (*cur) cudaDestroyTextureObject(*t);
+  *cur = nullptr; *t = 0;
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = const_cast<void *>(ptr);
+  rd.res.linear.desc = cudaCreateChannelDesc<int4>(); rd.res.linear.sizeInBytes = bytes;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.readMode = cudaReadModeElementType;
+  CUDA_TRY(cudaCreateTextureObject(t, &rd, &td, nullptr));
+  *cur = ptr; *cur_bytes = bytes;
+  return 0;
+}
+
+int forces_textures(imdb200_sim *s)
+{
+  static size_t max_texels = 0;
+  if (!max_texels) { cudaDeviceProp p; CUDA_TRY(cudaGetDeviceProperties(&p, s->cfg.device)); max_texels = (size_t) p.maxTexture1DLinear; }
+  const size_t bytes = (size_t) s->cap_atoms * sizeof(double4);
+  s->tex_ok = bytes / 16 <= max_texels;          // beyond the 1-D linear texture limit every gather stays on the LSU path
+  if (!s->tex_ok) return 0;
+  TRY(tex_make(&s->tex_pos, &s->tex_pos_ptr, s->pos, bytes, &s->tex_pos_bytes));
+  TRY(tex_make(&s->tex_posdf, &s->tex_posdf_ptr, s->posdf, bytes, &s->tex_posdf_bytes));
+  return 0;
+}
+
+void forces_free_textures(imdb200_sim *s)
+{
+  if (s->tex_pos_ptr) cudaDestroyTextureObject(s->tex_pos);
+  if (s->tex_posdf_ptr) cudaDestroyTextureObject(s->tex_posdf);
+  s->tex_pos_ptr = s->tex_posdf_ptr = nullptr;
+}
+#endif
+
 static FArgs make_args(imdb200_sim *s)
 {
   FArgs a;
+  a.tpos = s->tex_pos; a.tposdf = s->tex_posdf; a.use_tex = s->tex_ok;
   a.pos = s->pos; a.posdf = s->posdf; a.frc = s->frc; a.rho = s->rho; a.dF = s->dF; a.nbl = s->nbl; a.nnbc = s->nnbc;
   a.cls_shift = NBL_CBITS * skin_class(s);
   a.n_own = s->n_own; a.rows = s->max_nb / s->lanes;
@@ -465,8 +539,8 @@ template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 #define P2(L, MULTI, FUSE) \
   (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true, false, CUBIC>, s, a, 512, sm) \
                        : launch_k(k_pass2<512, L, MULTI, true, false, false, CUBIC>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass2<IMDB_NT, L, MULTI, false, true, FUSE, CUBIC>, s, a, IMDB_NT, sm) \
-                       : launch_k(k_pass2<IMDB_NT, L, MULTI, false, false, FUSE, CUBIC>, s, a, IMDB_NT, 0)))
+                 : (ts ? launch_k(k_pass2<IMDB_NT2, L, MULTI, false, true, FUSE, CUBIC>, s, a, IMDB_NT2, sm) \
+                       : launch_k(k_pass2<IMDB_NT2, L, MULTI, false, false, FUSE, CUBIC>, s, a, IMDB_NT2, 0)))
 
 template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
 {
@@ -490,6 +564,7 @@ int forces_pass2(imdb200_sim *s, int fuse) { return s->tabs.cubic ? forces_pass2
 
 int IMPL(forces_pass1)(imdb200_sim *s)
 {
+  TRY(forces_textures(s));
   FArgs a = make_args(s);
   switch (s->lanes) {
     case 1: TRY(launch1_L<1>(s, a)); break;
@@ -506,6 +581,7 @@ int IMPL(forces_pass1)(imdb200_sim *s)
 
 int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
 {
+  TRY(forces_textures(s));
   FArgs a = make_args(s);
   if (fuse && !forces_can_fuse_move(s)) return imdb_fail(IMDB200_ERR_ARG, "fused move_atoms is not available in this configuration");
   if (fuse) CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
@@ -518,7 +594,7 @@ int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
     case 32: TRY(launch2_L<32>(s, a, fuse)); break;
     default: return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
   }
-  const int nb = grid_for(s, s->press_calc ? 512 : IMDB_NT);
+  const int nb = grid_for(s, s->press_calc ? 512 : IMDB_NT2);
   if (fuse) {
     const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT;
     const int slots[3] = {SC_VIRIAL, nvt ? SC_EKIN1 : SC_EKIN, SC_EKIN2};

@@ -144,6 +144,9 @@ struct imdb200_sim {
   int skin_skip;                  // 1: the force kernels skip list entries that cannot be inside the cut-off yet
   int skin_all;                   // box/positions changed outside move_atoms since the build: use every entry
   double disp2;                   // max squared displacement of the current positions since the build; <0 unknown
+  // pos / posdf as linear textures for the TEX share of the gathers (forces.cu)
+  cudaTextureObject_t tex_pos, tex_posdf; const void *tex_pos_ptr, *tex_posdf_ptr; size_t tex_pos_bytes, tex_posdf_bytes;
+  int tex_ok;
   // restrictions / deformation tables per virtual type
   double *restr; int n_restr;
   // scalars
@@ -218,6 +221,8 @@ int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
 int forces_pass1(imdb200_sim *s);             // pair + rho + embedding
 int forces_pass2(imdb200_sim *s, int fuse_move);   // EAM force pass; fuse_move: move_atoms + check_nblist in its tail
 int forces_can_fuse_move(const imdb200_sim *s);
+int forces_textures(imdb200_sim *s);
+void forces_free_textures(imdb200_sim *s);
 int forces_pass1_quad(imdb200_sim *s);        // forces.cu is compiled once per interpolation order (quadratic / cubic)
 int forces_pass2_quad(imdb200_sim *s, int fuse_move);
 int forces_pass1_cubic(imdb200_sim *s);
