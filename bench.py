@@ -16,7 +16,7 @@ Printed JSON (one line, rank 0):
              host memory + K steps (energies read back every step) + download of positions, momenta and
              forces, all inside the timed region
   roofline   dominant kernel (pass 1: pair + density + embedding) against the measured HBM peak
-  cpu_baseline  the reference's own serial Verlet-list build (oracle/_ref) on a bounded sample
+  cpu_baseline  the reference's own MPI build (oracle/_ref on oracle/shmpi) on all host threads, bounded sample
 --impl reference: the reference's own CPU implementation on all host threads: IMD's MPI build on
 oracle/shmpi (shared-memory MPI subset, one rank per host thread); its OpenMP build as fallback.
 """
@@ -152,6 +152,54 @@ def balanced_grid(n):
     return best
 
 
+def host_rank_grid():
+    """All host threads this process may use, as an MPI rank count with a balanced 3-D process grid."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for n in range(cores, 0, -1):
+        g = balanced_grid(n)
+        if g:
+            return cores, n, g
+    return cores, 1, (1, 1, 1)
+
+
+def run_ref_mpi(tmp, tabs, grid, ranks, nc, nsteps, tag="mpi"):
+    """One run of IMD's MPI build (oracle/_ref/imd_ref_mpi_eam on oracle/shmpi): nc^3 fcc cells per rank, nsteps
+    MD steps from a fresh lattice; returns the main-loop seconds."""
+    from imd_b200 import synth
+    exe = os.path.join(ROOT, "oracle", "_ref", "imd_ref_mpi_eam")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/imd_ref_mpi_eam missing")
+    p = synth.cu_param(tmp, ncell=[nc * g for g in grid], name=f"{tag}{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs,
+                       extra=dict(cpu_dim=list(grid)))
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, "-p", p], capture_output=True, text=True, cwd=tmp, env=dict(os.environ, SHMPI_NP=str(ranks)),
+                       timeout=3000)
+    wall = time.perf_counter() - t0
+    m = re.search(r"([0-9.eE+-]+) seconds excluding setup time", r.stdout)
+    if r.returncode != 0 or not m:
+        raise RuntimeError("reference run failed:\n" + r.stdout[-1500:] + r.stderr[-1500:])
+    # IMD's timer is CPU time of rank 0 (= wall time of the main loop: ranks spin-wait, never sleep)
+    return min(float(m.group(1)), wall)
+
+
+def cpu_baseline_mpi(tmp, tabs, budget_s=15.0):
+    """cpu_baseline of the default run: IMD's own MPI build (the same Verlet-list code path as the path under test) on
+    every host thread, a bounded sample of about budget_s seconds: steps 6..25 of a run from the lattice
+    (two runs are timed, 5 and 25 steps, so that start-up and the first list build drop out)."""
+    cores, ranks, grid = host_rank_grid()
+    rate = 4 * 12 ** 3 * ranks * 4 / max(run_ref_mpi(tmp, tabs, grid, ranks, 12, 4, "cb"), 1e-6)
+    cap = int((32e6 / 4 / ranks) ** (1.0 / 3.0))
+    nc = int(min(100, cap, max(10, round((rate * budget_s / 30 / 4 / ranks) ** (1.0 / 3.0)))))
+    t5 = run_ref_mpi(tmp, tabs, grid, ranks, nc, 5, "cb")
+    t25 = run_ref_mpi(tmp, tabs, grid, ranks, nc, 25, "cb")
+    natoms = 4 * nc ** 3 * ranks
+    v = natoms * 20 / max(t25 - t5, 1e-9)
+    return {"value": v, "unit": "atom-steps/s", "cores": ranks, "kind": "reference",
+            "sample": f"IMD MPI build imd_mpi_nve_nvt_eam_nbl (-O3 -march=x86-64-v3) on {ranks} ranks (cpu_dim %d %d %d, "
+                      f"oracle/shmpi) of {cores} host threads, {natoms} atoms x 20 steps (steps 6-25), "
+                      f"{t25 - t5:.1f} s, same tables/T0/dt" % grid}
+
+
 def reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path on all host threads.
     First choice is IMD's MPI build (imd_mpi_nve_nvt_eam_nbl: the same Verlet-list code path, spatial domain
@@ -162,35 +210,21 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores, ranks, grid = host_rank_grid()
     tmp = tempfile.mkdtemp(prefix="imdref_")
     tabs = synth.make_eam_tables(tmp, "cu")
-    mpi_exe = os.path.join(ROOT, "oracle", "_ref", "imd_ref_mpi_eam")
     omp_exe = os.path.join(ROOT, "oracle", "_ref", "imd_ref_omp_eam")
-    ranks, grid = 1, (1, 1, 1)
-    for n in range(cores, 0, -1):
-        g = balanced_grid(n)
-        if g:
-            ranks, grid = n, g
-            break
 
     def run(kind, nc, nsteps):
         if kind == "mpi":
-            box = [nc * g for g in grid]
-            p = synth.cu_param(tmp, ncell=box, name=f"mpi{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs,
-                               extra=dict(cpu_dim=list(grid)))
-            exe, env = mpi_exe, dict(os.environ, SHMPI_NP=str(ranks))
-        else:
-            p = synth.cu_param(tmp, ncell=(nc, nc, nc), name=f"omp{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs)
-            exe, env = omp_exe, dict(os.environ, OMP_NUM_THREADS=str(cores))
-        t0 = time.perf_counter()
-        r = subprocess.run([exe, "-p", p], capture_output=True, text=True, cwd=tmp, env=env, timeout=3000)
-        wall = time.perf_counter() - t0
+            return run_ref_mpi(tmp, tabs, grid, ranks, nc, nsteps)
+        p = synth.cu_param(tmp, ncell=(nc, nc, nc), name=f"omp{nc}_{nsteps}", maxsteps=nsteps - 1, tables=tabs)
+        r = subprocess.run([omp_exe, "-p", p], capture_output=True, text=True, cwd=tmp,
+                           env=dict(os.environ, OMP_NUM_THREADS=str(cores)), timeout=3000)
         m = re.search(r"([0-9.eE+-]+) seconds excluding setup time", r.stdout)
         if r.returncode != 0 or not m:
             raise RuntimeError("reference run failed:\n" + r.stdout[-1500:] + r.stderr[-1500:])
-        # IMD's timer is CPU time of rank 0 (= wall time of the main loop: ranks spin-wait, never sleep)
-        return min(float(m.group(1)), wall)
+        return float(m.group(1))
 
     def measure(kind):
         # size the bounded sample from a 4-step probe so that the two runs below take about 100 s in total
@@ -207,8 +241,6 @@ def reference_arm(args):
 
     kind, note = "mpi", None
     try:
-        if not os.path.exists(mpi_exe):
-            raise RuntimeError("oracle/_ref/imd_ref_mpi_eam missing")
         natoms, dt = measure("mpi")
     except Exception as e:                                 # keep the arm alive: fall back to the OpenMP build
         kind, note = "omp", f"MPI build unavailable ({str(e)[:200]})"
@@ -341,7 +373,13 @@ def ours(args):
         ach = B_PASS1 * n / t_p1 / 1e9 if t_p1 > 0 else 0.0
         step_ach = B_ALG * (n * args.steps / (ms * 1e-3)) / 1e9
         prof = load_profile_traffic(n)
-        cpu = cpu_baseline_serial(tmp) if world == 1 and not args.no_cpu else None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            try:
+                cpu = cpu_baseline_mpi(tmp, tabs)
+            except Exception as e:                         # fall back to the serial build, say why
+                cpu = cpu_baseline_serial(tmp)
+                cpu["sample"] += f"; MPI build unavailable ({str(e)[:120]})"
         line = {
             "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -363,7 +401,8 @@ def ours(args):
                          "traffic": prof["dram_bytes_per_launch"] if prof else None,
                          "traffic_source": prof["source"] if prof else None, "peak_source": how,
                          "algorithmic_bytes_per_launch": B_PASS1 * n, "algorithmic_bytes_per_atom": B_PASS1,
-                         "limiter": "L1/shared data pipe 97 % busy (gathers 57 %, table bank conflicts 22 %), see profiles/README.md",
+                         "limiter": "L1 data stage: TEX pipe 90 % busy with the position gathers, LSU pipe 67 % with the table "
+                                    "look-ups in shared memory; HBM 16 %, FP64 pipe 28 % -- see profiles/README.md",
                          "whole_step": {"achieved": step_ach, "frac": step_ach / peak, "bytes_per_atom_step": B_ALG}},
             "phase_ms_per_step": {k: tm[k] / steps_t for k in
                                   ("rebuild_ms", "pass1_ms", "pass2_ms", "integrate_ms", "ghost_ms")},
