@@ -54,7 +54,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box",
 ]
 
 _lib = None
@@ -345,6 +345,11 @@ class IMDB200:
     def celldims(self):
         s = self.raw_scalars()
         return np.array(list(s.global_cell_dim), np.int32), np.array(list(s.cell_dim), np.int32)
+
+    def box(self):
+        out = np.zeros(9)
+        _chk(self.L.imdb200_get_box(self.h, out.ctypes.data))
+        return out.reshape(3, 3)
 
     def tot_presstens(self):
         return np.array(list(self.raw_scalars().tot_presstens))

@@ -139,6 +139,7 @@ int imdb200_set_restrictions(imdb200_sim *s, int total_types, const double *r)
   for (int i = 0; i < 3 * total_types; i++) if (r[i] != 1.0) all1 = 0;
   (void) sum;
   s->n_restr = all1 ? 0 : total_types;
+  s->nactive_dirty = 1;
   return 0;
 }
 
@@ -206,7 +207,8 @@ int imdb200_set_atoms(imdb200_sim *s, long n, const int *nummer, const int *sort
   s->n_own = n;
   s->natoms_global = s->nranks > 1 ? 0 : n;     // multi-rank: counted after the first binning
   s->need_filter = s->nranks > 1;               // keep only the atoms of this rank's domain
-  s->nactive = 3 * (long long) n;               /* src/imd_generate.c:450-451 */
+  s->nactive = 3 * (long long) n;               /* recounted with the restriction vectors after the first binning */
+  s->nactive_dirty = 1;
   s->n_ghost = 0;
   s->have_valid_nbl = 0;
   s->nbl_count = 0;
@@ -236,6 +238,7 @@ static int ready(imdb200_sim *s)
   if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
   if (!s->have_tabs || (s->n_own <= 0 && s->nranks == 1)) return imdb_fail(IMDB200_ERR_ARG, "potentials and atoms must be set first");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
+  if (s->nactive_dirty && s->have_valid_nbl) TRY(cells_count_nactive(s));   // restrictions changed between rebuilds
   return 0;
 }
 
@@ -385,6 +388,13 @@ int imdb200_get_scalars(imdb200_sim *s, imdb200_scalars *o)
   o->have_valid_nbl = s->have_valid_nbl; o->nbl_count = s->nbl_count; o->is_short = s->is_short;
   for (int d = 0; d < 3; d++) { o->global_cell_dim[d] = s->geom.gdim[d]; o->cell_dim[d] = s->geom.cdim[d]; }
   o->cellsz = s->geom.cellsz;
+  return 0;
+}
+
+int imdb200_get_box(imdb200_sim *s, double out9[9])
+{
+  if (!s || !out9) return imdb_fail(IMDB200_ERR_ARG, "null argument");
+  for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) out9[3 * b + d] = s->geom.box[b][d];
   return 0;
 }
 

@@ -652,6 +652,41 @@ static int bin_and_sort(imdb200_sim *s, long n, int filter, int *h_extra)
   return 0;
 }
 
+// nactive: the degrees of freedom that move -- 3 per atom of a real type, the restriction components of its virtual
+// type otherwise (read_atoms, src/imd_io_3d.c:469-481; generate_atoms, src/imd_generate.c:450-451).  It enters the
+// Nose-Hoover update (src/imd_integrate.c:1140) and the temperature the writers print.
+__global__ void k_count_nactive(const double4 *pos, long n, int ntypes, const double *restr, int n_restr,
+                                unsigned long long *out)
+{
+  long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  unsigned long long c = 0;
+  if (i < n) {
+    const int v = vsorte_of(pos[i].w);
+    c = 3;
+    if (v >= ntypes && restr && v < n_restr)
+      c = (unsigned long long) ((long long) restr[3 * v] + (long long) restr[3 * v + 1] + (long long) restr[3 * v + 2]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int cells_count_nactive(imdb200_sim *s)
+{
+  cudaStream_t st = s->stream;
+  unsigned long long *d = (unsigned long long *) (s->d_scal + SC_COUNT - 1);   // scratch slot, as for the list length
+  unsigned long long mine = 0;
+  CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(unsigned long long), st));
+  if (s->n_own > 0) { k_count_nactive<<<cdiv(s->n_own, 256), 256, 0, st>>>(s->pos, s->n_own, s->cfg.ntypes, s->restr, s->n_restr, d); LAUNCH_CHECK(); }
+  CUDA_TRY(cudaMemcpyAsync(&mine, d, sizeof(mine), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  long long tot = 0;
+  TRY(comm_allgather_ll(s, (long long) mine, &tot));
+  s->nactive = tot;
+  s->nactive_dirty = 0;
+  return 0;
+}
+
 // fix_cells + send_cells + make_nblist, i.e. the `0 == have_valid_nbl` branch of calc_forces
 // (src/imd_forces_nbl.c:304-317)
 int cells_rebuild(imdb200_sim *s)
@@ -677,9 +712,9 @@ int cells_rebuild(imdb200_sim *s)
     TRY(comm_allgather_ll(s, n, &tot));
     if (s->natoms_global == 0) s->natoms_global = tot;
     else if (tot != s->natoms_global) return imdb_fail(IMDB200_ERR_CELLS, "atom count changed from %lld to %lld in fix_cells", s->natoms_global, tot);
-    s->nactive = 3 * s->natoms_global;
   } else s->natoms_global = n;
   s->n_own = n;
+  if (s->nactive_dirty) TRY(cells_count_nactive(s));
   // ---- buffer cells: images of the boundary cells, ours or a neighbour's -----------------------------
   TRY(comm_setup_ghosts(s));
   TRY(comm_ghost_pos(s));

@@ -158,6 +158,7 @@ struct imdb200_sim {
   int *d_flags, *h_flags;
   int press_calc, is_short;
   long long nactive;   // sum of the restriction components over all atoms (3N by default)
+  int nactive_dirty;   // atoms or restrictions changed: recount at the next rebuild / step
   double eta;
   // timers
   cudaEvent_t ev[16];
@@ -206,6 +207,7 @@ int tables_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2
 int geom_make_box(imdb200_sim *s);           // make_box + init_cells when needed
 int cells_ensure_capacity(imdb200_sim *s, long n_atoms_total);
 int cells_rebuild(imdb200_sim *s);            // fix_cells + ghost images + make_nblist
+int cells_count_nactive(imdb200_sim *s);     // nactive from the virtual types and restriction vectors (collective)
 int scan_exclusive(imdb200_sim *s, const int *in, int *out, int n, int *total_dev);
 
 int comm_plan(imdb200_sim *s);                // halo plan for the current cell grid (after init_cells)

@@ -232,3 +232,19 @@ def maxwell_momenta(n, mass, temperature, seed=1):
     p = rng.standard_normal((n, 3)) * np.sqrt(temperature * np.asarray(mass).reshape(-1, 1))
     p -= p.mean(axis=0)
     return p
+
+
+def write_config(path, nummer, vsorte, masse, ort, impuls, box):
+    """Atom configuration in IMD's ASCII format (read_atoms, src/imd_io_3d.c:44-): number, (virtual) type, mass,
+    position, velocity; box vectors in the header (use with `box_from_header 1`)."""
+    box = np.asarray(box, np.float64).reshape(3, 3)
+    with open(path, "w") as f:
+        f.write("#F A 1 1 1 3 3 0\n#C number type mass x y z vx vy vz\n")
+        for tag, b in zip("XYZ", box):
+            f.write("#%s %.17e %.17e %.17e\n" % (tag, b[0], b[1], b[2]))
+        f.write("#E\n")
+        vel = np.asarray(impuls) / np.asarray(masse)[:, None]
+        for i in range(len(nummer)):
+            f.write("%d %d %.17e %.17e %.17e %.17e %.17e %.17e %.17e\n" % (
+                nummer[i], vsorte[i], masse[i], ort[i, 0], ort[i, 1], ort[i, 2], vel[i, 0], vel[i, 1], vel[i, 2]))
+    return path

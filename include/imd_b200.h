@@ -178,6 +178,9 @@ typedef struct {
   double cellsz;
 } imdb200_scalars;
 int  imdb200_get_scalars(imdb200_sim *sim, imdb200_scalars *out);
+/* replaces: reading the globals box_x, box_y, box_z (src/globals.h) after lin_deform has changed them;
+ * out9 = box_x, box_y, box_z */
+int  imdb200_get_box(imdb200_sim *sim, double out9[9]);
 
 /* copy the owned atoms back to the host (any pointer may be NULL); returns the count.
  * Order: the device's cell-sorted order; identify atoms by nummer (NUMMER, types.h:189). */

@@ -918,6 +918,40 @@ void orc_lin_deform(orc_sim *s, const double dx[3], const double dy[3], const do
   make_box(s);
 }
 
+/* deform_sample, src/imd_deform.c:232-269: per virtual type a shift, optionally scaled by a shear profile */
+void orc_deform_sample(orc_sim *s, double deform_size, const double *deform_shift, const int *shear_def,
+                       const double *deform_shear, const double *deform_base)
+{
+  long a;
+  for (a = 0; a < s->n; a++) {
+    double *o = s->ort + 3 * a, shear;
+    int sort = s->vsorte[a];
+    if (shear_def && shear_def[sort] == 1) {
+      vec3 ort, sh = {deform_shear[3 * sort], deform_shear[3 * sort + 1], deform_shear[3 * sort + 2]};
+      ort.x = o[0] - deform_base[3 * sort];
+      ort.y = o[1] - deform_base[3 * sort + 1];
+      ort.z = o[2] - deform_base[3 * sort + 2];
+      shear = SPROD(sh, ort);
+    } else shear = 1.0;
+    o[0] += shear * deform_size * deform_shift[3 * sort];
+    o[1] += shear * deform_size * deform_shift[3 * sort + 1];
+    o[2] += shear * deform_size * deform_shift[3 * sort + 2];
+  }
+}
+
+/* nactive = number of degrees of freedom that move: 3 per atom of a real type, the restriction components of
+   its virtual type otherwise (read_atoms, src/imd_io_3d.c:469-481; generate_atoms, src/imd_generate.c:450-451) */
+static void count_nactive(orc_sim *s)
+{
+  long a, n = 0;
+  for (a = 0; a < s->n; a++) {
+    int v = s->vsorte[a];
+    if (v < s->ntypes || !s->restr || v >= s->nvtypes) n += 3;
+    else n += (long) s->restr[3 * v] + (long) s->restr[3 * v + 1] + (long) s->restr[3 * v + 2];
+  }
+  s->nactive = n;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* construction / accessors                                                              */
 /* ------------------------------------------------------------------------------------ */
@@ -969,7 +1003,7 @@ void orc_set_atoms(orc_sim *s, long n, const int *nummer, const int *sorte, cons
     s->kraft[3 * a] = s->kraft[3 * a + 1] = s->kraft[3 * a + 2] = 0.0;
     s->poteng[a] = s->rho[a] = s->dF[a] = 0.0;
   }
-  s->nactive = 3 * n; /* sum of restriction components, src/imd_generate.c:450-451 */
+  count_nactive(s);
   if (!s->cells) make_box(s); /* first make_box -> init_cells (min/max_height start at 0) */
   s->have_valid_nbl = 0;
 }
@@ -979,6 +1013,7 @@ void orc_set_restrictions(orc_sim *s, int nvtypes, const double *restr3)
   s->nvtypes = nvtypes;
   s->restr = (double *) realloc(s->restr, sizeof(double) * 3 * nvtypes);
   memcpy(s->restr, restr3, sizeof(double) * 3 * nvtypes);
+  count_nactive(s);
 }
 
 void orc_set_integrator(orc_sim *s, int ensemble, double timestep, double temperature, double eta, double isq_tau_eta)

@@ -47,6 +47,9 @@ void orc_move_atoms(orc_sim *s, int do_press_calc);       /* src/imd_integrate.c
 void orc_check_nblist(orc_sim *s);                        /* src/imd_forces_nbl.c:2007-2037 */
 void orc_step(orc_sim *s, int nsteps);
 void orc_lin_deform(orc_sim *s, const double dx[3], const double dy[3], const double dz[3], double scale);
+/* deform_sample (src/imd_deform.c:232-269); arrays indexed by virtual type, 3 doubles each */
+void orc_deform_sample(orc_sim *s, double deform_size, const double *deform_shift, const int *shear_def,
+                       const double *deform_shear, const double *deform_base);
 
 long   orc_natoms(const orc_sim *s);
 int    orc_have_valid_nbl(const orc_sim *s);

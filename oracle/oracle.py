@@ -69,6 +69,7 @@ def lib():
         L.orc_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.orc_tot_presstens.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_interpolation.argtypes = [C.c_void_p, C.c_int]
+        L.orc_deform_sample.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -136,6 +137,14 @@ class OracleIMD:
     def lin_deform(self, dx, dy, dz, scale):
         v = [np.ascontiguousarray(x, np.float64) for x in (dx, dy, dz)]
         lib().orc_lin_deform(self.h, v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data, float(scale))
+
+    def deform_sample(self, deform_size, deform_shift, shear_def=None, deform_shear=None, deform_base=None):
+        sh = np.ascontiguousarray(deform_shift, np.float64).reshape(-1, 3)
+        n = len(sh)
+        sd = np.zeros(n, np.int32) if shear_def is None else np.ascontiguousarray(shear_def, np.int32)
+        ss = np.zeros((n, 3)) if deform_shear is None else np.ascontiguousarray(deform_shear, np.float64)
+        bs = np.zeros((n, 3)) if deform_base is None else np.ascontiguousarray(deform_base, np.float64)
+        lib().orc_deform_sample(self.h, float(deform_size), sh.ctypes.data, sd.ctypes.data, ss.ctypes.data, bs.ctypes.data)
 
     @property
     def natoms(self):

@@ -205,6 +205,12 @@ def run_protocol(sim, spec):
     out["cellsz"] = sim.cellsz
     frames = []
     for s in range(spec.get("nsteps", 1)):
+        # main_loop order (src/imd_main_3d.c:293-326): lin_deform, then deform_sample + check_nblist, then the forces
+        if s > 0 and spec.get("lindef_every", 0) and s % spec["lindef_every"] == 0:
+            sim.lin_deform()
+        if s > 0 and spec.get("deform_every", 0) and s % spec["deform_every"] == 0:
+            sim.deform_sample()
+            sim.check_nblist()
         sim.calc_forces(s)
         fr = {"scalars": sim.scalars()}
         if s in spec.get("record_atoms", [0]):
@@ -222,6 +228,7 @@ def run_protocol(sim, spec):
         frames.append(fr)
     out["frames"] = frames
     out["final"] = sim.atoms()
+    out["final_box"] = sim.box()
     out["nbl_count"] = sim.nbl_count
     return out
 

@@ -46,11 +46,15 @@ def make_sim(factory, g, tabdir, **kw):
         common["interp"] = str(g["interp"])
     integ = dict(ensemble=ens, timestep=float(g["timestep"]), temperature=float(g["temperature"]),
                  eta=float(g["eta0"]), isq_tau_eta=float(g["isq_tau_eta"]))
+    if "total_types" in g and factory.__name__ != "OracleIMD":
+        common["total_types"] = int(g["total_types"])
     try:
         sim = factory(int(g["ntypes"]), g["box"], **common, **integ, **kw)
     except TypeError:
         sim = factory(int(g["ntypes"]), g["box"], **common, **kw)
         sim.set_integrator(**integ)
+    if "restrictions" in g:                                # restrictionvector per virtual type
+        sim.set_restrictions(g["restrictions"])
     sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"],
                   vsorte=g["start:vsorte"])
     return sim
@@ -63,7 +67,15 @@ def run_protocol(sim, g):
     nsteps = int(g["nsteps"])
     rec = {int(x) for x in g["record"]}
     out = dict(epot=[], virial=[], ekin=[], eta=[], valid=[], atoms={}, nbl=None, tot_presstens={})
+    lindef = int(g["lindef_every"]) if "lindef_every" in g else 0
+    deform = int(g["deform_every"]) if "deform_every" in g else 0
     for s in range(nsteps):
+        # same order as main_loop (src/imd_main_3d.c:293-326)
+        if s > 0 and lindef and s % lindef == 0:
+            sim.lin_deform(g["lindef_x"], g["lindef_y"], g["lindef_z"], float(g["lindef_size"]))
+        if s > 0 and deform and s % deform == 0:
+            sim.deform_sample(float(g["deform_size"]), g["deform_shift"], g["shear_def"], g["deform_shear"], g["deform_base"])
+            sim.check_nblist()
         sim.calc_forces(s)
         sc = sim.scalars()
         out["epot"].append(sc["tot_pot_energy"]); out["virial"].append(sc["virial"])

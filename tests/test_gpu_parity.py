@@ -47,6 +47,23 @@ def test_cuda_cubic_interpolation_matches_reference_fixture(api, name, lanes, tm
     sim.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 8])
+@pytest.mark.parametrize("name", ["cu_lindef", "cu_frozen_nvt"])
+def test_cuda_deformation_and_restrictions_match_reference_fixture(api, name, lanes, tmp_path):
+    """lin_deform (uniaxial strain + shear: the box turns triclinic) and deform_sample with a frozen, pushed layer under
+    NVT (restrictionvector, nactive < 3N in the eta update) against the reference: src/imd_deform.c:35-119, 232-269,
+    src/imd_integrate.c:1020-1027, 1140, src/imd_io_3d.c:469-481."""
+    g = common.load_golden(name)
+    sim = common.make_sim(api.IMDB200, g, str(tmp_path), lanes_per_atom=lanes)
+    out = common.run_protocol(sim, g)
+    errs = common.compare(out, g, full_list=True, rtol=1e-10, traj_rtol=1e-8)
+    assert sim.scalars()["nactive"] == float(g["nactive"])
+    if "final:box" in g:
+        assert np.max(np.abs(sim.box() - g["final:box"])) <= 1e-13 * np.max(np.abs(g["final:box"]))
+    print(name, lanes, {k: f"{v:.1e}" for k, v in errs.items()})
+    sim.close()
+
+
 def test_cuda_cubic_run_loop_equals_stepwise_calls(api, tmp_path):
     """imdb200_run (fused integrator) and the separate calls stay bit-identical in the cubic kernels too."""
     g = common.load_golden("cu_spline")

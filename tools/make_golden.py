@@ -48,6 +48,18 @@ CASES = {
                         record=[0, 15], press=True, variant="eam_spline", interp="spline"),
     "cu_spline": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=40, nsteps=16,
                       record=[0, 15], press=False, variant="eam_spline", interp="spline"),
+    # homogeneous deformation (lin_deform, src/imd_deform.c:35-119) every 4 steps: uniaxial strain plus two shear
+    # components, so the box turns triclinic; the list stays valid across a deformation until check_nblist says no
+    "cu_lindef": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=30, nsteps=24,
+                      record=[0, 23], press=True, variant="eam", lindef_every=4,
+                      extra=dict(lindef_interval=4, lindef_size=2.5e-3, lindef_x=[1.0, 0.2, 0.0],
+                                 lindef_y=[0.0, -0.4, 0.0], lindef_z=[0.3, 0.0, 0.2])),
+    # slab with free surfaces in z, NVT: the bottom layer is virtual type 1, frozen in z (restrictionvector) and pushed
+    # along x every 5 steps, the rest is sheared (deform_sample, src/imd_deform.c:232-269); nactive < 3N enters eta
+    "cu_frozen_nvt": dict(kind="cu_vtypes", ncell=(5, 5, 4), ensemble="nvt", starttemp=0.06, warm=20, nsteps=20,
+                          record=[0, 19], press=False, variant="eam", deform_every=5,
+                          extra=dict(pbc_dirs=[1, 1, 0], total_types=2, restrictionvector=[1, 1, 1, 0],
+                                     max_deform_int=5, deform_size=1.0)),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
 }
@@ -69,6 +81,23 @@ def make_case(name, c):
         p = synth.cu_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
                            tables=tabs, extra=c.get("extra"))
         ntypes = 1
+    elif c["kind"] == "cu_vtypes":
+        # our own start configuration, read by the reference: fcc Cu, virtual type 1 for the bottom layer
+        tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+        ort, box = synth.fcc_lattice(c["ncell"], synth.CU_A0)
+        n = len(ort)
+        vs = (ort[:, 2] < 0.6 * synth.CU_A0).astype(np.int32)
+        masse = np.full(n, synth.CU_MASS)
+        mom = synth.maxwell_momenta(n, masse, c["starttemp"], 11)
+        cfgfile = synth.write_config(os.path.join(tmp, "start.conf"), np.arange(n), vs, masse, ort, mom, box)
+        extra = dict(c["extra"], box_from_header=1)
+        p = synth.cu_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"], tables=tabs,
+                           coordname=cfgfile, extra=extra)
+        # keys that take "<vtype> x y z" appear once per virtual type: append the second lines by hand
+        with open(p, "a") as f:
+            f.write("deform_shift 0 1.0 0.0 0.0\ndeform_shear 0 0.0 0.0 4.0e-4\ndeform_base 0 0.0 0.0 0.0\n"
+                    "deform_shift 1 0.012 0.0 0.0\n")
+        ntypes = 1
     elif c["kind"] == "nial":
         tabs = synth.make_eam_tables(tmp, "nial", nr=601, nrho=801)
         p = synth.nial_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
@@ -79,7 +108,8 @@ def make_case(name, c):
         p = synth.lj_param(tmp, ncell=c["ncell"], starttemp=c["starttemp"], table=tabs, extra=c.get("extra"))
         ntypes = 2
     spec = dict(variant=c["variant"], paramfile=p, warm=c["warm"], nsteps=c["nsteps"],
-                record_atoms=c["record"], record_nbl=[0], press=c["press"])
+                record_atoms=c["record"], record_nbl=[0], press=c["press"],
+                lindef_every=c.get("lindef_every", 0), deform_every=c.get("deform_every", 0))
     out = rd.run_in_subprocess(spec, tmp)
     g = dict(table_arrays(tabs))
     g["ntypes"] = ntypes
@@ -89,6 +119,19 @@ def make_case(name, c):
     g["nsteps"] = c["nsteps"]
     g["record"] = np.array(c["record"])
     g["pbc"] = np.array(c.get("extra", {}).get("pbc_dirs", [1, 1, 1]))
+    if c.get("lindef_every"):
+        e = c["extra"]
+        g["lindef_every"] = c["lindef_every"]; g["lindef_size"] = e["lindef_size"]
+        g["lindef_x"] = np.array(e["lindef_x"]); g["lindef_y"] = np.array(e["lindef_y"]); g["lindef_z"] = np.array(e["lindef_z"])
+        g["final:box"] = out["final_box"]
+    if c.get("deform_every"):
+        g["deform_every"] = c["deform_every"]; g["deform_size"] = c["extra"]["deform_size"]
+        g["total_types"] = 2
+        g["restrictions"] = np.array([[1.0, 1.0, 1.0], [1.0, 1.0, 0.0]])
+        g["deform_shift"] = np.array([[1.0, 0.0, 0.0], [0.012, 0.0, 0.0]])
+        g["shear_def"] = np.array([1, 0], np.int32)
+        g["deform_shear"] = np.array([[0.0, 0.0, 4.0e-4], [0.0, 0.0, 0.0]])
+        g["deform_base"] = np.zeros((2, 3))
     g["box"] = out["box"]
     g["cellsz"] = out["cellsz"]
     g["gdim"], g["cdim"] = out["celldims"]
