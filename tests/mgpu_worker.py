@@ -40,7 +40,11 @@ def make(g, tabdir, grid, **kw):
                        pbc=tuple(int(x) for x in g["pbc"]), nbl_margin=0.4, pair=paths["pair"],
                        embed=paths.get("embed"), rho=paths.get("rho"), ensemble=str(g["ensemble"]),
                        timestep=float(g["timestep"]), temperature=float(g["temperature"]), eta=float(g["eta0"]),
-                       isq_tau_eta=float(g["isq_tau_eta"]), **kw)
+                       isq_tau_eta=float(g["isq_tau_eta"]),
+                       total_types=int(g["total_types"]) if "total_types" in g else None,
+                       interp=str(g["interp"]) if "interp" in g else "3point", **kw)
+    if "restrictions" in g:
+        sim.set_restrictions(g["restrictions"])
     # every rank is handed ALL atoms and keeps those of its own domain
     sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"],
                   vsorte=g["start:vsorte"])

@@ -48,7 +48,7 @@ def test_cuda_cubic_interpolation_matches_reference_fixture(api, name, lanes, tm
 
 
 @pytest.mark.parametrize("lanes", [1, 8])
-@pytest.mark.parametrize("name", ["cu_lindef", "cu_frozen_nvt"])
+@pytest.mark.parametrize("name", ["cu_lindef", "cu_frozen_nvt", "cu_frozen_nve"])
 def test_cuda_deformation_and_restrictions_match_reference_fixture(api, name, lanes, tmp_path):
     """lin_deform (uniaxial strain + shear: the box turns triclinic) and deform_sample with a frozen, pushed layer under
     NVT (restrictionvector, nactive < 3N in the eta update) against the reference: src/imd_deform.c:35-119, 232-269,

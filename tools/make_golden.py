@@ -60,6 +60,11 @@ CASES = {
                           record=[0, 19], press=False, variant="eam", deform_every=5,
                           extra=dict(pbc_dirs=[1, 1, 0], total_types=2, restrictionvector=[1, 1, 1, 0],
                                      max_deform_int=5, deform_size=1.0)),
+    # the same slab under NVE: restrictions multiply the force before the kick (src/imd_integrate.c:193-197)
+    "cu_frozen_nve": dict(kind="cu_vtypes", ncell=(5, 5, 4), ensemble="nve", starttemp=0.06, warm=20, nsteps=12,
+                          record=[0, 11], press=False, variant="eam", deform_every=5,
+                          extra=dict(pbc_dirs=[1, 1, 0], total_types=2, restrictionvector=[1, 1, 1, 0],
+                                     max_deform_int=5, deform_size=1.0)),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
 }
