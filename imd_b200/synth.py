@@ -116,6 +116,18 @@ def make_eam_tables(outdir, kind="cu", prefix=None, nr=2001, nrho=4001,
     return paths
 
 
+def make_eeam_table(outdir, nt=1, prefix="eeam", npts=1201, p_end=30.0):
+    """EEAM energy modification term M(p), p = sum_j rho_j(r_ij)^2 (`eeam_energy_file`, format 2, one column per
+    type, not radial): a smooth synthetic function with non-trivial curvature."""
+    os.makedirs(outdir, exist_ok=True)
+    step = p_end / (npts - 1)
+    x = step * np.arange(npts)
+    cols = [(-0.08 - 0.02 * a) * np.sqrt(x + 0.5) + (6.0e-4 + 2.0e-4 * a) * x * x for a in range(nt)]
+    path = os.path.join(outdir, f"{prefix}_M.pot")
+    write_table2(path, [0.0] * nt, [p_end] * nt, [step] * nt, cols)
+    return path
+
+
 def make_lj_table(outdir, name="lj_ar.pot", eps=0.0104, sigma=3.40, r_begin=2.0, r_cut=8.5,
                   nsteps=5000, ntypes=2):
     """Tabulated LJ pair potential in format 1, the way util/imd_mklj.c:50-66 lays it out

@@ -40,13 +40,14 @@ struct orc_sim {
   int pbc[3];
   double nbl_margin, cellsz;
   int margin_added;
-  ptab tab[3];
+  ptab tab[4];         /* pair_pot, embed_pot, rho_h_tab, emod_pot (EEAM) */
   int default_fmt;
   int interp;          /* ORC_INTERP_*: which PAIR_INT the build selects, src/potaccess.h:24-36 */
   /* atoms: [0,n) real, [n, n+ng) buffer-cell copies */
   long n, ng, cap;
   int *nummer, *sorte, *vsorte;
   double *masse, *ort, *impuls, *kraft, *poteng, *rho, *dF, *presstens, *nblpos;
+  double *eam_p, *dM;  /* EEAM: p_i = sum rho_j^2 and M'(p_i) (EAM_P, EAM_DM, src/makros.h:96-99) */
   long gstage[3]; /* end index of the z-, y-, x-stage buffer atoms */
   long *gsrc; /* source atom of each buffer atom (may itself be a buffer atom) */
   signed char *gshift; /* accumulated image shift (box units), for reporting only */
@@ -196,8 +197,8 @@ static int read_table2(orc_sim *s, ptab *pt, FILE *f, int radial)
 int orc_read_table(orc_sim *s, int which, const char *path)
 {
   ptab *pt = &s->tab[which];
-  int radial = (which != ORC_EMBED);
-  int ncols = (which == ORC_EMBED) ? s->ntypes : s->ntypes * s->ntypes;
+  int radial = (which != ORC_EMBED && which != ORC_EMOD);
+  int ncols = (which == ORC_EMBED || which == ORC_EMOD) ? s->ntypes : s->ntypes * s->ntypes;
   int have_header = 0, have_format = 0, end_header = 0, format, size = ncols, i, rc;
   char buffer[1024];
   FILE *f = fopen(path, "r");
@@ -530,6 +531,7 @@ static void grow_atoms(orc_sim *s, long need)
   GROW(s->masse, double, 1); GROW(s->ort, double, 3); GROW(s->impuls, double, 3);
   GROW(s->kraft, double, 3); GROW(s->poteng, double, 1); GROW(s->rho, double, 1);
   GROW(s->dF, double, 1); GROW(s->presstens, double, 6); GROW(s->nblpos, double, 3);
+  GROW(s->eam_p, double, 1); GROW(s->dM, double, 1);
   GROW(s->gsrc, long, 1); GROW(s->gshift, signed char, 3);
 #undef GROW
 }
@@ -600,7 +602,7 @@ static void send_cells_pos(orc_sim *s, int first)
 static void send_cells_dF(orc_sim *s)
 {
   long g;
-  for (g = s->n; g < s->n + s->ng; g++) s->dF[g] = s->dF[s->gsrc[g]];
+  for (g = s->n; g < s->n + s->ng; g++) { s->dF[g] = s->dF[s->gsrc[g]]; s->dM[g] = s->dM[s->gsrc[g]]; } /* + EAM_DM :1044-1046 */
 }
 
 /* send_forces(add_rho,...) / send_forces(add_forces,...): src/imd_comm_force_3d.c:569-714,
@@ -618,6 +620,7 @@ static void send_forces_back(orc_sim *s, int what, int do_press)
       long t = s->gsrc[g];
       if (what == 0) { /* add_rho */
         s->rho[t] += s->rho[g];
+        s->eam_p[t] += s->eam_p[g];              /* EEAM :1081-1083 */
       } else { /* add_forces */
         s->kraft[3 * t] += s->kraft[3 * g];
         s->kraft[3 * t + 1] += s->kraft[3 * g + 1];
@@ -688,7 +691,8 @@ static void make_nblist(orc_sim *s)
 void orc_calc_forces(orc_sim *s, int do_press_calc)
 {
   const ptab *pair_pot = &s->tab[ORC_PAIR], *embed_pot = &s->tab[ORC_EMBED], *rho_h_tab = &s->tab[ORC_RHO];
-  const int nt = s->ntypes, inc = nt * nt, eam = rho_h_tab->loaded;
+  const ptab *emod_pot = &s->tab[ORC_EMOD];
+  const int nt = s->ntypes, inc = nt * nt, eam = rho_h_tab->loaded, eeam = eam && emod_pot->loaded;
   long n, ntot, a; int c, i; long m;
   int is_short = 0, idummy = 0;
 
@@ -700,7 +704,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
   for (a = 0; a < ntot; a++) {              /* :333-401 */
     s->kraft[3 * a] = s->kraft[3 * a + 1] = s->kraft[3 * a + 2] = 0.0;
     for (i = 0; i < 6; i++) s->presstens[6 * a + i] = 0.0;
-    s->poteng[a] = 0.0; s->rho[a] = 0.0;
+    s->poteng[a] = 0.0; s->rho[a] = 0.0; s->eam_p[a] = 0.0;
   }
 
   /* atom index of list slot: slot = cl_off[c] + j */
@@ -714,7 +718,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
       long ia = p->idx[i];
       double pp[6] = {0, 0, 0, 0, 0, 0};
       double d1x = s->ort[3 * ia], d1y = s->ort[3 * ia + 1], d1z = s->ort[3 * ia + 2];
-      double ffx = 0.0, ffy = 0.0, ffz = 0.0, ee = 0.0, eam_r = 0.0;
+      double ffx = 0.0, ffy = 0.0, ffz = 0.0, ee = 0.0, eam_r = 0.0, eam_p = 0.0;
       int it = s->sorte[ia];
       for (m = s->tl[n]; m < s->tl[n + 1]; m++) {
         long ja = SLOT2ATOM(s->tb[m]);
@@ -746,13 +750,15 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
           if (r2 < rho_h_tab->end[col]) {
             pair_int(s, rho_h_tab, col, inc, r2, &rho_h, &dummy, &is_short);
             eam_r += rho_h;
+            if (eeam) eam_p += rho_h * rho_h;            /* :591-593 */
           }
           if (it == jt) {
-            if (r2 < rho_h_tab->end[col]) s->rho[ja] += rho_h;
+            if (r2 < rho_h_tab->end[col]) { s->rho[ja] += rho_h; if (eeam) s->eam_p[ja] += rho_h * rho_h; }
           } else {
             if (r2 < rho_h_tab->end[col2]) {
               pair_int(s, rho_h_tab, col2, inc, r2, &rho_h, &dummy, &is_short);
               s->rho[ja] += rho_h;
+              if (eeam) s->eam_p[ja] += rho_h * rho_h;   /* :606-608 */
             }
           }
         }
@@ -760,6 +766,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
       s->kraft[3 * ia] += ffx; s->kraft[3 * ia + 1] += ffy; s->kraft[3 * ia + 2] += ffz; /* :907-918 */
       s->poteng[ia] += ee;
       if (eam) s->rho[ia] += eam_r;
+      if (eeam) s->eam_p[ia] += eam_p;                 /* :915-917 */
       if (do_press_calc) { int d; for (d = 0; d < 6; d++) s->presstens[6 * ia + d] += pp[d]; }
       n++;
     }
@@ -775,6 +782,11 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
         pair_int(s, embed_pot, s->sorte[ia], nt, s->rho[ia], &pot, &s->dF[ia], &idummy);
         s->poteng[ia] += pot;
         s->tot_pot_energy += pot;
+        if (eeam) {                                      /* :1090-1095 */
+          pair_int(s, emod_pot, s->sorte[ia], nt, s->eam_p[ia], &pot, &s->dM[ia], &idummy);
+          s->poteng[ia] += pot;
+          s->tot_pot_energy += pot;
+        }
       }
     }
     send_cells_dF(s); /* :1115 */
@@ -794,11 +806,13 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
           double r2 = ((dx * dx) + (dy * dy)) + (dz * dz);
           int jt = s->sorte[ja], col1 = jt * nt + it, col2 = it * nt + jt;
           if ((r2 < rho_h_tab->end[col1]) || (r2 < rho_h_tab->end[col2])) { /* :1172 */
-            double dummy, rho_i_strich, rho_j_strich, grad, fx, fy, fz;
-            pair_int(s, rho_h_tab, col1, inc, r2, &dummy, &rho_i_strich, &is_short);
-            if (col1 == col2) rho_j_strich = rho_i_strich;
-            else pair_int(s, rho_h_tab, col2, inc, r2, &dummy, &rho_j_strich, &is_short);
+            double rho_i = 0.0, rho_j = 0.0, rho_i_strich, rho_j_strich, grad, fx, fy, fz;
+            pair_int(s, rho_h_tab, col1, inc, r2, &rho_i, &rho_i_strich, &is_short);
+            if (col1 == col2) { rho_j_strich = rho_i_strich; rho_j = rho_i; }
+            else pair_int(s, rho_h_tab, col2, inc, r2, &rho_j, &rho_j_strich, &is_short);
             grad = 0.5 * (s->dF[ia] * rho_j_strich + s->dF[ja] * rho_i_strich); /* :1203 */
+            if (eeam)                                    /* :1204-1208 */
+              grad += (s->dM[ia] * rho_j * rho_j_strich + s->dM[ja] * rho_i * rho_i_strich);
             fx = dx * grad; fy = dy * grad; fz = dz * grad;
             s->kraft[3 * ja] -= fx; s->kraft[3 * ja + 1] -= fy; s->kraft[3 * ja + 2] -= fz;
             ffx += fx; ffy += fy; ffz += fz;
@@ -977,7 +991,7 @@ void orc_destroy(orc_sim *s)
 {
   int w;
   if (!s) return;
-  for (w = 0; w < 3; w++) {
+  for (w = 0; w < 4; w++) {
     free(s->tab[w].begin); free(s->tab[w].end); free(s->tab[w].step); free(s->tab[w].invstep);
     free(s->tab[w].len); free(s->tab[w].table); free(s->tab[w].table2);
   }
@@ -1050,6 +1064,13 @@ void orc_get_box(const orc_sim *s, double o[9])
   o[0] = s->box_x.x; o[1] = s->box_x.y; o[2] = s->box_x.z;
   o[3] = s->box_y.x; o[4] = s->box_y.y; o[5] = s->box_y.z;
   o[6] = s->box_z.x; o[7] = s->box_z.y; o[8] = s->box_z.z;
+}
+
+long orc_get_eeam(const orc_sim *s, double *eam_p, double *dM)
+{
+  long n;
+  for (n = 0; n < s->n; n++) { if (eam_p) eam_p[n] = s->eam_p[n]; if (dM) dM[n] = s->dM[n]; }
+  return s->n;
 }
 
 long orc_get_atoms(const orc_sim *s, int *nummer, int *sorte, int *vsorte, double *masse, double *ort,

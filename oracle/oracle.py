@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 
-PAIR, EMBED, RHO = 0, 1, 2
+PAIR, EMBED, RHO, EMOD = 0, 1, 2, 3
 NVE, NVT = 0, 1
 
 
@@ -69,6 +69,8 @@ def lib():
         L.orc_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.orc_tot_presstens.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_interpolation.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_eeam.restype = C.c_long
+        L.orc_get_eeam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_deform_sample.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -80,14 +82,15 @@ INTERP = {"3point": 0, "4point": 1, "spline": 2}
 
 class OracleIMD:
     def __init__(self, ntypes, box, pbc=(1, 1, 1), nbl_margin=0.4, pair=None, embed=None, rho=None,
-                 default_fmt=1, interp="3point"):
+                 default_fmt=1, interp="3point", emod=None):
         L = lib()
         b = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(9))
         p = np.ascontiguousarray(np.asarray(pbc, dtype=np.int32))
         self.h = L.orc_create(int(ntypes), _p(b, C.c_double), _p(p, C.c_int), float(nbl_margin))
         self.press = False
         L.orc_set_interpolation(self.h, INTERP[interp] if isinstance(interp, str) else int(interp))
-        for which, path in ((PAIR, pair), (EMBED, embed), (RHO, rho)):
+        self.eeam = emod is not None
+        for which, path in ((PAIR, pair), (EMBED, embed), (RHO, rho), (EMOD, emod)):
             if path:
                 rc = L.orc_read_table(self.h, which, os.fspath(path).encode())
                 if rc:
@@ -195,6 +198,9 @@ class OracleIMD:
         order = ["nummer", "sorte", "vsorte", "masse", "ort", "impuls", "kraft", "poteng", "rho", "dF",
                  "presstens", "nblpos"]
         lib().orc_get_atoms(self.h, *[d[k].ctypes.data for k in order])
+        if self.eeam:
+            d["eam_p"] = np.zeros(n); d["dM"] = np.zeros(n)
+            lib().orc_get_eeam(self.h, d["eam_p"].ctypes.data, d["dM"].ctypes.data)
         if sort:
             o = np.argsort(d["nummer"], kind="stable")
             d = {k: v[o] for k, v in d.items()}

@@ -46,7 +46,9 @@ class RefIMD:
         L.ref_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.ref_pair_int.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_set_eta.argtypes = [C.c_double]
-        self.has_eam = variant.startswith("eam")
+        self.has_eam = variant.startswith("eam") or variant == "eeam"
+        self.has_eeam = variant == "eeam"
+        L.ref_get_eeam.restype = C.c_long
         if quiet:
             sys.stdout.flush()
             saved = os.dup(1)
@@ -144,6 +146,9 @@ class RefIMD:
             _p(d["kraft"], C.c_double), _p(d["poteng"], C.c_double), _p(d["rho"], C.c_double),
             _p(d["dF"], C.c_double), _p(d["presstens"], C.c_double), _p(d["nblpos"], C.c_double))
         assert got == n, (got, n)
+        if self.has_eeam:
+            d["eam_p"] = np.zeros(n); d["dM"] = np.zeros(n)
+            self.lib.ref_get_eeam(_p(d["eam_p"], C.c_double), _p(d["dM"], C.c_double))
         if sort:  # canonical order: by atom number
             o = np.argsort(d["nummer"], kind="stable")
             d = {k: v[o] for k, v in d.items()}

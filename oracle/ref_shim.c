@@ -138,6 +138,20 @@ long ref_get_atoms(int *nummer, int *sorte, int *vsorte, double *masse,
   return n;
 }
 
+/* EEAM per-atom fields (src/imd_forces_nbl.c:591-610, 1090-1095), same order as ref_get_atoms */
+long ref_get_eeam(double *eam_p, double *eam_dM)
+{
+  long n = 0;
+#ifdef EEAM
+  int k, i;
+  for (k = 0; k < NCELLS; k++) {
+    cell *p = CELLPTR(k);
+    for (i = 0; i < p->n; i++, n++) { if (eam_p) eam_p[n] = EAM_P(p,i); if (eam_dM) eam_dM[n] = EAM_DM(p,i); }
+  }
+#endif
+  return n;
+}
+
 /* overwrite positions / momenta of the real atoms (same traversal order as ref_get_atoms);
    used to put reference and candidate on bit-identical states */
 void ref_set_atoms(const double *ort, const double *impuls)
@@ -197,6 +211,9 @@ void ref_pair_int(int which, int col, double r2, double *pot, double *grad)
 #ifdef EAM2
   if (which == 1) { pt = &embed_pot; inc = ntypes; }
   if (which == 2) pt = &rho_h_tab;
+#endif
+#ifdef EEAM
+  if (which == 3) { pt = &emod_pot; inc = ntypes; }
 #endif
   if (!pt) return;
   PAIR_INT(p, g, *pt, col, inc, r2, is_short);

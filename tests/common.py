@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 TABLE_KEYS = {"core_potential_file": "pair", "embedding_energy_file": "embed",
-              "atomic_e-density_file": "rho", "potfile": "pair"}
+              "atomic_e-density_file": "rho", "potfile": "pair", "eeam_energy_file": "emod"}
 
 # parity bars (BASELINE.json north_star): neighbour sets bit-exact; forces, energies and pressure
 # within 1e-10 relative of IMD's CPU build.
@@ -42,6 +42,8 @@ def make_sim(factory, g, tabdir, **kw):
     ens = str(g["ensemble"])
     common = dict(pbc=tuple(int(x) for x in g["pbc"]), nbl_margin=0.4, pair=paths["pair"],
                   embed=paths.get("embed"), rho=paths.get("rho"))
+    if "emod" in paths:                                    # fixture of an `eeam` reference build
+        common["emod"] = paths["emod"]
     if "interp" in g and str(g["interp"]) != "3point":     # fixture of a `4point` / `spline` reference build
         common["interp"] = str(g["interp"])
     integ = dict(ensemble=ens, timestep=float(g["timestep"]), temperature=float(g["temperature"]),
@@ -144,7 +146,7 @@ def compare(out, g, full_list=False, rtol=RTOL, traj_rtol=None, ignore_shift=Fal
         a = out["atoms"][s]
         # error growth of a chaotic trajectory: first frame at the parity bar, later ones looser
         tol = rtol if s == rec[0] else (traj_rtol or rtol * 1e3)
-        for k in ("kraft", "poteng", "rho", "dF"):
+        for k in ("kraft", "poteng", "rho", "dF") + (("eam_p", "dM") if f"f{s}:eam_p" in g else ()):
             if np.max(np.abs(g[f"f{s}:{k}"])) == 0 and np.max(np.abs(a[k])) == 0:
                 continue
             e = relerr(a[k], g[f"f{s}:{k}"])

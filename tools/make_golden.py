@@ -65,6 +65,11 @@ CASES = {
                           record=[0, 11], press=False, variant="eam", deform_every=5,
                           extra=dict(pbc_dirs=[1, 1, 0], total_types=2, restrictionvector=[1, 1, 1, 0],
                                      max_deform_int=5, deform_size=1.0)),
+    # `eeam` reference build: second embedding term M(sum rho^2), single- and two-species
+    "cu_eeam": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=30, nsteps=12,
+                    record=[0, 11], press=True, variant="eeam", eeam=True),
+    "nial_eeam": dict(kind="nial", ncell=(5, 5, 5), ensemble="nvt", starttemp=0.06, warm=30, nsteps=12,
+                      record=[0, 11], press=False, variant="eeam", eeam=True),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
 }
@@ -72,7 +77,7 @@ CASES = {
 
 def table_arrays(paths):
     out = {}
-    for key in ("core_potential_file", "embedding_energy_file", "atomic_e-density_file", "potfile"):
+    for key in ("core_potential_file", "embedding_energy_file", "atomic_e-density_file", "potfile", "eeam_energy_file"):
         if key in paths:
             with open(paths[key]) as f:
                 out["table:" + key] = np.frombuffer(f.read().encode(), dtype=np.uint8)
@@ -81,6 +86,9 @@ def table_arrays(paths):
 
 def make_case(name, c):
     tmp = tempfile.mkdtemp(prefix="gold_" + name)
+    if c.get("eeam"):
+        emod = synth.make_eeam_table(tmp, nt=2 if c["kind"] == "nial" else 1)
+        c = dict(c, extra=dict(c.get("extra") or {}, eeam_energy_file=emod))
     if c["kind"] == "cu":
         tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
         p = synth.cu_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
@@ -116,6 +124,8 @@ def make_case(name, c):
                 record_atoms=c["record"], record_nbl=[0], press=c["press"],
                 lindef_every=c.get("lindef_every", 0), deform_every=c.get("deform_every", 0))
     out = rd.run_in_subprocess(spec, tmp)
+    if c.get("eeam"):
+        tabs = dict(tabs, eeam_energy_file=c["extra"]["eeam_energy_file"])
     g = dict(table_arrays(tabs))
     g["ntypes"] = ntypes
     g["ensemble"] = c["ensemble"]
@@ -157,7 +167,7 @@ def make_case(name, c):
     g["nbl_count"] = out["nbl_count"]
     for s in c["record"]:
         a = out["frames"][s]["atoms"]
-        for k in ("kraft", "poteng", "rho", "dF", "presstens", "ort"):
+        for k in ("kraft", "poteng", "rho", "dF", "presstens", "ort") + (("eam_p", "dM") if c.get("eeam") else ()):
             g[f"f{s}:{k}"] = a[k]
         if c["press"]:
             g[f"f{s}:tot_presstens"] = out["frames"][s]["tot_presstens"]
