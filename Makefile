@@ -7,7 +7,7 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-
 CFLAGS   := -O2 -fPIC -Wall -std=c99 -D_POSIX_C_SOURCE=200809L
 CU       := $(wildcard imd_b200/csrc/*.cu)
 HC       := $(wildcard imd_b200/host/*.c)
-OBJ      := $(CU:imd_b200/csrc/%.cu=build/%.o) build/forces_cubic.o $(HC:imd_b200/host/%.c=build/host_%.o)
+OBJ      := $(CU:imd_b200/csrc/%.cu=build/%.o) build/forces_cubic.o build/forces_eeam.o build/forces_cubic_eeam.o $(HC:imd_b200/host/%.c=build/host_%.o)
 LIB      := imd_b200/libimd_b200.so
 
 all: $(LIB)
@@ -20,6 +20,15 @@ build/%.o: imd_b200/csrc/%.cu imd_b200/csrc/internal.cuh include/imd_b200.h
 build/forces_cubic.o: imd_b200/csrc/forces.cu imd_b200/csrc/internal.cuh include/imd_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -DIMDB_CUBIC=1 -c $< -o $@ 2> build/forces_cubic.ptxas.log || (cat build/forces_cubic.ptxas.log; false)
+
+# ... and for the extended-EAM terms (EEAM builds of the reference)
+build/forces_eeam.o: imd_b200/csrc/forces.cu imd_b200/csrc/internal.cuh include/imd_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -DIMDB_EEAM=1 -c $< -o $@ 2> build/forces_eeam.ptxas.log || (cat build/forces_eeam.ptxas.log; false)
+
+build/forces_cubic_eeam.o: imd_b200/csrc/forces.cu imd_b200/csrc/internal.cuh include/imd_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -DIMDB_CUBIC=1 -DIMDB_EEAM=1 -c $< -o $@ 2> build/forces_cubic_eeam.ptxas.log || (cat build/forces_cubic_eeam.ptxas.log; false)
 
 build/host_%.o: imd_b200/host/%.c include/imd_b200.h
 	@mkdir -p build

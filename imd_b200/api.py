@@ -54,7 +54,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam",
 ]
 
 _lib = None
@@ -91,6 +91,10 @@ def load_library():
     L.imdb200_deform_sample.argtypes = [vp, C.c_double, vp, vp, vp, vp]
     L.imdb200_get_scalars.argtypes = [vp, C.POINTER(Scalars)]
     L.imdb200_get_atoms.restype = C.c_long
+    L.imdb200_get_eeam.restype = C.c_long
+    L.imdb200_get_eeam.argtypes = [vp, vp, vp]
+    L.imdb200_set_eeam_table.argtypes = [vp, C.POINTER(PotTable)]
+    L.imdb200_get_box.argtypes = [vp, vp]
     L.imdb200_get_atoms.argtypes = [vp] + [vp] * 12
     L.imdb200_natoms_local.restype = C.c_long
     L.imdb200_natoms_local.argtypes = [vp]
@@ -189,7 +193,7 @@ class IMDB200:
     def __init__(self, ntypes, box, pbc=(1, 1, 1), nbl_margin=0.4, nbl_size=1.1, pair=None, embed=None,
                  rho=None, default_fmt=None, ensemble="nve", timestep=0.001, temperature=0.0, eta=0.0,
                  isq_tau_eta=0.0, device=-1, lanes_per_atom=0, total_types=None, cpu_dim=(1, 1, 1),
-                 my_coord=(0, 0, 0), interp="3point"):
+                 my_coord=(0, 0, 0), interp="3point", emod=None):
         L = load_library()
         self.L = L
         cfg = Config()
@@ -209,8 +213,11 @@ class IMDB200:
         _chk(L.imdb200_create(C.byref(cfg), C.byref(self.h)))
         self.ntypes = int(ntypes)
         self._tabs = []
+        self.eeam = False
         if pair is not None:
             self.set_potentials(pair, embed, rho, default_fmt)
+        if emod is not None:
+            self.set_eeam_table(emod)
 
     def close(self):
         if getattr(self, "h", None):
@@ -240,6 +247,13 @@ class IMDB200:
             self._tabs += [te, tr]
         _chk(self.L.imdb200_set_potentials(self.h, C.byref(tp), C.byref(te) if eam else None,
                                            C.byref(tr) if eam else None))
+
+    def set_eeam_table(self, emod):
+        """`eeam_energy_file` of an EEAM build: M(p), ntypes columns, not radial."""
+        tm, _ = read_pot_table(emod, self.ntypes, 0, self.ntypes, 2)
+        self._tabs.append(tm)
+        _chk(self.L.imdb200_set_eeam_table(self.h, C.byref(tm)))
+        self.eeam = True
 
     def comm_init(self, unique_id, rank, nranks):
         """Join the NCCL communicator of the process grid (one process per GPU); see imdb200_comm_init."""
@@ -366,6 +380,9 @@ class IMDB200:
                  "presstens", "nblpos"]
         got = self.L.imdb200_get_atoms(self.h, *[d[k].ctypes.data for k in order])
         assert got == n
+        if self.eeam:
+            d["eam_p"] = np.zeros(n); d["dM"] = np.zeros(n)
+            assert self.L.imdb200_get_eeam(self.h, d["eam_p"].ctypes.data, d["dM"].ctypes.data) == n
         if sort:
             o = np.argsort(d["nummer"], kind="stable")
             d = {k: v[o] for k, v in d.items()}

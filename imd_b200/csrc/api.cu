@@ -102,7 +102,7 @@ void imdb200_destroy(imdb200_sim *s)
   void *ptrs[] = {s->posdf, s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF,
                   s->nblpos, s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start,
                   s->cell_fill, s->cell_code, s->gsrc, s->ghost_num, s->ghost_raw, s->scan_tmp, s->nbl, s->nnb,
-                  s->restr, s->d_scal, s->d_partial, s->d_flags, s->xfer, s->nnbc, s->posf};
+                  s->restr, s->d_scal, s->d_partial, s->d_flags, s->xfer, s->nnbc, s->posf, s->eam_p, s->dM};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->h_flags) cudaFreeHost(s->h_flags);
@@ -118,6 +118,13 @@ int imdb200_set_potentials(imdb200_sim *s, const imdb200_pot_table *pair, const 
   CUDA_TRY(cudaSetDevice(s->cfg.device));
   TRY(tables_upload(s, pair, embed, rho));
   return geom_make_box(s);
+}
+
+int imdb200_set_eeam_table(imdb200_sim *s, const imdb200_pot_table *emod)
+{
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  return tables_upload_emod(s, emod);
 }
 
 int imdb200_set_stream(imdb200_sim *s, void *stream)
@@ -249,6 +256,7 @@ static int calc_forces_async(imdb200_sim *s)
   TRY(forces_pass1(s));
   if (s->tabs.have_eam) {
     TRY(comm_ghost_dF(s));                             // send_cells(copy_dF,...) (:1115)
+    if (s->tabs.have_eeam) TRY(comm_ghost_dM(s));
     TRY(forces_pass2(s, 0));
   }
   return 0;
@@ -318,7 +326,7 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     cudaEventRecord(s->ev[2], s->stream);
     // single-species EAM: move_atoms + check_nblist ride in the tail of pass 2 (bit-identical, one kernel less)
     const int fuse = forces_can_fuse_move(s);
-    if (s->tabs.have_eam) { TRY(comm_ghost_dF(s)); TRY(forces_pass2(s, fuse)); }
+    if (s->tabs.have_eam) { TRY(comm_ghost_dF(s)); if (s->tabs.have_eeam) TRY(comm_ghost_dM(s)); TRY(forces_pass2(s, fuse)); }
     cudaEventRecord(s->ev[3], s->stream);
     if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
     cudaEventRecord(s->ev[4], s->stream);
@@ -396,6 +404,17 @@ int imdb200_get_box(imdb200_sim *s, double out9[9])
   if (!s || !out9) return imdb_fail(IMDB200_ERR_ARG, "null argument");
   for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) out9[3 * b + d] = s->geom.box[b][d];
   return 0;
+}
+
+long imdb200_get_eeam(imdb200_sim *s, double *eam_p, double *dM)
+{
+  if (!s || s->n_own <= 0 || !s->tabs.have_eeam) return 0;
+  cudaSetDevice(s->cfg.device);
+  const long n = s->n_own;
+  if (eam_p) cudaMemcpyAsync(eam_p, s->eam_p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+  if (dM) cudaMemcpyAsync(dM, s->dM, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+  if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+  return n;
 }
 
 long imdb200_natoms_local(imdb200_sim *s) { return s ? s->n_own : 0; }

@@ -103,6 +103,7 @@ int cells_ensure_capacity(imdb200_sim *s, long need)
   TRY(regrow(&s->frc, n, cap)); TRY(regrow(&s->posdf, 0, cap));
   TRY(regrow(&s->nummer, n, cap)); TRY(regrow(&s->nummer_alt, 0, cap));
   TRY(regrow(&s->rho, n, cap)); TRY(regrow(&s->dF, n, cap));
+  TRY(regrow(&s->eam_p, 0, cap)); TRY(regrow(&s->dM, 0, cap));
   TRY(regrow(&s->cellid, n, cap)); TRY(regrow(&s->cellid_alt, 0, cap)); TRY(regrow(&s->perm, 0, cap));
   TRY(regrow(&s->gsrc, 0, cap)); TRY(regrow(&s->ghost_num, 0, cap)); TRY(regrow(&s->ghost_raw, 0, cap));
   TRY(regrow(&s->posf, 0, cap));

@@ -425,6 +425,20 @@ int comm_ghost_dF(imdb200_sim *s)
   return 0;
 }
 
+// EEAM builds copy EAM_DM together with EAM_DF (src/imd_comm_force_3d.c:1044-1046, 1116-1118, 1155-1157)
+int comm_ghost_dM(imdb200_sim *s)
+{
+  if (s->n_ghost == 0) return 0;
+  if (s->n_send) {
+    TRY(need_comm(s));
+    k_pack1<<<cdiv(s->n_send, 256), 256, 0, s->stream>>>(s->dM, s->send_idx, s->n_send, s->sendbuf1); LAUNCH_CHECK();
+    TRY(exchange_forward<double>(s, s->sendbuf1, s->dM + s->n_own, ncclFloat64, 1));
+  }
+  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dM, nullptr, s->pos, s->n_own, s->n_ghost, s->gsrc);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // send_forces(add_*, pack_*, unpack_*): field[c*stride + i], c < ncomp.  The image entries
 // [n_own, n_own+n_ghost) are added to their owners; the full-list force kernels never write to images,
 // so the step loop does not need this -- it is the reference's reverse path for callers that accumulate

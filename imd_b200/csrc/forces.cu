@@ -56,21 +56,33 @@
 // This file is compiled twice (Makefile): IMDB_CUBIC=0 holds the quadratic (PAIR_INT2) kernels and everything the
 // two builds share, IMDB_CUBIC=1 the same kernels for the cubic table modes (PAIR_INT3 / PAIR_INT_SP, one more
 // coefficient per lookup).  The kernels carry the flag as a template argument so that their symbols differ.
+// IMDB_EEAM=1 adds the extended-EAM terms (EEAM builds of the reference, src/imd_forces_nbl.c:591-610, 1090-1095,
+// 1181-1208): p_i = sum rho^2 in pass 1, a second embedding look-up M(p_i), and the dM terms in pass 2.
 #ifndef IMDB_CUBIC
 #define IMDB_CUBIC 0
 #endif
-#if IMDB_CUBIC
+#ifndef IMDB_EEAM
+#define IMDB_EEAM 0
+#endif
+#if IMDB_CUBIC && IMDB_EEAM
+#define IMPL(name) name##_cubic_eeam
+#elif IMDB_CUBIC
 #define IMPL(name) name##_cubic
+#elif IMDB_EEAM
+#define IMPL(name) name##_quad_eeam
 #else
 #define IMPL(name) name##_quad
 #endif
+#define IMDB_BASE_TU (!IMDB_CUBIC && !IMDB_EEAM)
 static constexpr bool CUBIC = IMDB_CUBIC != 0;
+static constexpr bool EEAMC = IMDB_EEAM != 0;
 
 struct FArgs {
   const double4 *pos;
   double4 *posdf;
   double4 *frc;
   double *rho, *dF;
+  double *eam_p, *dM;            // EEAM: p_i = sum rho^2 and M'(p_i) (EAM_P, EAM_DM)
   const int *nbl;
   cudaTextureObject_t tpos, tposdf;   // the same atom records as linear int4 textures (two texels per atom)
   int use_tex;                        // 0: the atom arrays exceed the 1-D linear texture limit, every gather on the LSU path
@@ -114,7 +126,7 @@ __device__ __forceinline__ void stage(void *dst, const void *src, int bytes)
 // pass 1: pair potential + host electron density (src/imd_forces_nbl.c:422-981), then the embedding
 // energy F(rho_i) and 2F'(rho_i) (:1079-1095)
 // ----------------------------------------------------------------------------------------------------
-template <int NT, int L, bool EAM, bool MULTI, bool SHARED, bool STRESS, bool TSMEM, bool CUB>
+template <int NT, int L, bool EAM, bool MULTI, bool SHARED, bool STRESS, bool TSMEM, bool CUB, bool EE>
 __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
     const long i = slot / L;
     const int sub = (int) (slot % L);
     const bool act = i < a.n_own;
-    double fx = 0.0, fy = 0.0, fz = 0.0, ee = 0.0, rh = 0.0, vir = 0.0;
+    double fx = 0.0, fy = 0.0, fz = 0.0, ee = 0.0, rh = 0.0, vir = 0.0, ph = 0.0;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
     int it = 0;
     double4 xi = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -222,8 +234,11 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         }
         if (inr) {
           const int e = MULTI ? kr * T.rho.ncols + col : kr;
-          if (CUB) rh += tab_val3(rAB[e], rCD[e], chir);
-          else rh += FUSED ? tab_val(fT[3 * kr + 2], fmid.y, chir) : tab_val(rAB[e], rC[e], chir);
+          double rv;
+          if (CUB) rv = tab_val3(rAB[e], rCD[e], chir);
+          else rv = FUSED ? tab_val(fT[3 * kr + 2], fmid.y, chir) : tab_val(rAB[e], rC[e], chir);
+          rh += rv;
+          if (EE) ph = fma(rv, rv, ph);                      // eam_p += rho_h*rho_h (:591-593)
         }
         }
       }
@@ -232,6 +247,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
       fx = lanes_sum<L>(fx); fy = lanes_sum<L>(fy); fz = lanes_sum<L>(fz);
       ee = lanes_sum<L>(ee); vir = lanes_sum<L>(vir);
       if (EAM) rh = lanes_sum<L>(rh);
+      if (EE) ph = lanes_sum<L>(ph);
       if (STRESS) { s0 = lanes_sum<L>(s0); s1 = lanes_sum<L>(s1); s2 = lanes_sum<L>(s2);
                     s3 = lanes_sum<L>(s3); s4 = lanes_sum<L>(s4); s5 = lanes_sum<L>(s5); }
     }
@@ -252,6 +268,14 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         }
         a.rho[i] = rh;
         a.dF[i] = dF;
+        if (EE) {                                          // PAIR_INT(pot, EAM_DM, emod_pot, ..., EAM_P) :1091-1094
+          tab_index(ph, T.emod.begin[it], T.emod.end[it], T.emod.invstep[it], k, chi, dummy);
+          const double *m = T.emodVG + ((size_t) k * T.emod.ncols + it) * 8;
+          const double2 m0 = ld2(m), m1 = ld2(m + 2), m2 = ld2(m + 4);
+          epot += tab_val3(m0, CUB ? m1 : make_double2(m1.x, 0.0), chi);
+          a.eam_p[i] = ph;
+          a.dM[i] = fma(chi, CUB ? fma(chi, __ldg(m + 6), m2.y) : m2.y, m2.x);
+        }
         if (!MULTI) a.posdf[i] = make_double4(xi.x, xi.y, xi.z, dF);
       }
       a.frc[i] = make_double4(fx, fy, fz, epot);
@@ -271,7 +295,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 // ----------------------------------------------------------------------------------------------------
 // pass 2: EAM forces (src/imd_forces_nbl.c:1117-1322)
 // ----------------------------------------------------------------------------------------------------
-template <int NT, int L, bool MULTI, bool STRESS, bool TSMEM, bool FUSE, bool CUB>
+template <int NT, int L, bool MULTI, bool STRESS, bool TSMEM, bool FUSE, bool CUB, bool EE>
 __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -304,6 +328,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       const double4 xi = gat[i];
       const int it = MULTI ? sorte_of(xi.w) : 0;
       const double dFi = MULTI ? a.dF[i] : xi.w;
+      const double dMi = EE ? a.dM[i] : 0.0;
       const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
       int jq[FDEPTH2];                                    // software pipeline as in pass 1
@@ -311,12 +336,12 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       for (int d = 0; d < FDEPTH2; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
       for (int m = sub; m < nn; m += FDEPTH2 * L, row += FDEPTH2 * 32) {
         double4 xq[FDEPTH2];
-        int jc[MULTI ? FDEPTH2 : 1];
+        int jc[(MULTI || EE) ? FDEPTH2 : 1];
 #pragma unroll
         for (int d = 0; d < FDEPTH2; d++) {
           const int j = jq[d] >= 0 ? jq[d] : (int) i;
           xq[d] = (d < IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j);
-          if (MULTI) jc[d] = j;
+          if (MULTI || EE) jc[d] = j;
         }
 #pragma unroll
         for (int d = 0; d < FDEPTH2; d++) jq[d] = (m + (FDEPTH2 + d) * L < nn) ? __ldcs(row + (FDEPTH2 + d) * 32) : -1;
@@ -324,7 +349,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
         for (int d = 0; d < FDEPTH2; d++) {
         if (m + d * L >= nn) break;
         const double4 xj = xq[d];
-        const int j = MULTI ? jc[d] : 0;
+        const int j = (MULTI || EE) ? jc[d] : 0;
         const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         double grad;
@@ -332,9 +357,19 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           if (!(r2 < r_end0)) continue;                    // :1172
           int k; double chi;
           tab_index_fast(r2, r_nb0, r_is0, k, chi, is_short);
-          const double2 h = rH[k];
-          const double hs = CUB ? fma(chi, rH3[k], h.y) : h.y;
-          grad = (dFi + xj.w) * fma(chi, hs, h.x);         // 0.5*(dF_i+dF_j)*rho' (:1203), col1 == col2
+          if (!EE) {
+            const double2 h = rH[k];
+            const double hs = CUB ? fma(chi, rH3[k], h.y) : h.y;
+            grad = (dFi + xj.w) * fma(chi, hs, h.x);       // 0.5*(dF_i+dF_j)*rho' (:1203), col1 == col2
+          } else {
+            // EEAM needs rho(r) as well: value and rho'/2 from the pass-1 coefficient arrays
+            const double2 ab = T.rhoAB[k];
+            double rv, hv;
+            if (CUB) { const double2 cd = T.rhoCD[k]; rv = tab_val3(ab, cd, chi); hv = r_is0 * fma(chi, fma(3.0 * chi, cd.y, cd.x + cd.x), ab.y); }
+            else { const double c2 = T.rhoC[k]; rv = tab_val(ab, c2, chi); hv = r_is0 * fma(chi + chi, c2, ab.y); }
+            // 0.5*(dF_i+dF_j)*rho' + (dM_i+dM_j)*rho*rho'  (:1203-1208), rho' = 2*hv
+            grad = (dFi + xj.w) * hv + (dMi + __ldg(a.dM + j)) * (rv * (hv + hv));
+          }
         } else {
           const int jt = sorte_of(xj.w);
           const int col1 = jt * nt + it, col2 = it * nt + jt;
@@ -344,13 +379,19 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           tab_index(r2, T.rho.begin[col1], T.rho.end[col1], T.rho.invstep[col1], k, chi, is_short);
           double2 h = rH[k * T.rho.ncols + col1];
           const double rho_i_strich = fma(chi, CUB ? fma(chi, rH3[k * T.rho.ncols + col1], h.y) : h.y, h.x);
-          double rho_j_strich = rho_i_strich;
+          double rho_j_strich = rho_i_strich, rho_i = 0.0, rho_j = 0.0;
+          if (EE) { const int e = k * T.rho.ncols + col1;
+                    rho_i = CUB ? tab_val3(T.rhoAB[e], T.rhoCD[e], chi) : tab_val(T.rhoAB[e], T.rhoC[e], chi); rho_j = rho_i; }
           if (col1 != col2) {
             tab_index(r2, T.rho.begin[col2], T.rho.end[col2], T.rho.invstep[col2], k, chi, is_short);
             h = rH[k * T.rho.ncols + col2];
             rho_j_strich = fma(chi, CUB ? fma(chi, rH3[k * T.rho.ncols + col2], h.y) : h.y, h.x);
+            if (EE) { const int e = k * T.rho.ncols + col2;
+                      rho_j = CUB ? tab_val3(T.rhoAB[e], T.rhoCD[e], chi) : tab_val(T.rhoAB[e], T.rhoC[e], chi); }
           }
           grad = dFi * rho_j_strich + __ldg(a.dF + j) * rho_i_strich;
+          // + dM_i*rho_j*rho_j' + dM_j*rho_i*rho_i' (:1204-1208); the "strich" values here are rho'/2
+          if (EE) grad += 2.0 * (dMi * rho_j * rho_j_strich + __ldg(a.dM + j) * rho_i * rho_i_strich);
         }
         fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
         vir = fma(r2, grad, vir);                          // SPROD(d,force) = r2*grad (:1280)
@@ -403,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   }
 }
 
-#if !IMDB_CUBIC
+#if IMDB_BASE_TU
 // ----------------------------------------------------------------------------------------------------
 // deterministic second reduction stage: one block sums the per-block partials in a fixed order
 // (replaces the MPI_Allreduce operand build-up of src/imd_forces_nbl.c:1975-1994 on one rank)
@@ -432,7 +473,7 @@ int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int 
   return 0;
 }
 
-#endif  // !IMDB_CUBIC
+#endif  // IMDB_BASE_TU
 
 // ----------------------------------------------------------------------------------------------------
 // launch wrappers: pick the template instance
@@ -449,7 +490,7 @@ static int skin_class(const imdb200_sim *s)
   return c < NBL_CLASSES ? c : NBL_CLASSES;
 }
 
-#if !IMDB_CUBIC
+#if IMDB_BASE_TU
 // The atom records as linear textures.  The L1 of an SM has two front ends, LSU (ld.global, shared memory) and TEX;
 // the force passes saturate the LSU data pipe with table look-ups + gathers while TEX idles, so a fixed share of
 // the gathers of every block goes through TEX instead (profiles/README.md, "two pipes").
@@ -492,7 +533,7 @@ static FArgs make_args(imdb200_sim *s)
 {
   FArgs a;
   a.tpos = s->tex_pos; a.tposdf = s->tex_posdf; a.use_tex = s->tex_ok;
-  a.pos = s->pos; a.posdf = s->posdf; a.frc = s->frc; a.rho = s->rho; a.dF = s->dF; a.nbl = s->nbl; a.nnbc = s->nnbc;
+  a.pos = s->pos; a.posdf = s->posdf; a.frc = s->frc; a.rho = s->rho; a.dF = s->dF; a.eam_p = s->eam_p; a.dM = s->dM; a.nbl = s->nbl; a.nnbc = s->nnbc;
   a.cls_shift = NBL_CBITS * skin_class(s);
   a.n_own = s->n_own; a.rows = s->max_nb / s->lanes;
   a.presstens = s->presstens; a.pstride = s->cap_atoms;
@@ -522,44 +563,55 @@ template <typename K> static int launch_k(K kern, imdb200_sim *s, const FArgs &a
 
 // the per-atom stress variant needs twelve more accumulator registers: half the threads, twice the registers
 #define P1(L, EAM, MULTI, SHARED) \
-  (s->press_calc ? (ts ? launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, true, CUBIC>, s, a, 512, sm) \
-                       : launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, false, CUBIC>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, true, CUBIC>, s, a, IMDB_NT, sm) \
-                       : launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, false, CUBIC>, s, a, IMDB_NT, 0)))
+  (s->press_calc ? (ts ? launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, true, CUBIC, EEAMC>, s, a, 512, sm) \
+                       : launch_k(k_pass1<512, L, EAM, MULTI, SHARED, true, false, CUBIC, EEAMC>, s, a, 512, 0)) \
+                 : (ts ? launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, true, CUBIC, EEAMC>, s, a, IMDB_NT, sm) \
+                       : launch_k(k_pass1<IMDB_NT, L, EAM, MULTI, SHARED, false, false, CUBIC, EEAMC>, s, a, IMDB_NT, 0)))
 
 template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 {
   const bool multi = s->tabs.ntypes > 1, ts = s->tabs.smem1 > 0;
   const int sm = s->tabs.smem1;
+#if IMDB_EEAM
+  if (!s->tabs.have_eam) return imdb_fail(IMDB200_ERR_ARG, "EEAM needs EAM tables");
+#else
   if (!s->tabs.have_eam) return multi ? P1(L, false, true, false) : P1(L, false, false, false);
+#endif
   if (s->tabs.shared_grid) return multi ? P1(L, true, true, true) : P1(L, true, false, true);
   return multi ? P1(L, true, true, false) : P1(L, true, false, false);
 }
 
 #define P2(L, MULTI, FUSE) \
-  (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true, false, CUBIC>, s, a, 512, sm) \
-                       : launch_k(k_pass2<512, L, MULTI, true, false, false, CUBIC>, s, a, 512, 0)) \
-                 : (ts ? launch_k(k_pass2<IMDB_NT2, L, MULTI, false, true, FUSE, CUBIC>, s, a, IMDB_NT2, sm) \
-                       : launch_k(k_pass2<IMDB_NT2, L, MULTI, false, false, FUSE, CUBIC>, s, a, IMDB_NT2, 0)))
+  (s->press_calc ? (ts ? launch_k(k_pass2<512, L, MULTI, true, true, false, CUBIC, EEAMC>, s, a, 512, sm) \
+                       : launch_k(k_pass2<512, L, MULTI, true, false, false, CUBIC, EEAMC>, s, a, 512, 0)) \
+                 : (ts ? launch_k(k_pass2<IMDB_NT2, L, MULTI, false, true, FUSE, CUBIC, EEAMC>, s, a, IMDB_NT2, sm) \
+                       : launch_k(k_pass2<IMDB_NT2, L, MULTI, false, false, FUSE, CUBIC, EEAMC>, s, a, IMDB_NT2, 0)))
 
 template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
 {
-  const bool multi = s->tabs.ntypes > 1, ts = s->tabs.smem2 > 0;
+  const bool multi = s->tabs.ntypes > 1, ts = s->tabs.smem2 > 0 && !(EEAMC && !multi);   // single-species EEAM reads rhoAB/rhoC
   const int sm = s->tabs.smem2;
   if (multi) return P2(L, true, false);
   return fuse ? P2(L, false, true) : P2(L, false, false);
 }
 
-#if !IMDB_CUBIC
+#if IMDB_BASE_TU
 // move_atoms can ride in the tail of pass 2 when pass 2 does not gather from pos (single species) and neither
 // the per-atom stress nor restriction vectors are in play
 int forces_can_fuse_move(const imdb200_sim *s)
 { return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0; }
 
-int forces_pass1_cubic(imdb200_sim *s);
-int forces_pass2_cubic(imdb200_sim *s, int fuse);
-int forces_pass1(imdb200_sim *s) { return s->tabs.cubic ? forces_pass1_cubic(s) : forces_pass1_quad(s); }
-int forces_pass2(imdb200_sim *s, int fuse) { return s->tabs.cubic ? forces_pass2_cubic(s, fuse) : forces_pass2_quad(s, fuse); }
+// forces.cu is compiled four times: quadratic / cubic table interpolation, each without / with the EEAM terms
+int forces_pass1(imdb200_sim *s)
+{
+  if (s->tabs.have_eeam) return s->tabs.cubic ? forces_pass1_cubic_eeam(s) : forces_pass1_quad_eeam(s);
+  return s->tabs.cubic ? forces_pass1_cubic(s) : forces_pass1_quad(s);
+}
+int forces_pass2(imdb200_sim *s, int fuse)
+{
+  if (s->tabs.have_eeam) return s->tabs.cubic ? forces_pass2_cubic_eeam(s, fuse) : forces_pass2_quad_eeam(s, fuse);
+  return s->tabs.cubic ? forces_pass2_cubic(s, fuse) : forces_pass2_quad(s, fuse);
+}
 #endif
 
 int IMPL(forces_pass1)(imdb200_sim *s)

@@ -54,6 +54,10 @@ struct DevTables {
   const double2 *rhoCD;   // [nrows][ncols]  (c2,c3) of rho
   const double  *rhoH3;   // [nrows][ncols]  h3: rho'/2 = h1+chi*(h2+chi*h3)
   int cubic;
+  // EEAM (extended EAM): energy modification term M(p), p = sum rho^2 -- same layout as embedVG
+  TabMeta emod;
+  const double  *emodVG;
+  int have_eeam;
   const double2 *fused;   // single species, phi and rho on one r^2 grid: [nrows][3] = (phi c0,c1) (phi c2, rho c2) (rho c0,c1),
                           // one 48-byte record per interval = three 16-byte loads per pair in pass 1
   int fused_rows;
@@ -105,7 +109,7 @@ struct imdb200_sim {
   double height[3], min_height[3], max_height[3], volume, volume_init;
   double cellsz0;                 // max table end (r^2) before the margin is added
   DevTables tabs;
-  void *tab_mem[8];               // device allocations behind DevTables
+  void *tab_mem[12];              // device allocations behind DevTables
   int have_tabs;
   cudaStream_t stream; int own_stream;
   // atoms
@@ -115,6 +119,7 @@ struct imdb200_sim {
   double4 *pos, *pos_alt, *mom, *mom_alt, *frc;
   int *nummer, *nummer_alt;
   double *rho, *dF, *nblpos, *presstens; // presstens [6][cap] SoA
+  double *eam_p, *dM;             // EEAM: p_i = sum rho^2 (owners) and M'(p_i) (owners and images)
   double4 *posdf;                 // single-species EAM: x,y,z + 2F'(rho) in .w, the pass-2 gather record
   int *cellid, *cellid_alt, *perm;
   void *xfer; size_t xfer_bytes;  // staging for set_atoms / get_atoms
@@ -203,6 +208,7 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
                   const imdb200_pot_table *rho);
 void tables_free(imdb200_sim *s);
 int tables_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2, double *pot, double *grad);
+int tables_upload_emod(imdb200_sim *s, const imdb200_pot_table *emod);   // EEAM energy modification term
 
 int geom_make_box(imdb200_sim *s);           // make_box + init_cells when needed
 int cells_ensure_capacity(imdb200_sim *s, long n_atoms_total);
@@ -216,6 +222,7 @@ int comm_migrate(imdb200_sim *s, const int *h_counts, long n_stay, long *n_new);
 int comm_setup_ghosts(imdb200_sim *s);        // per-cell counts, ghost ranges, send lists (at a rebuild)
 int comm_ghost_pos(imdb200_sim *s);           // send_cells(copy_cell,pack_cell,unpack_cell)
 int comm_ghost_dF(imdb200_sim *s);            // send_cells(copy_dF,pack_dF,unpack_dF)
+int comm_ghost_dM(imdb200_sim *s);            // the EAM_DM part of copy_dF in EEAM builds (src/imd_comm_force_3d.c:1044-1046)
 int comm_reverse_add(imdb200_sim *s, double *field, int ncomp, long stride);  // send_forces(add_*,...)
 int comm_sync_scalars(imdb200_sim *s);        // the MPI_Allreduce sites
 int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
@@ -229,6 +236,10 @@ int forces_pass1_quad(imdb200_sim *s);        // forces.cu is compiled once per 
 int forces_pass2_quad(imdb200_sim *s, int fuse_move);
 int forces_pass1_cubic(imdb200_sim *s);
 int forces_pass2_cubic(imdb200_sim *s, int fuse_move);
+int forces_pass1_quad_eeam(imdb200_sim *s);
+int forces_pass2_quad_eeam(imdb200_sim *s, int fuse_move);
+int forces_pass1_cubic_eeam(imdb200_sim *s);
+int forces_pass2_cubic_eeam(imdb200_sim *s, int fuse_move);
 int integrate_finish(imdb200_sim *s, int nblocks_move);   // reductions + Nose-Hoover update after the per-atom part
 int integrate_move(imdb200_sim *s);           // move_atoms_nve/nvt + check_nblist fused
 int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask);

@@ -119,7 +119,7 @@ template <typename T> static int upload(imdb200_sim *s, int slot, const std::vec
 
 void tables_free(imdb200_sim *s)
 {
-  for (int i = 0; i < 8; i++) { if (s->tab_mem[i]) cudaFree(s->tab_mem[i]); s->tab_mem[i] = nullptr; }
+  for (int i = 0; i < 12; i++) { if (s->tab_mem[i]) cudaFree(s->tab_mem[i]); s->tab_mem[i] = nullptr; }
   s->have_tabs = 0;
 }
 
@@ -235,6 +235,34 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
   T.smem2 = (bytes2 && bytes2 <= limit) ? (int) bytes2 : 0;
   s->cellsz0 = cz;
   s->have_tabs = 1;
+  return 0;
+}
+
+// EEAM: the energy modification term M(p) (emod_pot, src/imd_potential.c:82-85), one column per type, not radial.
+// Same derived layout as the embedding table: c0 c1 c2 c3 | g1 g2 g3 -.
+int tables_upload_emod(imdb200_sim *s, const imdb200_pot_table *emod)
+{
+  if (!s->have_tabs || !s->tabs.have_eam) return imdb_fail(IMDB200_ERR_ARG, "set the EAM tables before the EEAM table");
+  DevTables &T = s->tabs;
+  if (s->tab_mem[8]) { cudaFree(s->tab_mem[8]); s->tab_mem[8] = nullptr; }
+  T.have_eeam = 0; T.emodVG = nullptr;
+  if (!emod) return 0;
+  if (emod->ncols != T.ntypes) return imdb_fail(IMDB200_ERR_ARG, "EEAM table has %d columns, need %d", emod->ncols, T.ntypes);
+  TRY(fill_meta(T.emod, emod));
+  HostTab hm;
+  prepare(hm, emod, s->cfg.interpolation, 0);
+  double c4[4];
+  std::vector<double> h((size_t) emod->maxsteps * emod->ncols * 8, 0.0);
+  for (int k = 0; k < emod->maxsteps; k++)
+    for (int col = 0; col < emod->ncols; col++) {
+      coef(hm, k, col, c4);
+      double *o = &h[((size_t) k * emod->ncols + col) * 8];
+      const double is2 = 2 * emod->invstep[col];
+      o[0] = c4[0]; o[1] = c4[1]; o[2] = c4[2]; o[3] = c4[3];
+      o[4] = is2 * c4[1]; o[5] = 2 * is2 * c4[2]; o[6] = 3 * is2 * c4[3];
+    }
+  TRY(upload(s, 8, h, &T.emodVG));
+  T.have_eeam = 1;
   return 0;
 }
 

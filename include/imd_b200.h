@@ -101,6 +101,14 @@ void imdb200_destroy(imdb200_sim *sim);
 int  imdb200_set_potentials(imdb200_sim *sim, const imdb200_pot_table *pair,
                             const imdb200_pot_table *embed, const imdb200_pot_table *rho);
 
+/* EEAM builds (make targets with `eeam`, src/Makefile:1161-1163): the energy modification term M(p_i),
+ * p_i = sum_j rho_j(r_ij)^2 -- emod_pot, read from `eeam_energy_file` with ntypes columns, not radial
+ * (src/imd_potential.c:82-85).  Call after imdb200_set_potentials; NULL switches the term off again.  Replaces the
+ * `#ifdef EEAM` branches of calc_forces (src/imd_forces_nbl.c:591-610, 1090-1095, 1181-1208). */
+int  imdb200_set_eeam_table(imdb200_sim *sim, const imdb200_pot_table *emod);
+/* EAM_P and EAM_DM of the owned atoms, in the order of imdb200_get_atoms; returns the count */
+long imdb200_get_eeam(imdb200_sim *sim, double *eam_p, double *eam_dM);
+
 /* restrictions per virtual type (3 doubles each); default all 1 (src/imd_param.c:2053-2066) */
 int  imdb200_set_restrictions(imdb200_sim *sim, int total_types, const double *restrictions);
 

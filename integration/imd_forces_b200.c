@@ -157,6 +157,9 @@ static void b200_init(void)
 #ifdef EAM2
   b200_check(imdb200_set_potentials(b200, (imdb200_pot_table *) &pair_pot, (imdb200_pot_table *) &embed_pot,
                                     (imdb200_pot_table *) &rho_h_tab));
+#ifdef EEAM   /* `eeam` make targets: energy modification term M(p), src/imd_potential.c:82-85 */
+  b200_check(imdb200_set_eeam_table(b200, (imdb200_pot_table *) &emod_pot));
+#endif
 #else
   b200_check(imdb200_set_potentials(b200, (imdb200_pot_table *) &pair_pot, NULL, NULL));
 #endif

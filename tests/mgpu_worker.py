@@ -42,7 +42,7 @@ def make(g, tabdir, grid, **kw):
                        timestep=float(g["timestep"]), temperature=float(g["temperature"]), eta=float(g["eta0"]),
                        isq_tau_eta=float(g["isq_tau_eta"]),
                        total_types=int(g["total_types"]) if "total_types" in g else None,
-                       interp=str(g["interp"]) if "interp" in g else "3point", **kw)
+                       interp=str(g["interp"]) if "interp" in g else "3point", emod=paths.get("emod"), **kw)
     if "restrictions" in g:
         sim.set_restrictions(g["restrictions"])
     # every rank is handed ALL atoms and keeps those of its own domain

@@ -64,6 +64,20 @@ def test_cuda_deformation_and_restrictions_match_reference_fixture(api, name, la
     sim.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 8])
+@pytest.mark.parametrize("name", ["cu_eeam", "nial_eeam"])
+def test_cuda_eeam_matches_reference_fixture(api, name, lanes, tmp_path):
+    """Extended EAM (imdb200_set_eeam_table) against the reference's `eeam` build: p_i = sum rho^2, M(p_i), M'(p_i) and
+    the dM force terms (src/imd_forces_nbl.c:591-610, 1090-1095, 1181-1208), single- and two-species."""
+    g = common.load_golden(name)
+    sim = common.make_sim(api.IMDB200, g, str(tmp_path), lanes_per_atom=lanes)
+    out = common.run_protocol(sim, g)
+    errs = common.compare(out, g, full_list=True, rtol=1e-10, traj_rtol=1e-8)
+    assert "f0:eam_p" in errs and "f0:dM" in errs
+    print(name, lanes, {k: f"{v:.1e}" for k, v in errs.items()})
+    sim.close()
+
+
 def test_cuda_cubic_run_loop_equals_stepwise_calls(api, tmp_path):
     """imdb200_run (fused integrator) and the separate calls stay bit-identical in the cubic kernels too."""
     g = common.load_golden("cu_spline")

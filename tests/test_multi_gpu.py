@@ -34,7 +34,7 @@ def test_two_domains_match_reference_fixture(built_lib, name):
     _run("fixture:" + name, (2, 1, 1), 29611)
 
 
-@pytest.mark.parametrize("name", ["cu_lindef", "cu_frozen_nvt"])
+@pytest.mark.parametrize("name", ["cu_lindef", "cu_frozen_nvt", "nial_eeam"])
 def test_two_domains_deformation_and_restrictions(built_lib, name):
     """lin_deform re-plans the cell grid and the halo on every rank; deform_sample and the restriction vectors act on
     virtual types that live on both sides of the domain boundary; nactive is summed over ranks."""
