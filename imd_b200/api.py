@@ -54,7 +54,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order",
 ]
 
 _lib = None
@@ -174,6 +174,14 @@ def halo_peers(cpu_dim, my_coord, pbc=(1, 1, 1)):
     peer = (C.c_int * 27)(); code = (C.c_int * 27)()
     load_library().imdb200_halo_peers(_i3(cpu_dim), _i3(my_coord), _i3(pbc), peer, code)
     return list(peer), list(code)
+
+
+def halo_message_order(peer, my_rank):
+    """Peer-major order of the receive and send regions (one message per neighbour rank), see imd_b200.h."""
+    p = (C.c_int * 27)(*peer)
+    ro = (C.c_int * 26)(); so = (C.c_int * 26)(); nr = C.c_int(); ns = C.c_int()
+    load_library().imdb200_halo_message_order(p, int(my_rank), ro, C.byref(nr), so, C.byref(ns))
+    return list(ro)[:nr.value], list(so)[:ns.value]
 
 
 def comm_unique_id():

@@ -133,19 +133,16 @@ int comm_plan(imdb200_sim *s)
   // contiguous slice = one message per peer and exchange (up to 26 directions share 1..7 peers on small process
   // grids; a message costs ~6 us whatever its size).  Within a peer the receive regions follow ascending
   // direction and the send regions descending direction: what is sent towards d arrives as direction 26-d.
-  std::vector<int> rorder, sorder;
-  for (int d = 0; d < 27; d++) if (s->dir[d].peer >= 0) { rorder.push_back(d); sorder.push_back(d); }
-  std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) {
-    return s->dir[a].peer != s->dir[b].peer ? s->dir[a].peer < s->dir[b].peer : a < b; });
-  std::stable_sort(sorder.begin(), sorder.end(), [&](int a, int b) {
-    return s->dir[a].peer != s->dir[b].peer ? s->dir[a].peer < s->dir[b].peer : a > b; });
+  int ro[26], so[26], nro = 0, nso = 0;
+  imdb200_halo_message_order(peers, s->rank, ro, &nro, so, &nso);      // host/topology.c
+  const std::vector<int> rorder(ro, ro + nro);
+  const std::vector<int> sorder(so, so + nso);
   for (int pass = 0; pass < 2; pass++) {
     for (int d : (pass == 0 ? rorder : sorder)) {
       DirPlan &D = s->dir[d];
       const int sg[3] = {d % 3 - 1, (d / 3) % 3 - 1, d / 9 - 1};
       const int code = codes[d];
       const bool self = D.peer == s->rank;
-      if (pass == 1 && self) continue;
       int lo[3], hi[3];
       for (int a = 0; a < 3; a++) axis_range(sg[a], g.cdim[a], &lo[a], &hi[a]);
       if (pass == 0) D.gcell_off = (int) gc.size(); else D.scell_off = (int) sc.size();

@@ -7,6 +7,9 @@
  *                           plus the periodic image shift each neighbour's atoms need on arrival
  *                           (the shift vectors send_cells applies on boundary ranks,
  *                           src/imd_comm_force_3d.c:248-265).
+ *   imdb200_halo_message_order  the order in which the 26 halo regions are laid out so that all regions exchanged
+ *                           with one neighbour rank are adjacent: one message per peer instead of the reference's
+ *                           one per sweep direction (src/imd_comm_force_3d.c:268-395)
  */
 #include "../../include/imd_b200.h"
 #include <math.h>
@@ -69,4 +72,34 @@ void imdb200_halo_peers(const int cpu_dim[3], const int my_coord[3], const int p
     peer[d] = imdb200_cart_rank(pc, cpu_dim);
     code[d] = (sh[0] + 1) + 3 * (sh[1] + 1) + 9 * (sh[2] + 1);
   }
+}
+
+/* Peer-major layout of the halo regions.  recv_order lists the directions whose buffer cells this rank fills
+ * (every d with peer[d] >= 0, own rank included), grouped by peer rank ascending and inside a peer by ascending
+ * direction.  send_order lists the directions it sends towards (peer[d] >= 0 and != my_rank), grouped the same way
+ * but inside a peer by DESCENDING direction: what is sent towards d arrives at the peer as direction 26-d, so the
+ * peer's ascending receive order is the sender's descending send order and the slice exchanged between two ranks is
+ * contiguous and identically ordered on both sides. */
+void imdb200_halo_message_order(const int peer[27], int my_rank, int recv_order[26], int *n_recv,
+                                int send_order[26], int *n_send)
+{
+  int d, i, j, nr = 0, ns = 0;
+  for (d = 0; d < 27; d++) {
+    if (d == 13 || peer[d] < 0) continue;
+    recv_order[nr++] = d;
+    if (peer[d] != my_rank) send_order[ns++] = d;
+  }
+  for (i = 1; i < nr; i++) {                       /* insertion sorts: (peer, d) ascending */
+    int v = recv_order[i];
+    for (j = i - 1; j >= 0 && (peer[recv_order[j]] > peer[v] || (peer[recv_order[j]] == peer[v] && recv_order[j] > v)); j--)
+      recv_order[j + 1] = recv_order[j];
+    recv_order[j + 1] = v;
+  }
+  for (i = 1; i < ns; i++) {                       /* (peer ascending, d descending) */
+    int v = send_order[i];
+    for (j = i - 1; j >= 0 && (peer[send_order[j]] > peer[v] || (peer[send_order[j]] == peer[v] && send_order[j] < v)); j--)
+      send_order[j + 1] = send_order[j];
+    send_order[j + 1] = v;
+  }
+  *n_recv = nr; *n_send = ns;
 }

@@ -225,6 +225,12 @@ void imdb200_cart_coords(int rank, const int cpu_dim[3], int coord[3]);
  * d = (sx+1) + 3*(sy+1) + 9*(sz+1); peer[d] = -1 behind a free surface; code[d] = image shift, same encoding */
 void imdb200_halo_peers(const int cpu_dim[3], const int my_coord[3], const int pbc_dirs[3], int peer[27],
                         int code[27]);
+/* replaces: the message schedule of send_cells / send_forces (three sweeps of two messages,
+ * src/imd_comm_force_3d.c:268-395, 587-714) by one message per neighbour rank: the order in which the receive
+ * regions (recv_order, own-rank wraps included) and the send regions (send_order) of the 26 directions are laid out
+ * so that everything exchanged with one peer is one contiguous, identically ordered slice on both sides */
+void imdb200_halo_message_order(const int peer[27], int my_rank, int recv_order[26], int *n_recv,
+                                int send_order[26], int *n_send);
 
 #ifdef __cplusplus
 }

@@ -22,8 +22,10 @@ def main():
     coord = api.cart_coords(rank, grid)
     assert api.cart_rank(coord, grid) == rank
     peer, code = api.halo_peers(grid, coord, pbc)
+    recv_order, send_order = api.halo_message_order(peer, rank)
     everyone = [None] * world
-    dist.all_gather_object(everyone, dict(rank=rank, coord=coord, peer=peer, code=code))
+    dist.all_gather_object(everyone, dict(rank=rank, coord=coord, peer=peer, code=code, recv_order=recv_order,
+                                          send_order=send_order))
     # every rank checks the whole table: what A expects from direction d, B = peer_A(d) must send towards
     # 26-d, and the image shifts the two sides apply are opposite
     for a in everyone:
@@ -49,6 +51,22 @@ def main():
                     s = [d % 3 - 1, (d // 3) % 3 - 1, d // 9 - 1][ax]
                     if (a["coord"][ax] == 0 and s < 0) or (a["coord"][ax] == grid[ax] - 1 and s > 0):
                         assert a["peer"][d] == -1
+    # one message per peer: for every ordered pair (A -> B) the directions A sends towards B, taken in A's send order
+    # and mirrored (d -> 26-d), are exactly the directions B fills from A, in B's receive order -- so the slice is
+    # contiguous and identically ordered on both sides; peers appear as contiguous groups in both orders
+    for a in everyone:
+        for order in (a["recv_order"], a["send_order"]):
+            peers_seq = [a["peer"][d] for d in order]
+            groups = [p for i, p in enumerate(peers_seq) if i == 0 or peers_seq[i - 1] != p]
+            assert len(groups) == len(set(groups)), (a["rank"], peers_seq)
+        assert sorted(a["recv_order"]) == [d for d in range(27) if d != 13 and a["peer"][d] >= 0]
+        assert sorted(a["send_order"]) == [d for d in range(27) if d != 13 and a["peer"][d] >= 0 and a["peer"][d] != a["rank"]]
+        for b in everyone:
+            if b["rank"] == a["rank"]:
+                continue
+            sent = [26 - d for d in a["send_order"] if a["peer"][d] == b["rank"]]
+            got = [d for d in b["recv_order"] if b["peer"][d] == a["rank"]]
+            assert sent == got, (a["rank"], b["rank"], sent, got)
     # the 128-byte ncclUniqueId travels from rank 0 to everybody
     uid = idist.broadcast_unique_id(rank)
     ids = [None] * world

@@ -8,7 +8,8 @@ import pytest
 from tests import common
 
 
-@pytest.mark.parametrize("world,pbc,port", [(2, (1, 1, 1), 29631), (2, (0, 1, 1), 29632), (4, (1, 1, 0), 29633)])
+@pytest.mark.parametrize("world,pbc,port", [(2, (1, 1, 1), 29631), (2, (0, 1, 1), 29632), (4, (1, 1, 0), 29633),
+                                            (8, (1, 1, 1), 29634)])
 def test_process_grid_and_halo_plan_are_consistent(built_lib, world, pbc, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
