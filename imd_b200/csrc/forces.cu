@@ -338,9 +338,11 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
         double4 xq[FDEPTH2];
         int jc[(MULTI || EE) ? FDEPTH2 : 1];
 #pragma unroll
-        for (int d = 0; d < FDEPTH2; d++) {
+        for (int dd = 0; dd < FDEPTH2; dd++) {
+          // the TEX share is issued first (longer latency) and consumed last (entries FDEPTH2-IMDB_TEX2 .. FDEPTH2-1)
+          const int d = FDEPTH2 - 1 - dd;
           const int j = jq[d] >= 0 ? jq[d] : (int) i;
-          xq[d] = (d < IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j);
+          xq[d] = (d >= FDEPTH2 - IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j);
           if (MULTI || EE) jc[d] = j;
         }
 #pragma unroll
