@@ -14,8 +14,20 @@ from imd_b200 import synth
 
 REF = os.path.join(common.ROOT, "oracle", "_ref")
 need = [os.path.join(REF, x) for x in ("imd_ref_mpi_eam_par", "imd_ref_serial_eam")]
-pytestmark = pytest.mark.skipif(not all(os.path.exists(p) for p in need),
-                                reason="oracle/_ref binaries missing: run `make -C oracle ref` where /root/reference exists")
+need_ref = pytest.mark.skipif(not all(os.path.exists(p) for p in need),
+                              reason="oracle/_ref binaries missing: run `make -C oracle ref` where /root/reference exists")
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 5])
+def test_shmpi_selftest(tmp_path, nranks):
+    """The shared-memory MPI subset on its own (oracle/shmpi/selftest.c): collectives longer than a slot, messages
+    longer than a ring, out-of-order tags, MPI_ANY_SOURCE / MPI_ANY_TAG, MPI_Waitany, self-sends, the Cartesian calls;
+    also with more ranks than this suite's reference runs use and with an odd rank count."""
+    src = os.path.join(common.ROOT, "oracle", "shmpi")
+    exe = str(tmp_path / "selftest")
+    subprocess.check_call(["gcc", "-O2", "-I" + src, "-o", exe, os.path.join(src, "selftest.c"), os.path.join(src, "shmpi.c")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, SHMPI_NP=str(nranks), SHMPI_PIN="0"))
+    assert r.returncode == 0 and f"SHMPI_SELFTEST_OK {nranks}" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
 
 
 def _run(exe, param, cwd, np_=1):
@@ -52,6 +64,7 @@ def _follow(tmp, tabs, chk, name, exe, grid):
     return out, eng, _chkpt(os.path.join(tmp, name + ".00001.chkpt"))
 
 
+@need_ref
 @pytest.mark.parametrize("grid", [(1, 1, 1), (2, 1, 1), (1, 2, 2), (2, 2, 2)])
 def test_reference_mpi_build_on_shmpi_matches_serial_reference(start, grid):
     tmp, tabs, chk = start
