@@ -60,6 +60,9 @@ struct orc_sim {
   int have_valid_nbl, nbl_count;
   /* integrator */
   int ensemble; double timestep, temperature, eta, isq_tau_eta;
+  /* NPT_iso (src/imd_integrate.c:1472-1729): barostat friction xi, twice the kinetic energy of the previous step,
+     external pressure and its per-step increment, 1/tau_xi^2, the pressure the last step used */
+  double xi, Ekin_old, pressure_ext, d_pressure, isq_tau_xi, pressure;
   int nvtypes; double *restr;
   /* results */
   double tot_pot_energy, tot_kin_energy, virial;
@@ -844,10 +847,18 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
 
 /* move_atoms_nve (src/imd_integrate.c:32-497) and move_atoms_nvt (:891-1147); atoms are
    visited in cell-traversal order like the reference so that the energy sums round alike */
+static void calc_dyn_pressure(orc_sim *s);
+static void move_atoms_npt_iso(orc_sim *s, int do_press_calc);
+
 void orc_move_atoms(orc_sim *s, int do_press_calc)
 {
   int c, i; const double dt = s->timestep;
   double E_kin_1 = 0.0, E_kin_2 = 0.0, reibung = 0, eins_d_reib = 0;
+  if (s->ensemble == ORC_NPT_ISO) {
+    if (s->Ekin_old < 0.0) { calc_dyn_pressure(s); if (s->isq_tau_xi == 0.0) s->xi = 0.0; }   /* :1493-1496 */
+    move_atoms_npt_iso(s, do_press_calc);
+    return;
+  }
   if (s->ensemble == ORC_NVE) s->tot_kin_energy = 0.0;
   else {
     reibung = 1.0 - s->eta * dt / 2.0;               /* :907 */
@@ -889,6 +900,75 @@ void orc_move_atoms(orc_sim *s, int do_press_calc)
     ttt = s->nactive * s->temperature;
     s->eta += dt * (E_kin_2 / ttt - 1.0) * s->isq_tau_eta;              /* :1140-1141 */
   }
+}
+
+/* calc_dyn_pressure, src/imd_integrate.c:1403-1465: twice the kinetic energy from the current momenta */
+static void calc_dyn_pressure(orc_sim *s)
+{
+  int c, i; double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (c = 0; c < s->ncells; c++) {
+    cellist *p = &s->cells[s->cnp[c]];
+    for (i = 0; i < p->n; i++) {
+      long a = p->idx[i]; const double *P = s->impuls + 3 * a; double tmp = 1.0 / s->masse[a];
+      sx += P[0] * P[0] * tmp; sy += P[1] * P[1] * tmp; sz += P[2] * P[2] * tmp;
+    }
+  }
+  s->Ekin_old = sx + sy; s->Ekin_old += sz;
+}
+
+/* move_atoms_npt_iso, src/imd_integrate.c:1472-1729 (no UNIAX, no restrictions in the reference either) */
+static void move_atoms_npt_iso(orc_sim *s, int do_press_calc)
+{
+  int c, i; const double dt = s->timestep;
+  double Ekin_new = 0.0, pfric, pifric, rfric, rifric, xi_old, ttt;
+  s->pressure = (s->Ekin_old + s->virial) / (3 * s->volume);                         /* :1505 */
+  xi_old = s->xi;
+  s->xi += dt * (s->pressure - s->pressure_ext) * s->volume * s->isq_tau_xi / s->nactive;   /* :1509 */
+  pfric = 1.0 - (xi_old + s->eta) * dt / 2.0;                                        /* :1512-1515 */
+  pifric = 1.0 / (1.0 + (s->xi + s->eta) * dt / 2.0);
+  rfric = 1.0 + (s->xi) * dt / 2.0;
+  rifric = 1.0 / (1.0 - (s->xi) * dt / 2.0);
+  for (c = 0; c < s->ncells; c++) {
+    cellist *p = &s->cells[s->cnp[c]];
+    for (i = 0; i < p->n; i++) {
+      long a = p->idx[i];
+      double *P = s->impuls + 3 * a, *F = s->kraft + 3 * a, *X = s->ort + 3 * a, m = s->masse[a], tmp;
+      P[0] = (pfric * P[0] + dt * F[0]) * pifric;                                    /* :1572-1576 */
+      P[1] = (pfric * P[1] + dt * F[1]) * pifric;
+      P[2] = (pfric * P[2] + dt * F[2]) * pifric;
+      Ekin_new += ((P[0] * P[0] + P[1] * P[1]) + P[2] * P[2]) / m;                   /* :1591 */
+      tmp = dt / m;
+      X[0] = (rfric * X[0] + P[0] * tmp) * rifric;                                   /* :1603-1607 */
+      X[1] = (rfric * X[1] + P[1] * tmp) * rifric;
+      X[2] = (rfric * X[2] + P[2] * tmp) * rifric;
+      if (do_press_calc) {                                                           /* :1641-1652 */
+        double *S = s->presstens + 6 * a;
+        S[0] += P[0] * P[0] / m; S[1] += P[1] * P[1] / m; S[2] += P[2] * P[2] / m;
+        S[3] += P[1] * P[2] / m; S[4] += P[2] * P[0] / m; S[5] += P[0] * P[1] / m;
+      }
+    }
+  }
+  s->tot_kin_energy = (s->Ekin_old + Ekin_new) / 4.0;                                /* :1691 */
+  ttt = s->nactive * s->temperature;
+  s->eta += dt * (Ekin_new / ttt - 1.0) * s->isq_tau_eta;                            /* :1695-1696 */
+  s->Ekin_old = Ekin_new;
+  ttt = (1.0 + s->xi * dt / 2.0) / (1.0 - s->xi * dt / 2.0);                         /* :1704-1717 */
+  s->box_x.x *= ttt; s->box_x.y *= ttt; s->box_y.x *= ttt; s->box_y.y *= ttt;
+  s->box_x.z *= ttt; s->box_y.z *= ttt; s->box_z.x *= ttt; s->box_z.y *= ttt; s->box_z.z *= ttt;
+  make_box(s);
+  s->pressure_ext += s->d_pressure;                                                  /* :1727 */
+}
+
+/* NPT_iso state: after a restart-like hand-over all of it comes from the caller; a fresh run calls it with
+   xi = 0 and Ekin_old < 0, which makes the first step compute calc_dyn_pressure() like steps == steps_min does */
+void orc_set_npt(orc_sim *s, double xi, double Ekin_old, double pressure_ext, double d_pressure, double isq_tau_xi)
+{
+  s->xi = xi; s->Ekin_old = Ekin_old; s->pressure_ext = pressure_ext; s->d_pressure = d_pressure; s->isq_tau_xi = isq_tau_xi;
+}
+
+void orc_get_npt(const orc_sim *s, double out[4])
+{
+  out[0] = s->xi; out[1] = s->Ekin_old; out[2] = s->pressure; out[3] = s->pressure_ext;
 }
 
 /* check_nblist, src/imd_forces_nbl.c:2007-2037 */

@@ -18,7 +18,7 @@ typedef struct orc_sim orc_sim;
 
 /* which table: 0 = pair_pot (radial), 1 = embed_pot (not radial), 2 = rho_h_tab (radial) */
 enum { ORC_PAIR = 0, ORC_EMBED = 1, ORC_RHO = 2, ORC_EMOD = 3 };  /* 3: emod_pot of EEAM builds (not radial) */
-enum { ORC_NVE = 0, ORC_NVT = 1 };
+enum { ORC_NVE = 0, ORC_NVT = 1, ORC_NPT_ISO = 2 };
 /* table interpolation a reference build selects at compile time (src/potaccess.h:24-36, src/Makefile:1694-1701) */
 enum { ORC_INTERP_3POINT = 0, ORC_INTERP_4POINT = 1, ORC_INTERP_SPLINE = 2 };
 
@@ -40,6 +40,10 @@ void orc_set_atoms(orc_sim *s, long n, const int *nummer, const int *sorte, cons
 void orc_set_restrictions(orc_sim *s, int nvtypes, const double *restr3);
 void orc_set_integrator(orc_sim *s, int ensemble, double timestep, double temperature,
                         double eta, double isq_tau_eta);
+/* NPT_iso (move_atoms_npt_iso, src/imd_integrate.c:1472-1729): xi, Ekin_old (< 0: compute it from the momenta at
+ * the first step, like steps == steps_min), pressure_ext, its per-step increment, 1/tau_xi^2 */
+void orc_set_npt(orc_sim *s, double xi, double Ekin_old, double pressure_ext, double d_pressure, double isq_tau_xi);
+void orc_get_npt(const orc_sim *s, double out[4]);      /* xi, Ekin_old, pressure of the last step, pressure_ext */
 void orc_set_box(orc_sim *s, const double box[9]);        /* make_box, src/imd_geom_3d.c:52-104 */
 
 void orc_calc_forces(orc_sim *s, int do_press_calc);      /* src/imd_forces_nbl.c:281-1999 */

@@ -69,6 +69,8 @@ def lib():
         L.orc_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.orc_tot_presstens.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_interpolation.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_npt.argtypes = [C.c_void_p] + [C.c_double] * 5
+        L.orc_get_npt.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_get_eeam.restype = C.c_long
         L.orc_get_eeam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_deform_sample.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -111,8 +113,16 @@ class OracleIMD:
         lib().orc_set_atoms(self.h, n, *[None if x is None else x.ctypes.data for x in a])
 
     def set_integrator(self, ensemble="nve", timestep=0.001, temperature=0.0, eta=0.0, isq_tau_eta=0.0):
-        ens = NVT if str(ensemble).lower() == "nvt" else NVE
+        ens = {"nve": NVE, "nvt": NVT, "npt_iso": 2}[str(ensemble).lower()]
         lib().orc_set_integrator(self.h, ens, timestep, temperature, eta, isq_tau_eta)
+
+    def set_npt(self, xi=0.0, Ekin_old=-1.0, pressure_ext=0.0, d_pressure=0.0, isq_tau_xi=0.0):
+        lib().orc_set_npt(self.h, float(xi), float(Ekin_old), float(pressure_ext), float(d_pressure), float(isq_tau_xi))
+
+    def npt(self):
+        out = np.zeros(4)
+        lib().orc_get_npt(self.h, out.ctypes.data)
+        return dict(zip(("xi", "Ekin_old", "pressure", "pressure_ext"), out.tolist()))
 
     def set_restrictions(self, restr):
         r = np.ascontiguousarray(restr, np.float64).reshape(-1, 3)

@@ -46,8 +46,9 @@ class RefIMD:
         L.ref_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.ref_pair_int.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_set_eta.argtypes = [C.c_double]
-        self.has_eam = variant.startswith("eam") or variant == "eeam"
+        self.has_eam = variant.startswith("eam") or variant in ("eeam", "npt")
         self.has_eeam = variant == "eeam"
+        self.has_npt = variant == "npt"
         L.ref_get_eeam.restype = C.c_long
         if quiet:
             sys.stdout.flush()
@@ -113,6 +114,11 @@ class RefIMD:
         keys = ["tot_pot_energy", "tot_kin_energy", "virial", "vir_xx", "vir_yy", "vir_zz",
                 "vir_yz", "vir_zx", "vir_xy", "volume", "nactive", "eta", "temperature", "timestep"]
         return dict(zip(keys, out.tolist()))
+
+    def npt(self):
+        out = np.zeros(5)
+        self.lib.ref_get_npt(_p(out, C.c_double))
+        return dict(zip(("xi", "Ekin_old", "pressure", "pressure_ext", "isq_tau_xi"), out.tolist()))
 
     def set_eta(self, eta):
         self.lib.ref_set_eta(float(eta))
@@ -205,6 +211,8 @@ def run_protocol(sim, spec):
         sim.step(spec["warm"])
     sim.invalidate_nbl()  # lists of all implementations are built from the recorded start state
     out["start"] = sim.atoms()
+    if getattr(sim, "has_npt", False):
+        out["npt_start"] = sim.npt()
     out["box"] = sim.box()
     out["celldims"] = sim.celldims()
     out["cellsz"] = sim.cellsz
@@ -227,6 +235,8 @@ def run_protocol(sim, spec):
         sim.move_atoms()
         sim.check_nblist()
         fr["after"] = sim.scalars()
+        if getattr(sim, "has_npt", False):
+            fr["npt"] = sim.npt(); fr["box"] = sim.box()
         fr["valid"] = sim.have_valid_nbl
         if spec.get("press", False) and s in spec.get("record_atoms", [0]):
             fr["tot_presstens"] = sim.tot_presstens()

@@ -138,6 +138,16 @@ long ref_get_atoms(int *nummer, int *sorte, int *vsorte, double *masse,
   return n;
 }
 
+/* NPT_iso state (src/globals.h:407, 569-574): xi.x, Ekin_old, pressure, pressure_ext.x, isq_tau_xi */
+void ref_get_npt(double *out5)
+{
+#ifdef NPT
+  out5[0] = xi.x; out5[1] = Ekin_old; out5[2] = pressure; out5[3] = pressure_ext.x; out5[4] = isq_tau_xi;
+#else
+  out5[0] = out5[1] = out5[2] = out5[3] = out5[4] = 0.0;
+#endif
+}
+
 /* EEAM per-atom fields (src/imd_forces_nbl.c:591-610, 1090-1095), same order as ref_get_atoms */
 long ref_get_eeam(double *eam_p, double *eam_dM)
 {

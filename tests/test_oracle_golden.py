@@ -64,3 +64,42 @@ def test_oracle_perfect_lattice_known_answers(tmp_path):
     assert np.ptp(a["poteng"]) < 1e-12 and np.ptp(a["rho"]) < 1e-12
     pairs, _ = sim.nbl_pairs()
     assert len(pairs) == 39 * n
+
+
+def test_oracle_npt_iso_matches_reference_fixture(tmp_path):
+    """move_atoms_npt_iso (src/imd_integrate.c:1472-1729) of the reference's `npt_iso` build: the barostat variable xi,
+    the pressure it is driven by, eta, the breathing box and the trajectory.  Oracle only: the CUDA engine has no NPT
+    ensemble yet, this fixture is what it will be held against."""
+    g = common.load_golden("cu_npt_iso")
+    paths = common.write_tables(g, str(tmp_path))
+    sim = orc.OracleIMD(1, g["box"], pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
+    sim.set_integrator("npt_iso", float(g["timestep"]), float(g["temperature"]), float(g["eta0"]), float(g["isq_tau_eta"]))
+    sim.set_npt(xi=float(g["npt_start:xi"]), Ekin_old=float(g["npt_start:Ekin_old"]),
+                pressure_ext=float(g["npt_start:pressure_ext"]), d_pressure=0.0, isq_tau_xi=float(g["npt_start:isq_tau_xi"]))
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"])
+    n = int(g["nsteps"])
+    for s in range(n):
+        sim.calc_forces(s)
+        sc = sim.scalars()
+        tol = 1e-13 if s == 0 else 1e-10
+        assert abs(sc["tot_pot_energy"] - g["epot"][s]) <= tol * abs(g["epot"][s]), s
+        if s == 0:
+            a = sim.atoms()
+            assert common.relerr(a["kraft"], g["f0:kraft"]) <= 1e-13
+        sim.move_atoms()
+        sim.check_nblist()
+        st, sc = sim.npt(), sim.scalars()
+        assert abs(st["xi"] - g["npt:xi"][s]) <= tol * 10 * abs(g["npt:xi"][s]), s
+        assert abs(st["pressure"] - g["npt:pressure"][s]) <= tol * 10 * abs(g["npt:pressure"][s]), s
+        assert abs(sc["volume"] - g["npt:volume"][s]) <= 1e-13 * g["npt:volume"][s], s
+        assert abs(sc["eta"] - g["eta"][s]) <= tol * 10 * abs(g["eta"][s]), s
+        assert abs(sc["tot_kin_energy"] - g["ekin"][s]) <= tol * abs(g["ekin"][s]), s
+        assert np.max(np.abs(sim.box() - g["npt:box"][s])) <= 1e-13 * np.max(np.abs(g["npt:box"][s])), s
+        assert sim.have_valid_nbl == int(g["valid"][s]), f"check_nblist decision differs at step {s}"
+    a = sim.atoms()
+    box = sim.box()
+    d = a["ort"] - g["final:ort"]
+    frac = d @ np.linalg.inv(box)
+    d = (frac - np.round(frac)) @ box
+    assert np.max(np.abs(d)) <= 1e-9 * np.max(np.abs(box))
+    assert np.max(np.abs(a["impuls"] - g["final:impuls"])) <= 1e-9 * np.max(np.abs(g["final:impuls"]))

@@ -70,6 +70,11 @@ CASES = {
                     record=[0, 11], press=True, variant="eeam", eeam=True),
     "nial_eeam": dict(kind="nial", ncell=(5, 5, 5), ensemble="nvt", starttemp=0.06, warm=30, nsteps=12,
                       record=[0, 11], press=False, variant="eeam", eeam=True),
+    # `npt_iso` reference build (Nose-Hoover thermostat + isotropic barostat): the box breathes every step.  Oracle
+    # fixture only so far -- the CUDA engine does not have this ensemble yet
+    "cu_npt_iso": dict(kind="cu", ncell=(6, 6, 6), ensemble="npt_iso", starttemp=0.08, warm=25, nsteps=40,
+                       record=[0, 39], press=False, variant="npt",
+                       extra=dict(endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.5, pressure_start=0.02, pressure_end=0.02)),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
 }
@@ -153,7 +158,14 @@ def make_case(name, c):
     sc0 = out["frames"][0]["scalars"]
     g["timestep"] = sc0["timestep"]; g["temperature"] = sc0["temperature"]; g["eta0"] = sc0["eta"]
     g["nactive"] = sc0["nactive"]
-    g["isq_tau_eta"] = 1.0 / 0.1 ** 2 if c["ensemble"] == "nvt" else 0.0
+    g["isq_tau_eta"] = 1.0 / 0.1 ** 2 if c["ensemble"] in ("nvt", "npt_iso") else 0.0
+    if c["variant"] == "npt":
+        for k, v in out["npt_start"].items():
+            g["npt_start:" + k] = v
+        g["npt:xi"] = np.array([f["npt"]["xi"] for f in out["frames"]])
+        g["npt:pressure"] = np.array([f["npt"]["pressure"] for f in out["frames"]])
+        g["npt:volume"] = np.array([f["after"]["volume"] for f in out["frames"]])
+        g["npt:box"] = np.array([f["box"] for f in out["frames"]])
     for k in ("nummer", "sorte", "vsorte", "masse", "ort", "impuls"):
         g["start:" + k] = out["start"][k]
     for k in ("ort", "impuls"):
