@@ -128,6 +128,22 @@ def make_eeam_table(outdir, nt=1, prefix="eeam", npts=1201, p_end=30.0):
     return path
 
 
+def make_adp_tables(outdir, nt=1, prefix="adp", nr=701, r2_begin=1.0, rc=5.5):
+    """ADP dipole u(r) and quadrupole w(r) distortion functions (`adp_upotfile`, `adp_wpotfile`, format 2,
+    ntypes^2 columns in r^2, radial): smooth synthetic functions that vanish at the cut-off."""
+    os.makedirs(outdir, exist_ok=True)
+    step = (rc * rc - r2_begin) / (nr - 1)
+    r2 = r2_begin + step * np.arange(nr)
+    r = np.sqrt(r2)
+    ncol = nt * nt
+    ucols = [(0.030 + 0.006 * ((c // nt) + (c % nt))) * np.exp(-0.9 * (r - 2.5)) * _cut(r, rc, 0.6) for c in range(ncol)]
+    wcols = [(-0.012 + 0.003 * ((c // nt) + (c % nt))) * np.exp(-0.7 * (r - 2.5)) * _cut(r, rc, 0.6) for c in range(ncol)]
+    pu, pw = os.path.join(outdir, f"{prefix}_u.pot"), os.path.join(outdir, f"{prefix}_w.pot")
+    write_table2(pu, [r2_begin] * ncol, [rc * rc] * ncol, [step] * ncol, ucols)
+    write_table2(pw, [r2_begin] * ncol, [rc * rc] * ncol, [step] * ncol, wcols)
+    return pu, pw
+
+
 def make_lj_table(outdir, name="lj_ar.pot", eps=0.0104, sigma=3.40, r_begin=2.0, r_cut=8.5,
                   nsteps=5000, ntypes=2):
     """Tabulated LJ pair potential in format 1, the way util/imd_mklj.c:50-66 lays it out

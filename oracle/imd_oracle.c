@@ -40,7 +40,7 @@ struct orc_sim {
   int pbc[3];
   double nbl_margin, cellsz;
   int margin_added;
-  ptab tab[4];         /* pair_pot, embed_pot, rho_h_tab, emod_pot (EEAM) */
+  ptab tab[6];         /* pair_pot, embed_pot, rho_h_tab, emod_pot (EEAM), adp_upot, adp_wpot (ADP) */
   int default_fmt;
   int interp;          /* ORC_INTERP_*: which PAIR_INT the build selects, src/potaccess.h:24-36 */
   /* atoms: [0,n) real, [n, n+ng) buffer-cell copies */
@@ -48,6 +48,7 @@ struct orc_sim {
   int *nummer, *sorte, *vsorte;
   double *masse, *ort, *impuls, *kraft, *poteng, *rho, *dF, *presstens, *nblpos;
   double *eam_p, *dM;  /* EEAM: p_i = sum rho_j^2 and M'(p_i) (EAM_P, EAM_DM, src/makros.h:96-99) */
+  double *mu, *la;     /* ADP: dipole mu[3] and quadrupole lambda[6] = xx yy zz yz zx xy per atom (ADP_MU, ADP_LAMBDA) */
   long gstage[3]; /* end index of the z-, y-, x-stage buffer atoms */
   long *gsrc; /* source atom of each buffer atom (may itself be a buffer atom) */
   signed char *gshift; /* accumulated image shift (box units), for reporting only */
@@ -200,7 +201,7 @@ static int read_table2(orc_sim *s, ptab *pt, FILE *f, int radial)
 int orc_read_table(orc_sim *s, int which, const char *path)
 {
   ptab *pt = &s->tab[which];
-  int radial = (which != ORC_EMBED && which != ORC_EMOD);
+  int radial = (which != ORC_EMBED && which != ORC_EMOD);   /* adp_upot, adp_wpot are radial (src/imd_potential.c:87-92) */
   int ncols = (which == ORC_EMBED || which == ORC_EMOD) ? s->ntypes : s->ntypes * s->ntypes;
   int have_header = 0, have_format = 0, end_header = 0, format, size = ncols, i, rc;
   char buffer[1024];
@@ -534,7 +535,7 @@ static void grow_atoms(orc_sim *s, long need)
   GROW(s->masse, double, 1); GROW(s->ort, double, 3); GROW(s->impuls, double, 3);
   GROW(s->kraft, double, 3); GROW(s->poteng, double, 1); GROW(s->rho, double, 1);
   GROW(s->dF, double, 1); GROW(s->presstens, double, 6); GROW(s->nblpos, double, 3);
-  GROW(s->eam_p, double, 1); GROW(s->dM, double, 1);
+  GROW(s->eam_p, double, 1); GROW(s->dM, double, 1); GROW(s->mu, double, 3); GROW(s->la, double, 6);
   GROW(s->gsrc, long, 1); GROW(s->gshift, signed char, 3);
 #undef GROW
 }
@@ -605,7 +606,12 @@ static void send_cells_pos(orc_sim *s, int first)
 static void send_cells_dF(orc_sim *s)
 {
   long g;
-  for (g = s->n; g < s->n + s->ng; g++) { s->dF[g] = s->dF[s->gsrc[g]]; s->dM[g] = s->dM[s->gsrc[g]]; } /* + EAM_DM :1044-1046 */
+  for (g = s->n; g < s->n + s->ng; g++) {
+    long t = s->gsrc[g]; int d;
+    s->dF[g] = s->dF[t]; s->dM[g] = s->dM[t];            /* + EAM_DM :1044-1046 */
+    for (d = 0; d < 3; d++) s->mu[3 * g + d] = s->mu[3 * t + d];   /* + ADP_MU, ADP_LAMBDA :1047-1057 */
+    for (d = 0; d < 6; d++) s->la[6 * g + d] = s->la[6 * t + d];
+  }
 }
 
 /* send_forces(add_rho,...) / send_forces(add_forces,...): src/imd_comm_force_3d.c:569-714,
@@ -624,6 +630,8 @@ static void send_forces_back(orc_sim *s, int what, int do_press)
       if (what == 0) { /* add_rho */
         s->rho[t] += s->rho[g];
         s->eam_p[t] += s->eam_p[g];              /* EEAM :1081-1083 */
+        for (d = 0; d < 3; d++) s->mu[3 * t + d] += s->mu[3 * g + d];   /* ADP :1084-1094 */
+        for (d = 0; d < 6; d++) s->la[6 * t + d] += s->la[6 * g + d];
       } else { /* add_forces */
         s->kraft[3 * t] += s->kraft[3 * g];
         s->kraft[3 * t + 1] += s->kraft[3 * g + 1];
@@ -694,8 +702,8 @@ static void make_nblist(orc_sim *s)
 void orc_calc_forces(orc_sim *s, int do_press_calc)
 {
   const ptab *pair_pot = &s->tab[ORC_PAIR], *embed_pot = &s->tab[ORC_EMBED], *rho_h_tab = &s->tab[ORC_RHO];
-  const ptab *emod_pot = &s->tab[ORC_EMOD];
-  const int nt = s->ntypes, inc = nt * nt, eam = rho_h_tab->loaded, eeam = eam && emod_pot->loaded;
+  const ptab *emod_pot = &s->tab[ORC_EMOD], *adp_upot = &s->tab[ORC_ADP_U], *adp_wpot = &s->tab[ORC_ADP_W];
+  const int nt = s->ntypes, inc = nt * nt, eam = rho_h_tab->loaded, eeam = eam && emod_pot->loaded, adp = eam && adp_upot->loaded && adp_wpot->loaded;
   long n, ntot, a; int c, i; long m;
   int is_short = 0, idummy = 0;
 
@@ -708,6 +716,8 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
     s->kraft[3 * a] = s->kraft[3 * a + 1] = s->kraft[3 * a + 2] = 0.0;
     for (i = 0; i < 6; i++) s->presstens[6 * a + i] = 0.0;
     s->poteng[a] = 0.0; s->rho[a] = 0.0; s->eam_p[a] = 0.0;
+    for (i = 0; i < 3; i++) s->mu[3 * a + i] = 0.0;
+    for (i = 0; i < 6; i++) s->la[6 * a + i] = 0.0;
   }
 
   /* atom index of list slot: slot = cl_off[c] + j */
@@ -722,6 +732,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
       double pp[6] = {0, 0, 0, 0, 0, 0};
       double d1x = s->ort[3 * ia], d1y = s->ort[3 * ia + 1], d1z = s->ort[3 * ia + 2];
       double ffx = 0.0, ffy = 0.0, ffz = 0.0, ee = 0.0, eam_r = 0.0, eam_p = 0.0;
+      double mu[3] = {0, 0, 0}, la[6] = {0, 0, 0, 0, 0, 0};
       int it = s->sorte[ia];
       for (m = s->tl[n]; m < s->tl[n + 1]; m++) {
         long ja = SLOT2ATOM(s->tb[m]);
@@ -765,7 +776,28 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
             }
           }
         }
+        if (adp) { /* :613-631 */
+          double tmp, dummy;
+          if (r2 < adp_upot->end[col]) {
+            pair_int(s, adp_upot, col, inc, r2, &pot, &dummy, &is_short);
+            tmp = pot * dx; mu[0] += tmp; s->mu[3 * ja] -= tmp;
+            tmp = pot * dy; mu[1] += tmp; s->mu[3 * ja + 1] -= tmp;
+            tmp = pot * dz; mu[2] += tmp; s->mu[3 * ja + 2] -= tmp;
+          }
+          if (r2 < adp_wpot->end[col]) {
+            pair_int(s, adp_wpot, col, inc, r2, &pot, &dummy, &is_short);
+            tmp = pot * dx * dx; la[0] += tmp; s->la[6 * ja] += tmp;         /* xx */
+            tmp = pot * dy * dy; la[1] += tmp; s->la[6 * ja + 1] += tmp;     /* yy */
+            tmp = pot * dz * dz; la[2] += tmp; s->la[6 * ja + 2] += tmp;     /* zz */
+            tmp = pot * dy * dz; la[3] += tmp; s->la[6 * ja + 3] += tmp;     /* yz */
+            tmp = pot * dz * dx; la[4] += tmp; s->la[6 * ja + 4] += tmp;     /* zx */
+            tmp = pot * dx * dy; la[5] += tmp; s->la[6 * ja + 5] += tmp;     /* xy */
+          }
+        }
       }
+      if (adp) { int d;                                  /* :919-929 */
+        for (d = 0; d < 3; d++) s->mu[3 * ia + d] += mu[d];
+        for (d = 0; d < 6; d++) s->la[6 * ia + d] += la[d]; }
       s->kraft[3 * ia] += ffx; s->kraft[3 * ia + 1] += ffy; s->kraft[3 * ia + 2] += ffz; /* :907-918 */
       s->poteng[ia] += ee;
       if (eam) s->rho[ia] += eam_r;
@@ -790,6 +822,22 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
           s->poteng[ia] += pot;
           s->tot_pot_energy += pot;
         }
+        if (adp) {                                       /* :1096-1110 */
+          const double *L = s->la + 6 * ia, *M = s->mu + 3 * ia; double tr, tmp;
+          tr = (L[0] + L[1] + L[2]) / 3.0;
+          tmp = L[0] - tr; pot = tmp * tmp;
+          tmp = L[1] - tr; pot += tmp * tmp;
+          tmp = L[2] - tr; pot += tmp * tmp;
+          tmp = L[3]; pot += (tmp * tmp) * 2.0;
+          tmp = L[4]; pot += (tmp * tmp) * 2.0;
+          tmp = L[5]; pot += (tmp * tmp) * 2.0;
+          tmp = M[0]; pot += tmp * tmp;
+          tmp = M[1]; pot += tmp * tmp;
+          tmp = M[2]; pot += tmp * tmp;
+          pot *= 0.5;
+          s->poteng[ia] += pot;
+          s->tot_pot_energy += pot;
+        }
       }
     }
     send_cells_dF(s); /* :1115 */
@@ -808,8 +856,9 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
           double dx = s->ort[3 * ja] - d1x, dy = s->ort[3 * ja + 1] - d1y, dz = s->ort[3 * ja + 2] - d1z;
           double r2 = ((dx * dx) + (dy * dy)) + (dz * dz);
           int jt = s->sorte[ja], col1 = jt * nt + it, col2 = it * nt + jt;
+          double fx = 0.0, fy = 0.0, fz = 0.0; int have_force = 0;
           if ((r2 < rho_h_tab->end[col1]) || (r2 < rho_h_tab->end[col2])) { /* :1172 */
-            double rho_i = 0.0, rho_j = 0.0, rho_i_strich, rho_j_strich, grad, fx, fy, fz;
+            double rho_i = 0.0, rho_j = 0.0, rho_i_strich, rho_j_strich, grad;
             pair_int(s, rho_h_tab, col1, inc, r2, &rho_i, &rho_i_strich, &is_short);
             if (col1 == col2) { rho_j_strich = rho_i_strich; rho_j = rho_i; }
             else pair_int(s, rho_h_tab, col2, inc, r2, &rho_j, &rho_j_strich, &is_short);
@@ -817,6 +866,32 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
             if (eeam)                                    /* :1204-1208 */
               grad += (s->dM[ia] * rho_j * rho_j_strich + s->dM[ja] * rho_i * rho_i_strich);
             fx = dx * grad; fy = dy * grad; fz = dz * grad;
+            have_force = 1;
+          }
+          if (adp) {
+            if (r2 < adp_upot->end[col1]) {              /* dipole distortion :1217-1229 */
+              double pot, grad, tmp, m0, m1, m2;
+              pair_int(s, adp_upot, col1, inc, r2, &pot, &grad, &is_short);
+              m0 = s->mu[3 * ia] - s->mu[3 * ja]; m1 = s->mu[3 * ia + 1] - s->mu[3 * ja + 1]; m2 = s->mu[3 * ia + 2] - s->mu[3 * ja + 2];
+              tmp = (((m0 * dx) + (m1 * dy)) + (m2 * dz)) * grad;
+              fx += m0 * pot + tmp * dx; fy += m1 * pot + tmp * dy; fz += m2 * pot + tmp * dz;
+              have_force = 1;
+            }
+            if (r2 < adp_wpot->end[col1]) {              /* quadrupole distortion :1231-1254 */
+              double pot, grad, nu, f1, f2, L[6], vx, vy, vz; int d;
+              pair_int(s, adp_wpot, col1, inc, r2, &pot, &grad, &is_short);
+              for (d = 0; d < 6; d++) L[d] = s->la[6 * ia + d] + s->la[6 * ja + d];
+              vx = L[0] * dx + L[5] * dy + L[4] * dz;
+              vy = L[5] * dx + L[1] * dy + L[3] * dz;
+              vz = L[4] * dx + L[3] * dy + L[2] * dz;
+              nu = (L[0] + L[1] + L[2]) / 3.0;
+              f1 = 2.0 * pot;
+              f2 = ((((vx * dx) + (vy * dy)) + (vz * dz)) - nu * r2) * grad - nu * f1;
+              fx += f1 * vx + f2 * dx; fy += f1 * vy + f2 * dy; fz += f1 * vz + f2 * dz;
+              have_force = 1;
+            }
+          }
+          if (have_force) {                              /* :1267-1305 */
             s->kraft[3 * ja] -= fx; s->kraft[3 * ja + 1] -= fy; s->kraft[3 * ja + 2] -= fz;
             ffx += fx; ffy += fy; ffz += fz;
             s->virial -= ((dx * fx) + (dy * fy)) + (dz * fz); /* :1280 */
@@ -1071,7 +1146,7 @@ void orc_destroy(orc_sim *s)
 {
   int w;
   if (!s) return;
-  for (w = 0; w < 4; w++) {
+  for (w = 0; w < 6; w++) {
     free(s->tab[w].begin); free(s->tab[w].end); free(s->tab[w].step); free(s->tab[w].invstep);
     free(s->tab[w].len); free(s->tab[w].table); free(s->tab[w].table2);
   }
@@ -1144,6 +1219,13 @@ void orc_get_box(const orc_sim *s, double o[9])
   o[0] = s->box_x.x; o[1] = s->box_x.y; o[2] = s->box_x.z;
   o[3] = s->box_y.x; o[4] = s->box_y.y; o[5] = s->box_y.z;
   o[6] = s->box_z.x; o[7] = s->box_z.y; o[8] = s->box_z.z;
+}
+
+long orc_get_adp(const orc_sim *s, double *mu3, double *la6)
+{
+  if (mu3) memcpy(mu3, s->mu, sizeof(double) * 3 * s->n);
+  if (la6) memcpy(la6, s->la, sizeof(double) * 6 * s->n);
+  return s->n;
 }
 
 long orc_get_eeam(const orc_sim *s, double *eam_p, double *dM)

@@ -17,7 +17,7 @@ extern "C" {
 typedef struct orc_sim orc_sim;
 
 /* which table: 0 = pair_pot (radial), 1 = embed_pot (not radial), 2 = rho_h_tab (radial) */
-enum { ORC_PAIR = 0, ORC_EMBED = 1, ORC_RHO = 2, ORC_EMOD = 3 };  /* 3: emod_pot of EEAM builds (not radial) */
+enum { ORC_PAIR = 0, ORC_EMBED = 1, ORC_RHO = 2, ORC_EMOD = 3, ORC_ADP_U = 4, ORC_ADP_W = 5 };  /* 3: emod_pot of EEAM builds (not radial) */
 enum { ORC_NVE = 0, ORC_NVT = 1, ORC_NPT_ISO = 2 };
 /* table interpolation a reference build selects at compile time (src/potaccess.h:24-36, src/Makefile:1694-1701) */
 enum { ORC_INTERP_3POINT = 0, ORC_INTERP_4POINT = 1, ORC_INTERP_SPLINE = 2 };
@@ -72,6 +72,8 @@ long   orc_get_nbl_pairs(const orc_sim *s, int *pi, int *pj, signed char *shift,
 void   orc_tot_presstens(const orc_sim *s, double out6[6]);
 /* EEAM: p_i = sum_j rho_j(r_ij)^2 and M'(p_i), storage order of orc_get_atoms */
 long   orc_get_eeam(const orc_sim *s, double *eam_p, double *dM);
+/* ADP: dipole mu[3] and quadrupole lambda[6] (xx yy zz yz zx xy) per atom, storage order of orc_get_atoms */
+long   orc_get_adp(const orc_sim *s, double *mu3, double *la6);
 
 #ifdef __cplusplus
 }

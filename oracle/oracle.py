@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 
-PAIR, EMBED, RHO, EMOD = 0, 1, 2, 3
+PAIR, EMBED, RHO, EMOD, ADP_U, ADP_W = 0, 1, 2, 3, 4, 5
 NVE, NVT = 0, 1
 
 
@@ -72,6 +72,8 @@ def lib():
         L.orc_set_npt.argtypes = [C.c_void_p] + [C.c_double] * 5
         L.orc_get_npt.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_get_eeam.restype = C.c_long
+        L.orc_get_adp.restype = C.c_long
+        L.orc_get_adp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_eeam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_deform_sample.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -84,7 +86,7 @@ INTERP = {"3point": 0, "4point": 1, "spline": 2}
 
 class OracleIMD:
     def __init__(self, ntypes, box, pbc=(1, 1, 1), nbl_margin=0.4, pair=None, embed=None, rho=None,
-                 default_fmt=1, interp="3point", emod=None):
+                 default_fmt=1, interp="3point", emod=None, adp_u=None, adp_w=None):
         L = lib()
         b = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(9))
         p = np.ascontiguousarray(np.asarray(pbc, dtype=np.int32))
@@ -92,7 +94,8 @@ class OracleIMD:
         self.press = False
         L.orc_set_interpolation(self.h, INTERP[interp] if isinstance(interp, str) else int(interp))
         self.eeam = emod is not None
-        for which, path in ((PAIR, pair), (EMBED, embed), (RHO, rho), (EMOD, emod)):
+        self.adp = adp_u is not None
+        for which, path in ((PAIR, pair), (EMBED, embed), (RHO, rho), (EMOD, emod), (ADP_U, adp_u), (ADP_W, adp_w)):
             if path:
                 rc = L.orc_read_table(self.h, which, os.fspath(path).encode())
                 if rc:
@@ -211,6 +214,9 @@ class OracleIMD:
         if self.eeam:
             d["eam_p"] = np.zeros(n); d["dM"] = np.zeros(n)
             lib().orc_get_eeam(self.h, d["eam_p"].ctypes.data, d["dM"].ctypes.data)
+        if self.adp:
+            d["adp_mu"] = np.zeros((n, 3)); d["adp_lambda"] = np.zeros((n, 6))
+            lib().orc_get_adp(self.h, d["adp_mu"].ctypes.data, d["adp_lambda"].ctypes.data)
         if sort:
             o = np.argsort(d["nummer"], kind="stable")
             d = {k: v[o] for k, v in d.items()}

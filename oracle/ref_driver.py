@@ -46,9 +46,11 @@ class RefIMD:
         L.ref_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.ref_pair_int.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_set_eta.argtypes = [C.c_double]
-        self.has_eam = variant.startswith("eam") or variant in ("eeam", "npt")
+        self.has_eam = variant.startswith("eam") or variant in ("eeam", "npt", "adp")
         self.has_eeam = variant == "eeam"
         self.has_npt = variant == "npt"
+        self.has_adp = variant == "adp"
+        L.ref_get_adp.restype = C.c_long
         L.ref_get_eeam.restype = C.c_long
         if quiet:
             sys.stdout.flush()
@@ -155,6 +157,9 @@ class RefIMD:
         if self.has_eeam:
             d["eam_p"] = np.zeros(n); d["dM"] = np.zeros(n)
             self.lib.ref_get_eeam(_p(d["eam_p"], C.c_double), _p(d["dM"], C.c_double))
+        if self.has_adp:
+            d["adp_mu"] = np.zeros((n, 3)); d["adp_lambda"] = np.zeros((n, 6))
+            self.lib.ref_get_adp(_p(d["adp_mu"], C.c_double), _p(d["adp_lambda"], C.c_double))
         if sort:  # canonical order: by atom number
             o = np.argsort(d["nummer"], kind="stable")
             d = {k: v[o] for k, v in d.items()}

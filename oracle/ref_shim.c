@@ -138,6 +138,24 @@ long ref_get_atoms(int *nummer, int *sorte, int *vsorte, double *masse,
   return n;
 }
 
+/* ADP per-atom fields (src/imd_forces_nbl.c:613-631): mu[3], lambda[6] = xx yy zz yz zx xy */
+long ref_get_adp(double *mu3, double *la6)
+{
+  long n = 0;
+#ifdef ADP
+  int k, i;
+  for (k = 0; k < NCELLS; k++) {
+    cell *p = CELLPTR(k);
+    for (i = 0; i < p->n; i++, n++) {
+      if (mu3) { mu3[3*n] = ADP_MU(p,i,X); mu3[3*n+1] = ADP_MU(p,i,Y); mu3[3*n+2] = ADP_MU(p,i,Z); }
+      if (la6) { la6[6*n] = ADP_LAMBDA(p,i,xx); la6[6*n+1] = ADP_LAMBDA(p,i,yy); la6[6*n+2] = ADP_LAMBDA(p,i,zz);
+                 la6[6*n+3] = ADP_LAMBDA(p,i,yz); la6[6*n+4] = ADP_LAMBDA(p,i,zx); la6[6*n+5] = ADP_LAMBDA(p,i,xy); }
+    }
+  }
+#endif
+  return n;
+}
+
 /* NPT_iso state (src/globals.h:407, 569-574): xi.x, Ekin_old, pressure, pressure_ext.x, isq_tau_xi */
 void ref_get_npt(double *out5)
 {

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 TABLE_KEYS = {"core_potential_file": "pair", "embedding_energy_file": "embed",
-              "atomic_e-density_file": "rho", "potfile": "pair", "eeam_energy_file": "emod"}
+              "atomic_e-density_file": "rho", "potfile": "pair", "eeam_energy_file": "emod",
+              "adp_upotfile": "adp_u", "adp_wpotfile": "adp_w"}
 
 # parity bars (BASELINE.json north_star): neighbour sets bit-exact; forces, energies and pressure
 # within 1e-10 relative of IMD's CPU build.
@@ -44,6 +45,8 @@ def make_sim(factory, g, tabdir, **kw):
                   embed=paths.get("embed"), rho=paths.get("rho"))
     if "emod" in paths:                                    # fixture of an `eeam` reference build
         common["emod"] = paths["emod"]
+    if "adp_u" in paths:                                   # fixture of an `adp` reference build (oracle only so far)
+        common["adp_u"] = paths["adp_u"]; common["adp_w"] = paths["adp_w"]
     if "interp" in g and str(g["interp"]) != "3point":     # fixture of a `4point` / `spline` reference build
         common["interp"] = str(g["interp"])
     integ = dict(ensemble=ens, timestep=float(g["timestep"]), temperature=float(g["temperature"]),
@@ -146,7 +149,8 @@ def compare(out, g, full_list=False, rtol=RTOL, traj_rtol=None, ignore_shift=Fal
         a = out["atoms"][s]
         # error growth of a chaotic trajectory: first frame at the parity bar, later ones looser
         tol = rtol if s == rec[0] else (traj_rtol or rtol * 1e3)
-        for k in ("kraft", "poteng", "rho", "dF") + (("eam_p", "dM") if f"f{s}:eam_p" in g else ()):
+        for k in ("kraft", "poteng", "rho", "dF") + (("eam_p", "dM") if f"f{s}:eam_p" in g else ()) \
+                + (("adp_mu", "adp_lambda") if f"f{s}:adp_mu" in g else ()):
             if np.max(np.abs(g[f"f{s}:{k}"])) == 0 and np.max(np.abs(a[k])) == 0:
                 continue
             e = relerr(a[k], g[f"f{s}:{k}"])

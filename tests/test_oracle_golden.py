@@ -6,7 +6,7 @@ from tests import common
 from oracle import oracle as orc
 
 CASES = ["cu_nve", "nial_nvt", "lj_nve", "cu_slab", "cu_long", "cu_4point", "cu_spline", "nial_spline",
-         "cu_lindef", "cu_frozen_nvt", "cu_frozen_nve", "cu_eeam", "nial_eeam"]
+         "cu_lindef", "cu_frozen_nvt", "cu_frozen_nve", "cu_eeam", "nial_eeam", "cu_adp", "nial_adp"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -75,6 +75,11 @@ CASES = {
     "cu_npt_iso": dict(kind="cu", ncell=(6, 6, 6), ensemble="npt_iso", starttemp=0.08, warm=25, nsteps=40,
                        record=[0, 39], press=False, variant="npt",
                        extra=dict(endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.5, pressure_start=0.02, pressure_end=0.02)),
+    # `adp` reference build (angular-dependent potential).  Oracle fixtures only so far, like cu_npt_iso
+    "cu_adp": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=30, nsteps=12,
+                   record=[0, 11], press=True, variant="adp", adp=True),
+    "nial_adp": dict(kind="nial", ncell=(5, 5, 5), ensemble="nvt", starttemp=0.06, warm=30, nsteps=12,
+                     record=[0, 11], press=False, variant="adp", adp=True),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
 }
@@ -82,7 +87,8 @@ CASES = {
 
 def table_arrays(paths):
     out = {}
-    for key in ("core_potential_file", "embedding_energy_file", "atomic_e-density_file", "potfile", "eeam_energy_file"):
+    for key in ("core_potential_file", "embedding_energy_file", "atomic_e-density_file", "potfile", "eeam_energy_file", "adp_upotfile",
+                "adp_wpotfile"):
         if key in paths:
             with open(paths[key]) as f:
                 out["table:" + key] = np.frombuffer(f.read().encode(), dtype=np.uint8)
@@ -94,6 +100,9 @@ def make_case(name, c):
     if c.get("eeam"):
         emod = synth.make_eeam_table(tmp, nt=2 if c["kind"] == "nial" else 1)
         c = dict(c, extra=dict(c.get("extra") or {}, eeam_energy_file=emod))
+    if c.get("adp"):
+        pu, pw = synth.make_adp_tables(tmp, nt=2 if c["kind"] == "nial" else 1)
+        c = dict(c, extra=dict(c.get("extra") or {}, adp_upotfile=pu, adp_wpotfile=pw))
     if c["kind"] == "cu":
         tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
         p = synth.cu_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
@@ -131,6 +140,8 @@ def make_case(name, c):
     out = rd.run_in_subprocess(spec, tmp)
     if c.get("eeam"):
         tabs = dict(tabs, eeam_energy_file=c["extra"]["eeam_energy_file"])
+    if c.get("adp"):
+        tabs = dict(tabs, adp_upotfile=c["extra"]["adp_upotfile"], adp_wpotfile=c["extra"]["adp_wpotfile"])
     g = dict(table_arrays(tabs))
     g["ntypes"] = ntypes
     g["ensemble"] = c["ensemble"]
@@ -179,7 +190,8 @@ def make_case(name, c):
     g["nbl_count"] = out["nbl_count"]
     for s in c["record"]:
         a = out["frames"][s]["atoms"]
-        for k in ("kraft", "poteng", "rho", "dF", "presstens", "ort") + (("eam_p", "dM") if c.get("eeam") else ()):
+        for k in ("kraft", "poteng", "rho", "dF", "presstens", "ort") + (("eam_p", "dM") if c.get("eeam") else ()) \
+                + (("adp_mu", "adp_lambda") if c.get("adp") else ()):
             g[f"f{s}:{k}"] = a[k]
         if c["press"]:
             g[f"f{s}:tot_presstens"] = out["frames"][s]["tot_presstens"]
