@@ -142,9 +142,8 @@ int imdb200_set_restrictions(imdb200_sim *s, int total_types, const double *r)
   if (s->restr) cudaFree(s->restr);
   CUDA_TRY(cudaMalloc(&s->restr, 3 * total_types * sizeof(double)));
   CUDA_TRY(cudaMemcpy(s->restr, r, 3 * total_types * sizeof(double), cudaMemcpyHostToDevice));
-  int all1 = 1; double sum = 0;
+  int all1 = 1;
   for (int i = 0; i < 3 * total_types; i++) if (r[i] != 1.0) all1 = 0;
-  (void) sum;
   s->n_restr = all1 ? 0 : total_types;
   s->nactive_dirty = 1;
   return 0;
