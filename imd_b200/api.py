@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libimd_b200.so")
 
-NVE, NVT = 0, 1
+NVE, NVT, NPT_ISO = 0, 1, 2
 PAIR, EMBED, RHO = 0, 1, 2
 
 
@@ -33,7 +33,8 @@ class Config(C.Structure):
                 ("nbl_margin", C.c_double), ("nbl_size", C.c_double), ("timestep", C.c_double),
                 ("ensemble", C.c_int), ("temperature", C.c_double), ("eta", C.c_double),
                 ("isq_tau_eta", C.c_double), ("device", C.c_int), ("lanes_per_atom", C.c_int),
-                ("interpolation", C.c_int)]
+                ("interpolation", C.c_int), ("xi", C.c_double), ("isq_tau_xi", C.c_double),
+                ("pressure_ext", C.c_double), ("d_pressure", C.c_double)]
 
 
 class Scalars(C.Structure):
@@ -54,7 +55,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state",
 ]
 
 _lib = None
@@ -95,6 +96,8 @@ def load_library():
     L.imdb200_get_eeam.argtypes = [vp, vp, vp]
     L.imdb200_set_eeam_table.argtypes = [vp, C.POINTER(PotTable)]
     L.imdb200_get_box.argtypes = [vp, vp]
+    L.imdb200_set_npt_state.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.imdb200_get_npt_state.argtypes = [vp, vp]
     L.imdb200_get_atoms.argtypes = [vp] + [vp] * 12
     L.imdb200_natoms_local.restype = C.c_long
     L.imdb200_natoms_local.argtypes = [vp]
@@ -201,7 +204,8 @@ class IMDB200:
     def __init__(self, ntypes, box, pbc=(1, 1, 1), nbl_margin=0.4, nbl_size=1.1, pair=None, embed=None,
                  rho=None, default_fmt=None, ensemble="nve", timestep=0.001, temperature=0.0, eta=0.0,
                  isq_tau_eta=0.0, device=-1, lanes_per_atom=0, total_types=None, cpu_dim=(1, 1, 1),
-                 my_coord=(0, 0, 0), interp="3point", emod=None):
+                 my_coord=(0, 0, 0), interp="3point", emod=None, xi=0.0, isq_tau_xi=0.0, pressure_ext=0.0,
+                 d_pressure=0.0):
         L = load_library()
         self.L = L
         cfg = Config()
@@ -213,7 +217,8 @@ class IMDB200:
             cfg.box_x[d], cfg.box_y[d], cfg.box_z[d] = b[0, d], b[1, d], b[2, d]
             cfg.pbc_dirs[d] = int(pbc[d]); cfg.cpu_dim[d] = int(cpu_dim[d]); cfg.my_coord[d] = int(my_coord[d])
         cfg.nbl_margin = nbl_margin; cfg.nbl_size = nbl_size; cfg.timestep = timestep
-        cfg.ensemble = NVT if str(ensemble).lower() == "nvt" else NVE
+        cfg.ensemble = {"nve": NVE, "nvt": NVT, "npt_iso": NPT_ISO}[str(ensemble).lower()]
+        cfg.xi = xi; cfg.isq_tau_xi = isq_tau_xi; cfg.pressure_ext = pressure_ext; cfg.d_pressure = d_pressure
         cfg.temperature = temperature; cfg.eta = eta; cfg.isq_tau_eta = isq_tau_eta
         cfg.device = device; cfg.lanes_per_atom = lanes_per_atom
         cfg.interpolation = INTERP[interp] if isinstance(interp, str) else int(interp)
@@ -367,6 +372,15 @@ class IMDB200:
     def celldims(self):
         s = self.raw_scalars()
         return np.array(list(s.global_cell_dim), np.int32), np.array(list(s.cell_dim), np.int32)
+
+    def set_npt_state(self, xi=0.0, Ekin_old=-1.0, pressure_ext=0.0):
+        """NPT_iso hand-over: xi, twice the kinetic energy of the previous step (< 0: from the momenta), pressure_ext."""
+        _chk(self.L.imdb200_set_npt_state(self.h, float(xi), float(Ekin_old), float(pressure_ext)))
+
+    def npt(self):
+        out = np.zeros(4)
+        _chk(self.L.imdb200_get_npt_state(self.h, out.ctypes.data))
+        return dict(zip(("xi", "Ekin_old", "pressure", "pressure_ext"), out.tolist()))
 
     def box(self):
         out = np.zeros(9)

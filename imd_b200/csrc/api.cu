@@ -75,6 +75,7 @@ int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
   s->rank = (cfg->my_coord[0] * cfg->cpu_dim[1] + cfg->my_coord[1]) * cfg->cpu_dim[2] + cfg->my_coord[2];
   s->eta = cfg->eta;
   s->skin_skip = 1; s->disp2 = -1.0;
+  s->npt_xi = cfg->xi; s->npt_ekin_old = -1.0; s->npt_pressure_ext = cfg->pressure_ext;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   s->own_stream = 1;
   CUDA_TRY(cudaMalloc(&s->d_scal, SC_COUNT * sizeof(double)));
@@ -277,13 +278,41 @@ static void apply_check(imdb200_sim *s)
   if (s->h_scal[SC_MAXD2] > lim * lim) s->have_valid_nbl = 0;   /* src/imd_forces_nbl.c:2036 */
 }
 
+// NPT_iso: the barostat needs the global virial of this step and Ekin_old on the host before the launch
+static int move_npt(imdb200_sim *s)
+{
+  if (s->npt_ekin_old < 0.0) {                       // steps == steps_min in the reference (:1493-1496)
+    TRY(integrate_npt_dyn_pressure(s));
+    TRY(fetch_scalars(s));
+    s->npt_ekin_old = s->h_scal[SC_EKIN2];
+    if (s->cfg.isq_tau_xi == 0.0) s->npt_xi = 0.0;
+  }
+  TRY(integrate_move_npt(s));
+  TRY(fetch_scalars(s));
+  return integrate_npt_after_fetch(s);
+}
+
 int imdb200_move_atoms(imdb200_sim *s)
 {
   TRY(ready(s));
   if (s->nbl_count == 0) return imdb_fail(IMDB200_ERR_ARG, "move_atoms before the first calc_forces");
-  TRY(integrate_move(s));
-  TRY(fetch_scalars(s));
+  if (s->cfg.ensemble == IMDB200_ENS_NPT_ISO) TRY(move_npt(s));
+  else { TRY(integrate_move(s)); TRY(fetch_scalars(s)); }
   s->disp2 = s->h_scal[SC_MAXD2];
+  return 0;
+}
+
+int imdb200_set_npt_state(imdb200_sim *s, double xi, double Ekin_old, double pressure_ext)
+{
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
+  s->npt_xi = xi; s->npt_ekin_old = Ekin_old; s->npt_pressure_ext = pressure_ext;
+  return 0;
+}
+
+int imdb200_get_npt_state(imdb200_sim *s, double out4[4])
+{
+  if (!s || !out4) return imdb_fail(IMDB200_ERR_ARG, "null argument");
+  out4[0] = s->npt_xi; out4[1] = s->npt_ekin_old; out4[2] = s->npt_pressure; out4[3] = s->npt_pressure_ext;
   return 0;
 }
 
@@ -327,9 +356,10 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     const int fuse = forces_can_fuse_move(s);
     if (s->tabs.have_eam) { TRY(comm_ghost_dF(s)); if (s->tabs.have_eeam) TRY(comm_ghost_dM(s)); TRY(forces_pass2(s, fuse)); }
     cudaEventRecord(s->ev[3], s->stream);
-    if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
+    if (s->cfg.ensemble == IMDB200_ENS_NPT_ISO) { TRY(fetch_scalars(s)); TRY(move_npt(s)); }   // virial first, see move_npt
+    else if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
     cudaEventRecord(s->ev[4], s->stream);
-    TRY(fetch_scalars(s));   // one sync per step: the host decides about the rebuild
+    if (s->cfg.ensemble != IMDB200_ENS_NPT_ISO) TRY(fetch_scalars(s));   // one sync per step: the host decides about the rebuild
     s->disp2 = s->h_scal[SC_MAXD2];
     apply_check(s);
     float ms;

@@ -601,7 +601,8 @@ template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
 // move_atoms can ride in the tail of pass 2 when pass 2 does not gather from pos (single species) and neither
 // the per-atom stress nor restriction vectors are in play
 int forces_can_fuse_move(const imdb200_sim *s)
-{ return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0; }
+{ return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0 &&
+         s->cfg.ensemble != IMDB200_ENS_NPT_ISO; }
 
 // forces.cu is compiled four times: quadratic / cubic table interpolation, each without / with the EEAM terms
 int forces_pass1(imdb200_sim *s)

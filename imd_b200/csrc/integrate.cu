@@ -124,7 +124,7 @@ int integrate_move(imdb200_sim *s)
 // what follows the per-atom part: kinetic-energy sums, Nose-Hoover update, stress totals
 int integrate_finish(imdb200_sim *s, int nb)
 {
-  const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT, st = s->press_calc != 0;
+  const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT || s->cfg.ensemble == IMDB200_ENS_NPT_ISO, st = s->press_calc != 0;
   if (nvt) {
     if (nb > 0) { const int slots[2] = {SC_EKIN1, SC_EKIN2}; TRY(reduce_finish(s, nb, 2, slots, 0)); }
     TRY(comm_sync_scalars(s));    // MPI_Allreduce of E_kin_1/2 (src/imd_integrate.c:1104-1130)
@@ -142,6 +142,117 @@ int integrate_finish(imdb200_sim *s, int nb)
     TRY(reduce_finish(s, nbp, 6, slots, 0));
   }
   return 0;
+}
+
+// ---- NPT_iso: Nose-Hoover thermostat + isotropic barostat (move_atoms_npt_iso, src/imd_integrate.c:1472-1729) --------
+// Per atom:  p = (pfric*p + dt*F)*pifric,  x = (rfric*x + p*dt/m)*rifric  (:1572-1576, 1603-1607); the four factors
+// come from eta, xi_old and xi, which the host advances from the global pressure before the launch.  red[0] is twice
+// the kinetic energy before the kick (the reference's Ekin_old), red[1] after it (Ekin_new), as in NVT.
+struct NptArgs {
+  double4 *pos, *mom; const double4 *frc;
+  const double *nblpos; long nstride;
+  double *presstens; long pstride;
+  long n;
+  double dt, pfric, pifric, rfric, rifric;
+  double *partial;
+  unsigned long long *maxd2;
+};
+
+template <bool STRESS>
+__global__ void __launch_bounds__(IBLOCK) k_move_atoms_npt(NptArgs a)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  double red[2] = {0.0, 0.0};
+  double d2 = 0.0;
+  if (i < a.n) {
+    double4 x = a.pos[i], p = a.mom[i];
+    const double4 f = a.frc[i];
+    const double m = p.w;
+    red[0] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;
+    p.x = (a.pfric * p.x + a.dt * f.x) * a.pifric;
+    p.y = (a.pfric * p.y + a.dt * f.y) * a.pifric;
+    p.z = (a.pfric * p.z + a.dt * f.z) * a.pifric;
+    red[1] = (p.x * p.x + p.y * p.y + p.z * p.z) / m;                  // :1591
+    const double tmp = a.dt / m;
+    x.x = (a.rfric * x.x + p.x * tmp) * a.rifric;
+    x.y = (a.rfric * x.y + p.y * tmp) * a.rifric;
+    x.z = (a.rfric * x.z + p.z * tmp) * a.rifric;
+    a.mom[i] = p;
+    a.pos[i] = x;
+    d2 = r2_exact(x.x - a.nblpos[i], x.y - a.nblpos[a.nstride + i], x.z - a.nblpos[2 * a.nstride + i]);
+    if (STRESS) {                                                      // :1641-1652
+      double *s = a.presstens + i;
+      s[0] += p.x * p.x / m; s[a.pstride] += p.y * p.y / m; s[2 * a.pstride] += p.z * p.z / m;
+      s[3 * a.pstride] += p.y * p.z / m; s[4 * a.pstride] += p.z * p.x / m; s[5 * a.pstride] += p.x * p.y / m;
+    }
+  }
+  d2 = block_max(d2);
+  if (threadIdx.x == 0) atomicMax(a.maxd2, (unsigned long long) __double_as_longlong(d2));
+  block_sum_store<2>(red, a.partial);
+}
+
+// calc_dyn_pressure (:1403-1465): twice the kinetic energy from the current momenta, local share into SC_EKIN2
+__global__ void __launch_bounds__(IBLOCK) k_dyn_pressure(const double4 *mom, long n, double *partial)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  double red[1] = {0.0};
+  if (i < n) { const double4 p = mom[i]; red[0] = (p.x * p.x + p.y * p.y + p.z * p.z) / p.w; }
+  block_sum_store<1>(red, partial);
+}
+
+int integrate_npt_dyn_pressure(imdb200_sim *s)
+{
+  const int nb = cdiv(s->n_own, IBLOCK);
+  if (nb > 0) {
+    k_dyn_pressure<<<nb, IBLOCK, 0, s->stream>>>(s->mom, s->n_own, s->d_partial); LAUNCH_CHECK();
+    const int slots[1] = {SC_EKIN2};
+    TRY(reduce_finish(s, nb, 1, slots, 0));
+  }
+  return 0;
+}
+
+// The caller has fetched the scalars of calc_forces (global virial) and knows the global Ekin_old.
+int integrate_move_npt(imdb200_sim *s)
+{
+  const double dt = s->cfg.timestep, vol = s->volume;
+  s->npt_pressure = (s->npt_ekin_old + s->h_scal[SC_VIRIAL]) / (3 * vol);                         // :1505
+  const double xi_old = s->npt_xi;
+  s->npt_xi += dt * (s->npt_pressure - s->npt_pressure_ext) * vol * s->cfg.isq_tau_xi / (double) s->nactive;   // :1509
+  NptArgs a;
+  a.pos = s->pos; a.mom = s->mom; a.frc = s->frc;
+  a.nblpos = s->nblpos; a.nstride = s->cap_atoms;
+  a.presstens = s->presstens; a.pstride = s->cap_atoms;
+  a.n = s->n_own; a.dt = dt;
+  a.pfric = 1.0 - (xi_old + s->eta) * dt / 2.0;                                                    // :1512-1515
+  a.pifric = 1.0 / (1.0 + (s->npt_xi + s->eta) * dt / 2.0);
+  a.rfric = 1.0 + (s->npt_xi) * dt / 2.0;
+  a.rifric = 1.0 / (1.0 - (s->npt_xi) * dt / 2.0);
+  a.partial = s->d_partial;
+  a.maxd2 = (unsigned long long *) (s->d_scal + SC_MAXD2);
+  const int nb = cdiv(s->n_own, IBLOCK);
+  CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
+  if (nb > 0) {
+    if (s->press_calc) k_move_atoms_npt<true><<<nb, IBLOCK, 0, s->stream>>>(a);
+    else k_move_atoms_npt<false><<<nb, IBLOCK, 0, s->stream>>>(a);
+    LAUNCH_CHECK();
+  }
+  // E_kin sums, tot_kin_energy = (Ekin_old + Ekin_new)/4 and the eta update are NVT's (:1691-1696)
+  return integrate_finish(s, nb);
+}
+
+// After the scalar fetch that follows integrate_move_npt: remember Ekin_new, let the box breathe (:1704-1718),
+// advance the external pressure (:1727).
+int integrate_npt_after_fetch(imdb200_sim *s)
+{
+  s->npt_ekin_old = s->h_scal[SC_EKIN2];
+  const double dt = s->cfg.timestep;
+  const double ttt = (1.0 + s->npt_xi * dt / 2.0) / (1.0 - s->npt_xi * dt / 2.0);
+  if (ttt < 0) return imdb_fail(IMDB200_ERR_EXPLODE, "box size has become negative!");
+  Geom &g = s->geom;
+  for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) g.box[b][d] *= ttt;
+  s->skin_all = 1;                 // the images move with the box: the displacement bound of the skin classes is void
+  s->npt_pressure_ext += s->cfg.d_pressure;
+  return geom_make_box(s);
 }
 
 int integrate_check_nblist(imdb200_sim *s)

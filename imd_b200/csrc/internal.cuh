@@ -164,6 +164,9 @@ struct imdb200_sim {
   int press_calc, is_short;
   long long nactive;   // sum of the restriction components over all atoms (3N by default)
   int nactive_dirty;   // atoms or restrictions changed: recount at the next rebuild / step
+  // NPT_iso: barostat friction, twice the global kinetic energy after the last step (< 0: unknown), external pressure,
+  // the pressure the last step used
+  double npt_xi, npt_ekin_old, npt_pressure_ext, npt_pressure;
   double eta;
   // timers
   cudaEvent_t ev[16];
@@ -242,6 +245,9 @@ int forces_pass1_cubic_eeam(imdb200_sim *s);
 int forces_pass2_cubic_eeam(imdb200_sim *s, int fuse_move);
 int integrate_finish(imdb200_sim *s, int nblocks_move);   // reductions + Nose-Hoover update after the per-atom part
 int integrate_move(imdb200_sim *s);           // move_atoms_nve/nvt + check_nblist fused
+int integrate_move_npt(imdb200_sim *s);       // move_atoms_npt_iso + check_nblist fused; integrate_npt_after_fetch follows the scalar fetch
+int integrate_npt_dyn_pressure(imdb200_sim *s);   // calc_dyn_pressure into SC_EKIN2 (local share)
+int integrate_npt_after_fetch(imdb200_sim *s);
 int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask);
 
 // ---- device helpers ------------------------------------------------------------------------------------

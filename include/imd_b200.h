@@ -38,7 +38,7 @@ enum {
   IMDB200_ERR_EXPLODE = -7  /* "system seems to explode!" (src/imd_geom_3d.c:96)          */
 };
 
-enum { IMDB200_ENS_NVE = 0, IMDB200_ENS_NVT = 1 }; /* ensemble keyword, src/imd_param.c:377-444 */
+enum { IMDB200_ENS_NVE = 0, IMDB200_ENS_NVT = 1, IMDB200_ENS_NPT_ISO = 2 }; /* ensemble keyword, src/imd_param.c:377-444 */
 
 /* Table interpolation.  The reference fixes it at compile time (src/potaccess.h:24-36; make targets with
  * `4point` or `spline` in their name, src/Makefile:1694-1701); here it is a run-time field of the config.
@@ -80,6 +80,11 @@ typedef struct {
   int device;              /* CUDA device ordinal, -1: current device                      */
   int lanes_per_atom;      /* 0 = choose; else 1,2,4,8,16,32 lanes cooperate on one atom   */
   int interpolation;       /* IMDB200_INTERP_*; what a `4point` / `spline` build of IMD selects */
+  /* NPT_iso (ensemble npt_iso, src/imd_integrate.c:1472-1729) */
+  double xi;               /* xi.x: barostat friction at the start                         */
+  double isq_tau_xi;       /* 1/tau_xi^2                                                   */
+  double pressure_ext;     /* pressure_start                                               */
+  double d_pressure;       /* (pressure_end - pressure_start) / (steps_max - steps_min)    */
 } imdb200_config;
 
 void        imdb200_default_config(imdb200_config *cfg);
@@ -186,6 +191,11 @@ typedef struct {
   double cellsz;
 } imdb200_scalars;
 int  imdb200_get_scalars(imdb200_sim *sim, imdb200_scalars *out);
+/* NPT_iso hand-over between runs (the reference keeps xi, Ekin_old and pressure_ext in globals, src/globals.h:407,
+ * 571-574): Ekin_old < 0 makes the next move_atoms compute it from the momenta (calc_dyn_pressure, what the
+ * reference does at steps == steps_min).  out4 = xi, Ekin_old, pressure used by the last step, pressure_ext. */
+int  imdb200_set_npt_state(imdb200_sim *sim, double xi, double Ekin_old, double pressure_ext);
+int  imdb200_get_npt_state(imdb200_sim *sim, double out4[4]);
 /* replaces: reading the globals box_x, box_y, box_z (src/globals.h) after lin_deform has changed them;
  * out9 = box_x, box_y, box_z */
 int  imdb200_get_box(imdb200_sim *sim, double out9[9]);
