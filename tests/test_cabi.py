@@ -70,3 +70,28 @@ def test_host_table_reader_matches_oracle_reader(built_lib, tmp_path):
                 v, _ = o.pair_int(which, col, x)
                 assert np.allclose(v[:-1], tab[:n - 1], rtol=0, atol=1e-12 * max(1.0, np.abs(tab).max()))
             built_lib.imdb200_free_pot_table(C.byref(pt))
+
+
+def test_ctypes_mirror_has_the_layout_of_the_c_structs(tmp_path):
+    """imdb200_config / imdb200_scalars as gcc lays them out against imd_b200/api.py's ctypes mirror: sizes and the
+    offsets of the fields behind the first alignment gap (a silent mismatch would scramble every parameter)."""
+    import ctypes as C
+    import subprocess
+    from imd_b200 import api
+    src = tmp_path / "layout.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "imd_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(imdb200_config), offsetof(imdb200_config, nbl_margin),
+         offsetof(imdb200_config, ensemble), offsetof(imdb200_config, interpolation), offsetof(imdb200_config, xi),
+         sizeof(imdb200_scalars), offsetof(imdb200_scalars, cellsz));
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(common.ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(api.Config), api.Config.nbl_margin.offset, api.Config.ensemble.offset, api.Config.interpolation.offset,
+            api.Config.xi.offset, C.sizeof(api.Scalars), api.Scalars.cellsz.offset]
+    assert got == want, (got, want)
