@@ -55,7 +55,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state", "imdb200_set_adp_tables", "imdb200_get_adp",
 ]
 
 _lib = None
@@ -92,6 +92,9 @@ def load_library():
     L.imdb200_deform_sample.argtypes = [vp, C.c_double, vp, vp, vp, vp]
     L.imdb200_get_scalars.argtypes = [vp, C.POINTER(Scalars)]
     L.imdb200_get_atoms.restype = C.c_long
+    L.imdb200_get_adp.restype = C.c_long
+    L.imdb200_get_adp.argtypes = [vp, vp, vp]
+    L.imdb200_set_adp_tables.argtypes = [vp, C.POINTER(PotTable), C.POINTER(PotTable)]
     L.imdb200_get_eeam.restype = C.c_long
     L.imdb200_get_eeam.argtypes = [vp, vp, vp]
     L.imdb200_set_eeam_table.argtypes = [vp, C.POINTER(PotTable)]
@@ -205,7 +208,7 @@ class IMDB200:
                  rho=None, default_fmt=None, ensemble="nve", timestep=0.001, temperature=0.0, eta=0.0,
                  isq_tau_eta=0.0, device=-1, lanes_per_atom=0, total_types=None, cpu_dim=(1, 1, 1),
                  my_coord=(0, 0, 0), interp="3point", emod=None, xi=0.0, isq_tau_xi=0.0, pressure_ext=0.0,
-                 d_pressure=0.0):
+                 d_pressure=0.0, adp_u=None, adp_w=None):
         L = load_library()
         self.L = L
         cfg = Config()
@@ -231,6 +234,9 @@ class IMDB200:
             self.set_potentials(pair, embed, rho, default_fmt)
         if emod is not None:
             self.set_eeam_table(emod)
+        self.adp = False
+        if adp_u is not None:
+            self.set_adp_tables(adp_u, adp_w)
 
     def close(self):
         if getattr(self, "h", None):
@@ -267,6 +273,15 @@ class IMDB200:
         self._tabs.append(tm)
         _chk(self.L.imdb200_set_eeam_table(self.h, C.byref(tm)))
         self.eeam = True
+
+    def set_adp_tables(self, adp_u, adp_w):
+        """`adp_upotfile` / `adp_wpotfile` of an ADP build: u(r), w(r), ntypes^2 columns in r^2, radial."""
+        nt = self.ntypes
+        tu, _ = read_pot_table(adp_u, nt * nt, 1, nt, 2)
+        tw, _ = read_pot_table(adp_w, nt * nt, 1, nt, 2)
+        self._tabs += [tu, tw]
+        _chk(self.L.imdb200_set_adp_tables(self.h, C.byref(tu), C.byref(tw)))
+        self.adp = True
 
     def comm_init(self, unique_id, rank, nranks):
         """Join the NCCL communicator of the process grid (one process per GPU); see imdb200_comm_init."""
@@ -405,6 +420,9 @@ class IMDB200:
         if self.eeam:
             d["eam_p"] = np.zeros(n); d["dM"] = np.zeros(n)
             assert self.L.imdb200_get_eeam(self.h, d["eam_p"].ctypes.data, d["dM"].ctypes.data) == n
+        if self.adp:
+            d["adp_mu"] = np.zeros((n, 3)); d["adp_lambda"] = np.zeros((n, 6))
+            assert self.L.imdb200_get_adp(self.h, d["adp_mu"].ctypes.data, d["adp_lambda"].ctypes.data) == n
         if sort:
             o = np.argsort(d["nummer"], kind="stable")
             d = {k: v[o] for k, v in d.items()}

@@ -103,7 +103,7 @@ void imdb200_destroy(imdb200_sim *s)
   void *ptrs[] = {s->posdf, s->pos, s->pos_alt, s->mom, s->mom_alt, s->frc, s->nummer, s->nummer_alt, s->rho, s->dF,
                   s->nblpos, s->presstens, s->cellid, s->cellid_alt, s->perm, s->cell_count, s->cell_start,
                   s->cell_fill, s->cell_code, s->gsrc, s->ghost_num, s->ghost_raw, s->scan_tmp, s->nbl, s->nnb,
-                  s->restr, s->d_scal, s->d_partial, s->d_flags, s->xfer, s->nnbc, s->posf, s->eam_p, s->dM};
+                  s->restr, s->d_scal, s->d_partial, s->d_flags, s->xfer, s->nnbc, s->posf, s->eam_p, s->dM, s->adp_mu, s->adp_la};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->h_flags) cudaFreeHost(s->h_flags);
@@ -126,6 +126,16 @@ int imdb200_set_eeam_table(imdb200_sim *s, const imdb200_pot_table *emod)
   if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
   return tables_upload_emod(s, emod);
+}
+
+int imdb200_set_adp_tables(imdb200_sim *s, const imdb200_pot_table *u, const imdb200_pot_table *w)
+{
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  TRY(tables_upload_adp(s, u, w));
+  TRY(adp_ensure_arrays(s));
+  s->have_valid_nbl = 0;
+  return geom_make_box(s);                 // cellsz may have grown
 }
 
 int imdb200_set_stream(imdb200_sim *s, void *stream)
@@ -254,10 +264,13 @@ static int calc_forces_async(imdb200_sim *s)
   if (!s->have_valid_nbl) TRY(cells_rebuild(s));       // fix_cells, send_cells, make_nblist (:304-317)
   else TRY(comm_ghost_pos(s));                         // send_cells(copy_cell,...) (:314)
   TRY(forces_pass1(s));
+  if (s->tabs.have_adp) TRY(forces_adp_pass1(s));
   if (s->tabs.have_eam) {
     TRY(comm_ghost_dF(s));                             // send_cells(copy_dF,...) (:1115)
     if (s->tabs.have_eeam) TRY(comm_ghost_dM(s));
+    if (s->tabs.have_adp) TRY(forces_adp_halo(s));
     TRY(forces_pass2(s, 0));
+    if (s->tabs.have_adp) TRY(forces_adp_pass2(s));
   }
   return 0;
 }
@@ -354,7 +367,14 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     cudaEventRecord(s->ev[2], s->stream);
     // single-species EAM: move_atoms + check_nblist ride in the tail of pass 2 (bit-identical, one kernel less)
     const int fuse = forces_can_fuse_move(s);
-    if (s->tabs.have_eam) { TRY(comm_ghost_dF(s)); if (s->tabs.have_eeam) TRY(comm_ghost_dM(s)); TRY(forces_pass2(s, fuse)); }
+    if (s->tabs.have_adp) TRY(forces_adp_pass1(s));
+    if (s->tabs.have_eam) {
+      TRY(comm_ghost_dF(s));
+      if (s->tabs.have_eeam) TRY(comm_ghost_dM(s));
+      if (s->tabs.have_adp) TRY(forces_adp_halo(s));
+      TRY(forces_pass2(s, fuse));
+      if (s->tabs.have_adp) TRY(forces_adp_pass2(s));
+    }
     cudaEventRecord(s->ev[3], s->stream);
     if (s->cfg.ensemble == IMDB200_ENS_NPT_ISO) { TRY(fetch_scalars(s)); TRY(move_npt(s)); }   // virial first, see move_npt
     else if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
@@ -433,6 +453,25 @@ int imdb200_get_box(imdb200_sim *s, double out9[9])
   if (!s || !out9) return imdb_fail(IMDB200_ERR_ARG, "null argument");
   for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) out9[3 * b + d] = s->geom.box[b][d];
   return 0;
+}
+
+__global__ void k_unpack_soa(const double *src, long stride, int ncomp, long n, double *out);
+
+long imdb200_get_adp(imdb200_sim *s, double *mu3, double *la6)
+{
+  if (!s || s->n_own <= 0 || !s->tabs.have_adp || !s->adp_mu) return 0;
+  cudaSetDevice(s->cfg.device);
+  const long n = s->n_own;
+  cudaStream_t st = s->stream;
+  if (ensure_xfer(s, (size_t) n * 6 * sizeof(double))) return -1;
+  double *b = (double *) s->xfer;
+  const int nb = cdiv(n, 256);
+  if (mu3) { k_unpack_soa<<<nb, 256, 0, st>>>(s->adp_mu, s->adp_cap, 3, n, b); g_kernel_launches++;
+             cudaMemcpyAsync(mu3, b, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
+  if (la6) { k_unpack_soa<<<nb, 256, 0, st>>>(s->adp_la, s->adp_cap, 6, n, b); g_kernel_launches++;
+             cudaMemcpyAsync(la6, b, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, st); }
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  return n;
 }
 
 long imdb200_get_eeam(imdb200_sim *s, double *eam_p, double *dM)

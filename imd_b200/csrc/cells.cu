@@ -116,7 +116,7 @@ int cells_ensure_capacity(imdb200_sim *s, long need)
   CUDA_TRY(cudaMemset(s->presstens, 0, 6 * cap * sizeof(double)));
   s->cap_atoms = cap;
   s->have_valid_nbl = 0;
-  return 0;
+  return adp_ensure_arrays(s);             // ADP: mu / lambda follow the capacity
 }
 
 // =====================================================================================================

@@ -422,6 +422,45 @@ int comm_ghost_dF(imdb200_sim *s)
   return 0;
 }
 
+// owners -> images for a caller-chosen SoA field (ADP: mu and lambda travel with EAM_DF, src/imd_comm_force_3d.c:1047-1057)
+__global__ void k_pack_soa(const double *src, long stride, int ncomp, const int *idx, long n, double *out)
+{
+  long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int i = idx[t];
+  for (int c = 0; c < ncomp; c++) out[(size_t) c * n + t] = src[(size_t) c * stride + i];
+}
+__global__ void k_ghost_soa_self(double *field, long stride, int ncomp, long n_own, long n_ghost, const int *gsrc)
+{
+  long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (t >= n_ghost) return;
+  const int src = gsrc[t];
+  if (src < 0) return;                                  // remote values were received in place
+  for (int c = 0; c < ncomp; c++) field[(size_t) c * stride + n_own + t] = field[(size_t) c * stride + src];
+}
+
+int comm_ghost_field(imdb200_sim *s, double *field, int ncomp, long stride)
+{
+  if (s->n_ghost == 0) return 0;
+  if (ncomp < 1 || ncomp > 8) return imdb_fail(IMDB200_ERR_ARG, "comm_ghost_field: 1..8 components");
+  if (s->n_send) {
+    TRY(need_comm(s));
+    ncclComm_t c = (ncclComm_t) s->nccl_comm;
+    k_pack_soa<<<cdiv(s->n_send, 256), 256, 0, s->stream>>>(field, stride, ncomp, s->send_idx, s->n_send, s->sendbuf1); LAUNCH_CHECK();
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int comp = 0; comp < ncomp; comp++)
+      for (int q = 0; q < s->n_peers; q++) {
+        const PeerPlan &P = s->peers[q];
+        if (P.send_cnt) NCCL_TRY(g_nccl.Send(s->sendbuf1 + (size_t) comp * s->n_send + P.send_off, P.send_cnt, ncclFloat64, P.peer, c, s->stream));
+        if (P.recv_cnt) NCCL_TRY(g_nccl.Recv(field + (size_t) comp * stride + s->n_own + P.recv_off, P.recv_cnt, ncclFloat64, P.peer, c, s->stream));
+      }
+    NCCL_TRY(g_nccl.GroupEnd());
+  }
+  k_ghost_soa_self<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(field, stride, ncomp, s->n_own, s->n_ghost, s->gsrc);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // EEAM builds copy EAM_DM together with EAM_DF (src/imd_comm_force_3d.c:1044-1046, 1116-1118, 1155-1157)
 int comm_ghost_dM(imdb200_sim *s)
 {

@@ -602,7 +602,7 @@ template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
 // the per-atom stress nor restriction vectors are in play
 int forces_can_fuse_move(const imdb200_sim *s)
 { return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0 &&
-         s->cfg.ensemble != IMDB200_ENS_NPT_ISO; }
+         s->cfg.ensemble != IMDB200_ENS_NPT_ISO && !s->tabs.have_adp; }
 
 // forces.cu is compiled four times: quadratic / cubic table interpolation, each without / with the EEAM terms
 int forces_pass1(imdb200_sim *s)

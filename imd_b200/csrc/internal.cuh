@@ -58,6 +58,10 @@ struct DevTables {
   TabMeta emod;
   const double  *emodVG;
   int have_eeam;
+  // ADP: dipole u(r) and quadrupole w(r) distortion functions, (c0,c1,c2,c3) per interval and column (forces_adp.cu)
+  TabMeta adpu, adpw;
+  const double4 *adpuK, *adpwK;
+  int have_adp;
   const double2 *fused;   // single species, phi and rho on one r^2 grid: [nrows][3] = (phi c0,c1) (phi c2, rho c2) (rho c0,c1),
                           // one 48-byte record per interval = three 16-byte loads per pair in pass 1
   int fused_rows;
@@ -120,6 +124,7 @@ struct imdb200_sim {
   int *nummer, *nummer_alt;
   double *rho, *dF, *nblpos, *presstens; // presstens [6][cap] SoA
   double *eam_p, *dM;             // EEAM: p_i = sum rho^2 (owners) and M'(p_i) (owners and images)
+  double *adp_mu, *adp_la; long adp_cap;   // ADP: mu [3][adp_cap], lambda [6][adp_cap] (xx yy zz yz zx xy), owners and images
   double4 *posdf;                 // single-species EAM: x,y,z + 2F'(rho) in .w, the pass-2 gather record
   int *cellid, *cellid_alt, *perm;
   void *xfer; size_t xfer_bytes;  // staging for set_atoms / get_atoms
@@ -212,6 +217,7 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
 void tables_free(imdb200_sim *s);
 int tables_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2, double *pot, double *grad);
 int tables_upload_emod(imdb200_sim *s, const imdb200_pot_table *emod);   // EEAM energy modification term
+int tables_upload_adp(imdb200_sim *s, const imdb200_pot_table *u, const imdb200_pot_table *w);   // ADP u(r), w(r)
 
 int geom_make_box(imdb200_sim *s);           // make_box + init_cells when needed
 int cells_ensure_capacity(imdb200_sim *s, long n_atoms_total);
@@ -225,6 +231,7 @@ int comm_migrate(imdb200_sim *s, const int *h_counts, long n_stay, long *n_new);
 int comm_setup_ghosts(imdb200_sim *s);        // per-cell counts, ghost ranges, send lists (at a rebuild)
 int comm_ghost_pos(imdb200_sim *s);           // send_cells(copy_cell,pack_cell,unpack_cell)
 int comm_ghost_dF(imdb200_sim *s);            // send_cells(copy_dF,pack_dF,unpack_dF)
+int comm_ghost_field(imdb200_sim *s, double *field, int ncomp, long stride);   // owners -> images for field[c*stride + i], c < ncomp <= 8
 int comm_ghost_dM(imdb200_sim *s);            // the EAM_DM part of copy_dF in EEAM builds (src/imd_comm_force_3d.c:1044-1046)
 int comm_reverse_add(imdb200_sim *s, double *field, int ncomp, long stride);  // send_forces(add_*,...)
 int comm_sync_scalars(imdb200_sim *s);        // the MPI_Allreduce sites
@@ -233,6 +240,10 @@ int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
 int forces_pass1(imdb200_sim *s);             // pair + rho + embedding
 int forces_pass2(imdb200_sim *s, int fuse_move);   // EAM force pass; fuse_move: move_atoms + check_nblist in its tail
 int forces_can_fuse_move(const imdb200_sim *s);
+int forces_adp_pass1(imdb200_sim *s);         // ADP: mu, lambda and the ADP energy (after pass 1)
+int forces_adp_halo(imdb200_sim *s);          // ADP: mu, lambda of the owners into the images
+int forces_adp_pass2(imdb200_sim *s);         // ADP: dipole and quadrupole forces (after pass 2)
+int adp_ensure_arrays(imdb200_sim *s);
 int forces_textures(imdb200_sim *s);
 void forces_free_textures(imdb200_sim *s);
 int forces_pass1_quad(imdb200_sim *s);        // forces.cu is compiled once per interpolation order (quadratic / cubic)

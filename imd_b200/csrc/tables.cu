@@ -266,6 +266,41 @@ int tables_upload_emod(imdb200_sim *s, const imdb200_pot_table *emod)
   return 0;
 }
 
+// ADP: dipole u(r) and quadrupole w(r) distortion functions (adp_upot, adp_wpot: ntypes^2 columns in r^2, radial,
+// src/imd_potential.c:87-92), as (c0,c1,c2,c3) per interval and column.
+static int upload_adp_one(imdb200_sim *s, int slot, const imdb200_pot_table *pt, TabMeta &meta, const double4 **dev)
+{
+  TRY(fill_meta(meta, pt));
+  HostTab h;
+  prepare(h, pt, s->cfg.interpolation, 1);
+  std::vector<double4> k((size_t) pt->maxsteps * pt->ncols);
+  double c4[4];
+  for (int r = 0; r < pt->maxsteps; r++)
+    for (int col = 0; col < pt->ncols; col++) { coef(h, r, col, c4); k[(size_t) r * pt->ncols + col] = make_double4(c4[0], c4[1], c4[2], c4[3]); }
+  return upload(s, slot, k, dev);
+}
+
+int tables_upload_adp(imdb200_sim *s, const imdb200_pot_table *u, const imdb200_pot_table *w)
+{
+  if (!s->have_tabs || !s->tabs.have_eam) return imdb_fail(IMDB200_ERR_ARG, "set the EAM tables before the ADP tables");
+  DevTables &T = s->tabs;
+  for (int slot = 9; slot <= 10; slot++) if (s->tab_mem[slot]) { cudaFree(s->tab_mem[slot]); s->tab_mem[slot] = nullptr; }
+  T.have_adp = 0; T.adpuK = T.adpwK = nullptr;
+  if (!u && !w) return 0;
+  if (!u || !w) return imdb_fail(IMDB200_ERR_ARG, "ADP needs both the u and the w table");
+  const int nt = T.ntypes;
+  if (u->ncols != nt * nt || w->ncols != nt * nt) return imdb_fail(IMDB200_ERR_ARG, "ADP tables need %d columns", nt * nt);
+  TRY(upload_adp_one(s, 9, u, T.adpu, &T.adpuK));
+  TRY(upload_adp_one(s, 10, w, T.adpw, &T.adpwK));
+  // radial tables take part in cellsz = max end (src/imd_potential.c:406)
+  for (int col = 0; col < nt * nt; col++) {
+    if (u->end[col] > s->cellsz0) s->cellsz0 = u->end[col];
+    if (w->end[col] > s->cellsz0) s->cellsz0 = w->end[col];
+  }
+  T.have_adp = 1;
+  return 0;
+}
+
 // ---- test hook: PAIR_INT through the device lookup code -------------------------------------------
 __global__ void k_pair_int(DevTables T, int which, int col, long n, const double *r2, double *pot, double *grad)
 {

@@ -114,6 +114,14 @@ int  imdb200_set_eeam_table(imdb200_sim *sim, const imdb200_pot_table *emod);
 /* EAM_P and EAM_DM of the owned atoms, in the order of imdb200_get_atoms; returns the count */
 long imdb200_get_eeam(imdb200_sim *sim, double *eam_p, double *eam_dM);
 
+/* ADP builds (make targets with `adp`): dipole and quadrupole distortion functions u(r), w(r) -- adp_upot and
+ * adp_wpot, read from `adp_upotfile` / `adp_wpotfile` with ntypes^2 columns in r^2 (src/imd_potential.c:87-92).
+ * Call after imdb200_set_potentials; NULL, NULL switches the terms off.  Replaces the `#ifdef ADP` branches of
+ * calc_forces (src/imd_forces_nbl.c:613-631, 919-929, 1096-1110, 1217-1255).  NOT YET RUN ON A GPU. */
+int  imdb200_set_adp_tables(imdb200_sim *sim, const imdb200_pot_table *u, const imdb200_pot_table *w);
+/* ADP_MU [n][3] and ADP_LAMBDA [n][6] = xx yy zz yz zx xy of the owned atoms, in the order of imdb200_get_atoms */
+long imdb200_get_adp(imdb200_sim *sim, double *mu3, double *lambda6);
+
 /* restrictions per virtual type (3 doubles each); default all 1 (src/imd_param.c:2053-2066) */
 int  imdb200_set_restrictions(imdb200_sim *sim, int total_types, const double *restrictions);
 

@@ -92,6 +92,19 @@ def test_cuda_npt_iso_matches_reference_fixture(api, tmp_path):
     assert r.returncode == 0 and "NPT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.xfail(strict=False, reason="the ADP kernels (forces_adp.cu) were written after this round's GPU budget was "
+                                         "spent: they compile, their oracle twin passes the same fixtures on the CPU, "
+                                         "but they have not run on a B200 yet (DESIGN.md section 8)")
+@pytest.mark.parametrize("name,lanes", [("cu_adp", 1), ("nial_adp", 4)])
+def test_cuda_adp_matches_reference_fixture(api, name, lanes, tmp_path):
+    """imdb200_set_adp_tables against the reference's `adp` build: mu, lambda, the ADP energy and the dipole / quadrupole
+    forces (src/imd_forces_nbl.c:613-631, 1096-1110, 1217-1255), in its own process (tests/adp_worker.py)."""
+    import os, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(common.ROOT, "tests", "adp_worker.py"), name, str(tmp_path), str(lanes)],
+                       capture_output=True, text=True, timeout=300, cwd=common.ROOT)
+    assert r.returncode == 0 and "ADP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_cuda_cubic_run_loop_equals_stepwise_calls(api, tmp_path):
     """imdb200_run (fused integrator) and the separate calls stay bit-identical in the cubic kernels too."""
     g = common.load_golden("cu_spline")
