@@ -64,6 +64,7 @@ struct orc_sim {
   /* NPT_iso (src/imd_integrate.c:1472-1729): barostat friction xi, twice the kinetic energy of the previous step,
      external pressure and its per-step increment, 1/tau_xi^2, the pressure the last step used */
   double xi, Ekin_old, pressure_ext, d_pressure, isq_tau_xi, pressure;
+  double tauber;       /* > 0: Berendsen variant of NVE (`ber` builds, src/imd_integrate.c:44-53, 341-350) */
   int nvtypes; double *restr;
   /* results */
   double tot_pot_energy, tot_kin_energy, virial;
@@ -934,6 +935,13 @@ void orc_move_atoms(orc_sim *s, int do_press_calc)
     move_atoms_npt_iso(s, do_press_calc);
     return;
   }
+  double cc = 1.0;
+  if (s->ensemble == ORC_NVE && s->tauber > 0.0) {   /* Ju Li's Berendsen thermostat, from the PREVIOUS step's Ekin :44-52 */
+    cc = 1. - dt / s->tauber * ((2.0 * s->tot_kin_energy / s->nactive + 8.6174101569719990e-06) / (s->temperature + 8.6174101569719990e-06) - 1.);
+    if (cc < 0.5) cc = 0.5;
+    else if (cc > 2.0) cc = 2.0;
+    cc = sqrt(cc);
+  }
   if (s->ensemble == ORC_NVE) s->tot_kin_energy = 0.0;
   else {
     reibung = 1.0 - s->eta * dt / 2.0;               /* :907 */
@@ -952,6 +960,7 @@ void orc_move_atoms(orc_sim *s, int do_press_calc)
         P[0] += dt * F[0]; P[1] += dt * F[1]; P[2] += dt * F[2];        /* :213-217 */
         k2 = (P[0] * P[0] + P[1] * P[1]) + P[2] * P[2];
         s->tot_kin_energy += (k1 + k2) / (4 * m);                       /* :329-335 */
+        if (s->tauber > 0.0) { P[0] *= cc; P[1] *= cc; P[2] *= cc; }    /* :341-350 */
       } else {
         E_kin_1 += ((P[0] * P[0] + P[1] * P[1]) + P[2] * P[2]) / m;    /* :951 */
         F[0] *= R[0]; F[1] *= R[1]; F[2] *= R[2];
@@ -1036,6 +1045,12 @@ static void move_atoms_npt_iso(orc_sim *s, int do_press_calc)
 
 /* NPT_iso state: after a restart-like hand-over all of it comes from the caller; a fresh run calls it with
    xi = 0 and Ekin_old < 0, which makes the first step compute calc_dyn_pressure() like steps == steps_min does */
+/* Berendsen variant of NVE; tot_kin_energy is the value the previous move_atoms left (0 at the start of a run) */
+void orc_set_berendsen(orc_sim *s, double tauber, double tot_kin_energy)
+{
+  s->tauber = tauber; s->tot_kin_energy = tot_kin_energy;
+}
+
 void orc_set_npt(orc_sim *s, double xi, double Ekin_old, double pressure_ext, double d_pressure, double isq_tau_xi)
 {
   s->xi = xi; s->Ekin_old = Ekin_old; s->pressure_ext = pressure_ext; s->d_pressure = d_pressure; s->isq_tau_xi = isq_tau_xi;

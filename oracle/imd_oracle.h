@@ -43,7 +43,9 @@ void orc_set_integrator(orc_sim *s, int ensemble, double timestep, double temper
 /* NPT_iso (move_atoms_npt_iso, src/imd_integrate.c:1472-1729): xi, Ekin_old (< 0: compute it from the momenta at
  * the first step, like steps == steps_min), pressure_ext, its per-step increment, 1/tau_xi^2 */
 void orc_set_npt(orc_sim *s, double xi, double Ekin_old, double pressure_ext, double d_pressure, double isq_tau_xi);
-void orc_get_npt(const orc_sim *s, double out[4]);      /* xi, Ekin_old, pressure of the last step, pressure_ext */
+void orc_get_npt(const orc_sim *s, double out[4]);
+/* `ber` builds: Berendsen scaling of the momenta inside move_atoms_nve (src/imd_integrate.c:44-53, 341-350) */
+void orc_set_berendsen(orc_sim *s, double tauber, double tot_kin_energy);      /* xi, Ekin_old, pressure of the last step, pressure_ext */
 void orc_set_box(orc_sim *s, const double box[9]);        /* make_box, src/imd_geom_3d.c:52-104 */
 
 void orc_calc_forces(orc_sim *s, int do_press_calc);      /* src/imd_forces_nbl.c:281-1999 */

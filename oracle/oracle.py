@@ -71,6 +71,7 @@ def lib():
         L.orc_set_interpolation.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_npt.argtypes = [C.c_void_p] + [C.c_double] * 5
         L.orc_get_npt.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_berendsen.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.orc_get_eeam.restype = C.c_long
         L.orc_get_adp.restype = C.c_long
         L.orc_get_adp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -121,6 +122,9 @@ class OracleIMD:
 
     def set_npt(self, xi=0.0, Ekin_old=-1.0, pressure_ext=0.0, d_pressure=0.0, isq_tau_xi=0.0):
         lib().orc_set_npt(self.h, float(xi), float(Ekin_old), float(pressure_ext), float(d_pressure), float(isq_tau_xi))
+
+    def set_berendsen(self, tauber, tot_kin_energy=0.0):
+        lib().orc_set_berendsen(self.h, float(tauber), float(tot_kin_energy))
 
     def npt(self):
         out = np.zeros(4)

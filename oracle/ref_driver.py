@@ -46,7 +46,7 @@ class RefIMD:
         L.ref_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.ref_pair_int.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_set_eta.argtypes = [C.c_double]
-        self.has_eam = variant.startswith("eam") or variant in ("eeam", "npt", "adp")
+        self.has_eam = variant.startswith("eam") or variant in ("eeam", "npt", "adp", "ber")
         self.has_eeam = variant == "eeam"
         self.has_npt = variant == "npt"
         self.has_adp = variant == "adp"

@@ -103,3 +103,26 @@ def test_oracle_npt_iso_matches_reference_fixture(tmp_path):
     d = (frac - np.round(frac)) @ box
     assert np.max(np.abs(d)) <= 1e-9 * np.max(np.abs(box))
     assert np.max(np.abs(a["impuls"] - g["final:impuls"])) <= 1e-9 * np.max(np.abs(g["final:impuls"]))
+
+
+def test_oracle_berendsen_matches_reference_fixture(tmp_path):
+    """`ber` builds: Berendsen scaling of the momenta inside move_atoms_nve (src/imd_integrate.c:44-53, 341-350),
+    driven by the kinetic energy of the PREVIOUS step.  Oracle only so far."""
+    g = common.load_golden("cu_berendsen")
+    paths = common.write_tables(g, str(tmp_path))
+    sim = orc.OracleIMD(1, g["box"], pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
+    sim.set_integrator("nve", float(g["timestep"]), float(g["temperature"]))
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"])
+    sim.set_berendsen(float(g["tau_berendsen"]), float(g["ekin_start"]))
+    for s in range(int(g["nsteps"])):
+        sim.calc_forces(s)
+        tol = 1e-13 if s == 0 else 1e-10
+        assert abs(sim.scalars()["tot_pot_energy"] - g["epot"][s]) <= tol * abs(g["epot"][s]), s
+        sim.move_atoms()
+        sim.check_nblist()
+        assert abs(sim.scalars()["tot_kin_energy"] - g["ekin"][s]) <= tol * abs(g["ekin"][s]), s
+        assert sim.have_valid_nbl == int(g["valid"][s])
+    a = sim.atoms()
+    assert np.max(np.abs(a["impuls"] - g["final:impuls"])) <= 1e-9 * np.max(np.abs(g["final:impuls"]))
+    # the thermostat did something: the kinetic energy moved towards the target faster than plain NVE would
+    assert abs(g["ekin"][-1] - g["ekin"][0]) > 1e-3 * abs(g["ekin"][0])

@@ -80,6 +80,10 @@ CASES = {
                    record=[0, 11], press=True, variant="adp", adp=True),
     "nial_adp": dict(kind="nial", ncell=(5, 5, 5), ensemble="nvt", starttemp=0.06, warm=30, nsteps=12,
                      record=[0, 11], press=False, variant="adp", adp=True),
+    # `ber` reference build: Berendsen scaling inside move_atoms_nve, target temperature above the current one.
+    # Oracle fixture only so far
+    "cu_berendsen": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.05, warm=15, nsteps=30,
+                         record=[0, 29], press=False, variant="ber", extra=dict(tau_berendsen=0.05, endtemp=0.09)),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
 }
@@ -170,6 +174,10 @@ def make_case(name, c):
     g["timestep"] = sc0["timestep"]; g["temperature"] = sc0["temperature"]; g["eta0"] = sc0["eta"]
     g["nactive"] = sc0["nactive"]
     g["isq_tau_eta"] = 1.0 / 0.1 ** 2 if c["ensemble"] in ("nvt", "npt_iso") else 0.0
+    if c["variant"] == "ber":
+        g["tau_berendsen"] = c["extra"]["tau_berendsen"]
+        g["ekin_start"] = out["frames"][0]["scalars"]["tot_kin_energy"]      # what the last warm-up step left
+        g["temperature_steps"] = np.array([f["scalars"]["temperature"] for f in out["frames"]])
     if c["variant"] == "npt":
         for k, v in out["npt_start"].items():
             g["npt_start:" + k] = v
