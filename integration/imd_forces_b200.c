@@ -160,6 +160,9 @@ static void b200_init(void)
 #ifdef EEAM   /* `eeam` make targets: energy modification term M(p), src/imd_potential.c:82-85 */
   b200_check(imdb200_set_eeam_table(b200, (imdb200_pot_table *) &emod_pot));
 #endif
+#ifdef ADP    /* `adp` make targets: u(r), w(r), src/imd_potential.c:87-92 (device side not yet run on a GPU) */
+  b200_check(imdb200_set_adp_tables(b200, (imdb200_pot_table *) &adp_upot, (imdb200_pot_table *) &adp_wpot));
+#endif
 #else
   b200_check(imdb200_set_potentials(b200, (imdb200_pot_table *) &pair_pot, NULL, NULL));
 #endif
