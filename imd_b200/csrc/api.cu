@@ -261,6 +261,7 @@ static int ready(imdb200_sim *s)
 
 static int calc_forces_async(imdb200_sim *s)
 {
+  s->p2p_step = s->have_valid_nbl;                     // steps with a list build keep the NCCL exchange
   if (!s->have_valid_nbl) TRY(cells_rebuild(s));       // fix_cells, send_cells, make_nblist (:304-317)
   else TRY(comm_ghost_pos(s));                         // send_cells(copy_cell,...) (:314)
   TRY(forces_pass1(s));
@@ -361,6 +362,7 @@ int imdb200_run(imdb200_sim *s, int nsteps)
   for (int k = 0; k < nsteps; k++) {
     const bool rebuild = !s->have_valid_nbl;
     cudaEventRecord(s->ev[0], s->stream);
+    s->p2p_step = !rebuild;
     if (rebuild) TRY(cells_rebuild(s)); else TRY(comm_ghost_pos(s));
     cudaEventRecord(s->ev[1], s->stream);
     TRY(forces_pass1(s));

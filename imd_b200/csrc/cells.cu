@@ -695,6 +695,7 @@ int cells_rebuild(imdb200_sim *s)
   const Geom &g = s->geom;
   cudaStream_t st = s->stream;
   if (s->n_own <= 0 && s->nranks == 1) return imdb_fail(IMDB200_ERR_ARG, "no atoms");
+  s->p2p_step = 0;                            // every exchange of a step with a list build goes through NCCL
   // ---- fix_cells: wrap into the box, bin, sort into cell order, hand atoms over to their new owners ----
   CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, FL_COUNT * sizeof(int), st));
   int *h_extra = s->h_starts;                 // pinned scratch: [0] atoms that stay, [1..28] extra bins

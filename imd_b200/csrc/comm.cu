@@ -88,11 +88,12 @@ extern "C" int imdb200_comm_init(imdb200_sim *s, const void *id128, int rank, in
     CUDA_TRY(cudaMalloc(&s->d_glob, SC_COUNT * sizeof(double)));
     CUDA_TRY(cudaMemset(s->d_glob, 0, SC_COUNT * sizeof(double)));
   }
-  return 0;
+  return comm_p2p_enable(s);               // peer-memory halo, only with IMDB200_HALO_P2P=1
 }
 
 void comm_free(imdb200_sim *s)
 {
+  comm_p2p_free(s);
   if (s->nccl_comm && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t) s->nccl_comm);
   s->nccl_comm = nullptr;
   void *ptrs[] = {s->gcells, s->gcount, s->gstart, s->scells, s->scount, s->sstart, s->send_idx, s->sendbuf4,
@@ -329,6 +330,12 @@ static int ensure_send_capacity(imdb200_sim *s, long n)
   return 0;
 }
 
+static int allgather_bytes(imdb200_sim *s, const void *mine, void *all, size_t bytes)
+{
+  NCCL_TRY(g_nccl.AllGather(mine, all, bytes, ncclInt8, (ncclComm_t) s->nccl_comm, s->stream));
+  return 0;
+}
+
 // At a rebuild: how many atoms sit in every buffer cell, where the images go, what we have to send.
 int comm_setup_ghosts(imdb200_sim *s)
 {
@@ -389,14 +396,17 @@ int comm_setup_ghosts(imdb200_sim *s)
     k_packi<<<cdiv(s->n_send, 256), 256, 0, st>>>(s->nummer, s->send_idx, s->n_send, s->sendbufi); LAUNCH_CHECK();
     TRY(exchange_forward<int>(s, s->sendbufi, s->ghost_num, ncclInt32, 1));
   }
+  if (s->p2p_on) TRY(comm_p2p_setup(s, allgather_bytes));
   return 0;
 }
 
 // send_cells(copy_cell, pack_cell, unpack_cell): positions (and types) of the owners into the buffer cells
 int comm_ghost_pos(imdb200_sim *s)
 {
+  const bool p2p = s->p2p_step && comm_p2p_ready(s);
+  if (p2p) TRY(comm_p2p_positions(s));     // direct stores into the neighbours' ghost_raw + stream flags
   if (s->n_ghost == 0) return 0;
-  if (s->n_send) {
+  if (s->n_send && !p2p) {
     TRY(need_comm(s));
     k_pack4<<<cdiv(s->n_send, 256), 256, 0, s->stream>>>(s->pos, s->send_idx, s->n_send, s->sendbuf4); LAUNCH_CHECK();
     TRY(exchange_forward<double>(s, (const double *) s->sendbuf4, (double *) s->ghost_raw, ncclFloat64, 4));
@@ -410,8 +420,10 @@ int comm_ghost_pos(imdb200_sim *s)
 // send_cells(copy_dF, pack_dF, unpack_dF): 2F'(rho) of the owners into the buffer cells
 int comm_ghost_dF(imdb200_sim *s)
 {
+  const bool p2p = s->p2p_step && comm_p2p_ready(s);
+  if (p2p) TRY(comm_p2p_dF(s));
   if (s->n_ghost == 0) return 0;
-  if (s->n_send) {
+  if (s->n_send && !p2p) {
     TRY(need_comm(s));
     k_pack1<<<cdiv(s->n_send, 256), 256, 0, s->stream>>>(s->dF, s->send_idx, s->n_send, s->sendbuf1); LAUNCH_CHECK();
     TRY(exchange_forward<double>(s, s->sendbuf1, s->dF + s->n_own, ncclFloat64, 1));

@@ -178,6 +178,8 @@ struct imdb200_sim {
   double t_ms[8];
   // comm
   void *nccl_comm; int rank, nranks;
+  // halo exchange over peer memory (comm_p2p.cu; off unless IMDB200_HALO_P2P=1, not yet run on a GPU)
+  int p2p_on, p2p_step; void *p2p;   // p2p_step: this exchange belongs to a step without a list build
 };
 
 // The list of an atom is stored in NBL_CLASSES+1 groups by the pair distance r_b at build time:
@@ -235,6 +237,12 @@ int comm_ghost_field(imdb200_sim *s, double *field, int ncomp, long stride);   /
 int comm_ghost_dM(imdb200_sim *s);            // the EAM_DM part of copy_dF in EEAM builds (src/imd_comm_force_3d.c:1044-1046)
 int comm_reverse_add(imdb200_sim *s, double *field, int ncomp, long stride);  // send_forces(add_*,...)
 int comm_sync_scalars(imdb200_sim *s);        // the MPI_Allreduce sites
+extern "C" int comm_p2p_enable(imdb200_sim *s);
+void comm_p2p_free(imdb200_sim *s);
+int comm_p2p_setup(imdb200_sim *s, int (*allgather)(imdb200_sim *, const void *, void *, size_t));
+int comm_p2p_ready(const imdb200_sim *s);
+int comm_p2p_positions(imdb200_sim *s);
+int comm_p2p_dF(imdb200_sim *s);
 int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
 
 int forces_pass1(imdb200_sim *s);             // pair + rho + embedding

@@ -17,14 +17,15 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _run(case, grid, port):
+def _run(case, grid, port, env=None):
     n = grid[0] * grid[1] * grid[2]
     if _ngpus() < n:
         pytest.skip(f"needs {n} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(common.ROOT, "tests", "mgpu_worker.py"), case] + [str(x) for x in grid]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=common.ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=common.ROOT,
+                       env=dict(os.environ, **(env or {})))
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     print(r.stdout[-1500:])
 
@@ -39,6 +40,15 @@ def test_two_domains_deformation_and_restrictions(built_lib, name):
     """lin_deform re-plans the cell grid and the halo on every rank; deform_sample and the restriction vectors act on
     virtual types that live on both sides of the domain boundary; nactive is summed over ranks."""
     _run("fixture:" + name, (2, 1, 1), 29619)
+
+
+@pytest.mark.xfail(strict=False, reason="the peer-memory halo (comm_p2p.cu, IMDB200_HALO_P2P=1) was written after this "
+                                         "round's GPU budget was spent and has not run on a GPU yet")
+@pytest.mark.parametrize("name", ["cu_long", "nial_nvt"])
+def test_two_domains_peer_memory_halo(built_lib, name):
+    """The same fixtures with the halo exchanged by direct stores into the neighbour's ghost region and stream memory
+    operations instead of NCCL messages; separate processes anyway (torchrun)."""
+    _run("fixture:" + name, (2, 1, 1), 29620, env={"IMDB200_HALO_P2P": "1"})
 
 
 def test_two_domains_split_along_z(built_lib):
