@@ -88,7 +88,7 @@ def test_cuda_npt_iso_matches_reference_fixture(api, tmp_path):
     tests down with it."""
     import os, subprocess, sys
     r = subprocess.run([sys.executable, os.path.join(common.ROOT, "tests", "npt_worker.py"), str(tmp_path)],
-                       capture_output=True, text=True, timeout=300, cwd=common.ROOT)
+                       capture_output=True, text=True, timeout=120, cwd=common.ROOT)
     assert r.returncode == 0 and "NPT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -101,7 +101,7 @@ def test_cuda_adp_matches_reference_fixture(api, name, lanes, tmp_path):
     forces (src/imd_forces_nbl.c:613-631, 1096-1110, 1217-1255), in its own process (tests/adp_worker.py)."""
     import os, subprocess, sys
     r = subprocess.run([sys.executable, os.path.join(common.ROOT, "tests", "adp_worker.py"), name, str(tmp_path), str(lanes)],
-                       capture_output=True, text=True, timeout=300, cwd=common.ROOT)
+                       capture_output=True, text=True, timeout=120, cwd=common.ROOT)
     assert r.returncode == 0 and "ADP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
