@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libimd_b200.so")
+# IMDB200_LIB: another build of the same library (tools/build_variant.sh: kernel experiments, never a fallback)
+LIB_PATH = os.environ.get("IMDB200_LIB") or os.path.join(HERE, "libimd_b200.so")
 
 NVE, NVT, NPT_ISO = 0, 1, 2
 PAIR, EMBED, RHO = 0, 1, 2

@@ -28,6 +28,7 @@ int imdb_fail(int code, const char *fmt, ...)
 
 extern "C" {
 
+void imdb200_destroy(imdb200_sim *s);
 const char *imdb200_last_error(void) { return g_err; }
 void imdb200_set_error_handler(void (*h)(const char *)) { g_handler = h; }
 long long imdb200_kernel_launches(void) { return g_kernel_launches; }
@@ -43,6 +44,23 @@ void imdb200_default_config(imdb200_config *c)
   c->ensemble = IMDB200_ENS_NVE;
   c->device = -1;
   c->lanes_per_atom = 0;
+}
+
+static int create_device_state(imdb200_sim *s)
+{
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  s->own_stream = 1;
+  CUDA_TRY(cudaMalloc(&s->d_scal, SC_COUNT * sizeof(double)));
+  CUDA_TRY(cudaMemset(s->d_scal, 0, SC_COUNT * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &s->eta, sizeof(double), cudaMemcpyHostToDevice));
+  s->d_glob = s->d_scal;            // one rank: the local block is the global one
+  CUDA_TRY(cudaMallocHost(&s->h_scal, SC_COUNT * sizeof(double)));
+  memset(s->h_scal, 0, SC_COUNT * sizeof(double));
+  CUDA_TRY(cudaMalloc(&s->d_flags, FL_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMemset(s->d_flags, 0, FL_COUNT * sizeof(int)));
+  CUDA_TRY(cudaMallocHost(&s->h_flags, FL_COUNT * sizeof(int)));
+  for (int i = 0; i < 16; i++) CUDA_TRY(cudaEventCreate(&s->ev[i]));
+  return 0;
 }
 
 int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
@@ -62,6 +80,7 @@ int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
     return imdb_fail(IMDB200_ERR_CUDA, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", dev, prop.name, prop.major, prop.minor);
   if (cfg->ntypes < 1 || cfg->ntypes * cfg->ntypes > IMDB_MAXCOL) return imdb_fail(IMDB200_ERR_ARG, "ntypes must be 1..4");
   imdb200_sim *s = (imdb200_sim *) calloc(1, sizeof(imdb200_sim));
+  if (!s) return imdb_fail(IMDB200_ERR_ARG, "out of host memory");
   s->cfg = *cfg;
   s->cfg.device = dev;
   if (s->cfg.total_types < s->cfg.ntypes) s->cfg.total_types = s->cfg.ntypes;
@@ -76,18 +95,8 @@ int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
   s->eta = cfg->eta;
   s->skin_skip = 1; s->disp2 = -1.0;
   s->npt_xi = cfg->xi; s->npt_ekin_old = -1.0; s->npt_pressure_ext = cfg->pressure_ext;
-  CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  s->own_stream = 1;
-  CUDA_TRY(cudaMalloc(&s->d_scal, SC_COUNT * sizeof(double)));
-  CUDA_TRY(cudaMemset(s->d_scal, 0, SC_COUNT * sizeof(double)));
-  CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &s->eta, sizeof(double), cudaMemcpyHostToDevice));
-  s->d_glob = s->d_scal;            // one rank: the local block is the global one
-  CUDA_TRY(cudaMallocHost(&s->h_scal, SC_COUNT * sizeof(double)));
-  memset(s->h_scal, 0, SC_COUNT * sizeof(double));
-  CUDA_TRY(cudaMalloc(&s->d_flags, FL_COUNT * sizeof(int)));
-  CUDA_TRY(cudaMemset(s->d_flags, 0, FL_COUNT * sizeof(int)));
-  CUDA_TRY(cudaMallocHost(&s->h_flags, FL_COUNT * sizeof(int)));
-  for (int i = 0; i < 16; i++) CUDA_TRY(cudaEventCreate(&s->ev[i]));
+  const int rc = create_device_state(s);
+  if (rc) { imdb200_destroy(s); return rc; }       // nothing of a half-built handle is left behind
   *out = s;
   return 0;
 }
@@ -96,7 +105,7 @@ void imdb200_destroy(imdb200_sim *s)
 {
   if (!s) return;
   cudaSetDevice(s->cfg.device);
-  cudaStreamSynchronize(s->stream);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   tables_free(s);
   comm_free(s);
   forces_free_textures(s);
@@ -108,7 +117,7 @@ void imdb200_destroy(imdb200_sim *s)
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->h_flags) cudaFreeHost(s->h_flags);
   for (int i = 0; i < 16; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
-  if (s->own_stream) cudaStreamDestroy(s->stream);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   free(s);
 }
 
@@ -150,7 +159,10 @@ int imdb200_set_stream(imdb200_sim *s, void *stream)
 int imdb200_set_restrictions(imdb200_sim *s, int total_types, const double *r)
 {
   if (!s || total_types < 1 || !r) return imdb_fail(IMDB200_ERR_ARG, "bad restrictions");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));        // queued kernels may still read the old table
   if (s->restr) cudaFree(s->restr);
+  s->restr = nullptr;
   CUDA_TRY(cudaMalloc(&s->restr, 3 * total_types * sizeof(double)));
   CUDA_TRY(cudaMemcpy(s->restr, r, 3 * total_types * sizeof(double), cudaMemcpyHostToDevice));
   int all1 = 1;
@@ -162,9 +174,13 @@ int imdb200_set_restrictions(imdb200_sim *s, int total_types, const double *r)
 
 static int ensure_partials(imdb200_sim *s)
 {
+  const size_t need = ((size_t) s->cap_atoms * 32 / 128 + 64) * 8 * sizeof(double);
+  if (s->d_partial && need <= s->partial_bytes) return 0;      // no allocation on a repeated set_atoms
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
   if (s->d_partial) cudaFree(s->d_partial);
-  s->d_partial = nullptr;
-  CUDA_TRY(cudaMalloc(&s->d_partial, ((size_t) s->cap_atoms * 32 / 128 + 64) * 8 * sizeof(double)));
+  s->d_partial = nullptr; s->partial_bytes = 0;
+  CUDA_TRY(cudaMalloc(&s->d_partial, need));
+  s->partial_bytes = need;
   return 0;
 }
 
@@ -282,7 +298,10 @@ int imdb200_calc_forces(imdb200_sim *s, int steps)
   TRY(ready(s));
   TRY(calc_forces_async(s));
   TRY(fetch_scalars(s));
-  if (s->h_flags[FL_SHORT]) fprintf(stderr, "Short distance, pair, step %d!\n", steps); /* :982 */
+  if (s->h_flags[FL_SHORT] && !s->short_warned && s->rank == 0) {   // once per handle, rank 0 speaks for all (the flag is global)
+    fprintf(stderr, "Short distance, pair, step %d!\n", steps); /* :982 */
+    s->short_warned = 1;
+  }
   return 0;
 }
 
@@ -351,6 +370,8 @@ int imdb200_set_eta(imdb200_sim *s, double eta)
 {
   if (!s) return IMDB200_ERR_ARG;
   s->eta = eta;
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
   CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &eta, sizeof(double), cudaMemcpyHostToDevice));
   return 0;
 }
@@ -392,7 +413,7 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     s->t_ms[5] += rebuild ? 1.0 : 0.0;
     s->t_ms[6] += 1.0;
   }
-  if (s->is_short) fprintf(stderr, "Short distance!\n");
+  if (s->is_short && !s->short_warned && s->rank == 0) { fprintf(stderr, "Short distance!\n"); s->short_warned = 1; }
   return 0;
 }
 
@@ -459,31 +480,36 @@ int imdb200_get_box(imdb200_sim *s, double out9[9])
 
 __global__ void k_unpack_soa(const double *src, long stride, int ncomp, long n, double *out);
 
+// the getters return the atom count, 0 when there is nothing to report and -1 after a CUDA error (imdb200_last_error)
+#define GET_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+  imdb_fail(IMDB200_ERR_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return -1; } } while (0)
+#define GET_LAUNCHED() do { g_kernel_launches++; GET_TRY(cudaGetLastError()); } while (0)
+
 long imdb200_get_adp(imdb200_sim *s, double *mu3, double *la6)
 {
   if (!s || s->n_own <= 0 || !s->tabs.have_adp || !s->adp_mu) return 0;
-  cudaSetDevice(s->cfg.device);
+  GET_TRY(cudaSetDevice(s->cfg.device));
   const long n = s->n_own;
   cudaStream_t st = s->stream;
   if (ensure_xfer(s, (size_t) n * 6 * sizeof(double))) return -1;
   double *b = (double *) s->xfer;
   const int nb = cdiv(n, 256);
-  if (mu3) { k_unpack_soa<<<nb, 256, 0, st>>>(s->adp_mu, s->adp_cap, 3, n, b); g_kernel_launches++;
-             cudaMemcpyAsync(mu3, b, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
-  if (la6) { k_unpack_soa<<<nb, 256, 0, st>>>(s->adp_la, s->adp_cap, 6, n, b); g_kernel_launches++;
-             cudaMemcpyAsync(la6, b, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, st); }
-  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  if (mu3) { k_unpack_soa<<<nb, 256, 0, st>>>(s->adp_mu, s->adp_cap, 3, n, b); GET_LAUNCHED();
+             GET_TRY(cudaMemcpyAsync(mu3, b, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st)); GET_TRY(cudaStreamSynchronize(st)); }
+  if (la6) { k_unpack_soa<<<nb, 256, 0, st>>>(s->adp_la, s->adp_cap, 6, n, b); GET_LAUNCHED();
+             GET_TRY(cudaMemcpyAsync(la6, b, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, st)); }
+  GET_TRY(cudaStreamSynchronize(st));
   return n;
 }
 
 long imdb200_get_eeam(imdb200_sim *s, double *eam_p, double *dM)
 {
   if (!s || s->n_own <= 0 || !s->tabs.have_eeam) return 0;
-  cudaSetDevice(s->cfg.device);
+  GET_TRY(cudaSetDevice(s->cfg.device));
   const long n = s->n_own;
-  if (eam_p) cudaMemcpyAsync(eam_p, s->eam_p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
-  if (dM) cudaMemcpyAsync(dM, s->dM, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
-  if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+  if (eam_p) GET_TRY(cudaMemcpyAsync(eam_p, s->eam_p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (dM) GET_TRY(cudaMemcpyAsync(dM, s->dM, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  GET_TRY(cudaStreamSynchronize(s->stream));
   return n;
 }
 
@@ -528,37 +554,38 @@ long imdb200_get_atoms(imdb200_sim *s, int *nummer, int *sorte, int *vsorte, dou
                        double *presstens, double *nblpos)
 {
   if (!s || s->n_own <= 0) return 0;
-  cudaSetDevice(s->cfg.device);
+  GET_TRY(cudaSetDevice(s->cfg.device));
   const long n = s->n_own;
   cudaStream_t st = s->stream;
   if (ensure_xfer(s, (size_t) n * 7 * sizeof(double))) return -1;
-  double *b3 = (double *) s->xfer, *b1 = b3 + 6 * n;     // up to 6 components + 1 scalar
+  // one staging area, re-used in stream order: up to 6 components + 1 scalar
+  double *b_ort = (double *) s->xfer, *b_imp = b_ort, *b_frc = b_ort, *b_pt = b_ort, *b_np = b_ort, *b_m = b_ort + 6 * n, *b_e = b_m;
+  int *bi = (int *) b_ort;
   const int nb = cdiv(n, 256);
-#define D2H(dst, src, bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)
-  if (ort) { k_unpack3<<<nb, 256, 0, st>>>(s->pos, n, b3, nullptr); g_kernel_launches++; D2H(ort, b3, 3 * n * sizeof(double)); }
+#define D2H(dst, src, bytes) GET_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
+  if (ort) { k_unpack3<<<nb, 256, 0, st>>>(s->pos, n, b_ort, nullptr); GET_LAUNCHED(); D2H(ort, b_ort, 3 * n * sizeof(double)); }
   if (sorte || vsorte) {
-    int *bi = (int *) b3;
-    k_unpack_types<<<nb, 256, 0, st>>>(s->pos, n, bi, bi + n); g_kernel_launches++;
+    k_unpack_types<<<nb, 256, 0, st>>>(s->pos, n, bi, bi + n); GET_LAUNCHED();
     if (sorte) D2H(sorte, bi, n * sizeof(int));
     if (vsorte) D2H(vsorte, bi + n, n * sizeof(int));
   }
   if (impuls || masse) {
-    k_unpack3<<<nb, 256, 0, st>>>(s->mom, n, impuls ? b3 : nullptr, masse ? b1 : nullptr); g_kernel_launches++;
-    if (impuls) D2H(impuls, b3, 3 * n * sizeof(double));
-    if (masse) D2H(masse, b1, n * sizeof(double));
+    k_unpack3<<<nb, 256, 0, st>>>(s->mom, n, impuls ? b_imp : nullptr, masse ? b_m : nullptr); GET_LAUNCHED();
+    if (impuls) D2H(impuls, b_imp, 3 * n * sizeof(double));
+    if (masse) D2H(masse, b_m, n * sizeof(double));
   }
   if (kraft || poteng) {
-    k_unpack3<<<nb, 256, 0, st>>>(s->frc, n, kraft ? b3 : nullptr, poteng ? b1 : nullptr); g_kernel_launches++;
-    if (kraft) D2H(kraft, b3, 3 * n * sizeof(double));
-    if (poteng) D2H(poteng, b1, n * sizeof(double));
+    k_unpack3<<<nb, 256, 0, st>>>(s->frc, n, kraft ? b_frc : nullptr, poteng ? b_e : nullptr); GET_LAUNCHED();
+    if (kraft) D2H(kraft, b_frc, 3 * n * sizeof(double));
+    if (poteng) D2H(poteng, b_e, n * sizeof(double));
   }
   if (nummer) D2H(nummer, s->nummer, n * sizeof(int));
   if (rho) { if (s->tabs.have_eam) D2H(rho, s->rho, n * sizeof(double)); else memset(rho, 0, n * sizeof(double)); }
   if (dF) { if (s->tabs.have_eam) D2H(dF, s->dF, n * sizeof(double)); else memset(dF, 0, n * sizeof(double)); }
-  if (presstens) { k_unpack_soa<<<nb, 256, 0, st>>>(s->presstens, s->cap_atoms, 6, n, b3); g_kernel_launches++; D2H(presstens, b3, 6 * n * sizeof(double)); }
-  if (nblpos) { k_unpack_soa<<<nb, 256, 0, st>>>(s->nblpos, s->cap_atoms, 3, n, b3); g_kernel_launches++; D2H(nblpos, b3, 3 * n * sizeof(double)); }
+  if (presstens) { k_unpack_soa<<<nb, 256, 0, st>>>(s->presstens, s->cap_atoms, 6, n, b_pt); GET_LAUNCHED(); D2H(presstens, b_pt, 6 * n * sizeof(double)); }
+  if (nblpos) { k_unpack_soa<<<nb, 256, 0, st>>>(s->nblpos, s->cap_atoms, 3, n, b_np); GET_LAUNCHED(); D2H(nblpos, b_np, 3 * n * sizeof(double)); }
 #undef D2H
-  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  GET_TRY(cudaStreamSynchronize(st));
   return n;
 }
 

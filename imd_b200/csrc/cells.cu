@@ -215,8 +215,11 @@ __global__ void k_wrap_bin(double4 *pos, long n, Geom g, BinArgs b, int *cellid,
     if (owner != me) {
       away = true;
       const int stride = d == 0 ? 1 : (d == 1 ? 3 : 9);
-      if (owner == (me + 1) % np) dir += stride;
-      else if (owner == (me + np - 1) % np) dir -= stride;
+      // the side follows from the coordinates; the periodic wrap only joins the two ends where the axis is
+      // periodic (with cpu_dim == 2 on a free axis "me+1 mod 2" would also match the neighbour BELOW)
+      const bool wrap = g.pbc[d] == 1 && np > 2;
+      if (owner == me + 1 || (wrap && me == np - 1 && owner == 0)) dir += stride;
+      else if (owner == me - 1 || (wrap && me == 0 && owner == np - 1)) dir -= stride;
       else lost = true;                                     // "Atom jumped multiple CPUs" (:170)
       v = 1;
     } else v = v - g.coff[d] + 1;

@@ -587,25 +587,28 @@ int comm_migrate(imdb200_sim *s, const int *h_counts, long n_stay, long *n_new)
 }
 
 // ---- the MPI_Allreduce sites: every rank gets every rank's scalar block and combines them in rank order --------
-__global__ void k_combine_scalars(const double *all, int nranks, double *glob)
+__global__ void k_combine_scalars(const double *all, int nranks, double *glob, int *flags)
 {
   const int v = threadIdx.x;
   if (v >= SC_COUNT) return;
   double x = all[v];
   for (int r = 1; r < nranks; r++) {
     const double y = all[r * SC_COUNT + v];
-    if (v == SC_MAXD2) x = fmax(x, y);         // MPI_MAX of check_nblist (src/imd_forces_nbl.c:2032)
+    if (v == SC_MAXD2 || v == SC_SHORT) x = fmax(x, y);   // MPI_MAX of check_nblist (src/imd_forces_nbl.c:2032)
     else if (v != SC_ETA) x += y;              // MPI_SUM; eta is identical on every rank
   }
   glob[v] = x;
+  if (v == SC_SHORT && x > 0.0) flags[FL_SHORT] = 1;      // a short distance seen by any rank is seen by all
 }
+__global__ void k_short_to_scal(const int *flags, double *scal) { scal[SC_SHORT] = flags[FL_SHORT] ? 1.0 : 0.0; }
 
 int comm_sync_scalars(imdb200_sim *s)
 {
   if (s->nranks == 1) return 0;
   TRY(need_comm(s));
+  k_short_to_scal<<<1, 1, 0, s->stream>>>(s->d_flags, s->d_scal); LAUNCH_CHECK();
   NCCL_TRY(g_nccl.AllGather(s->d_scal, s->d_all, SC_COUNT, ncclFloat64, (ncclComm_t) s->nccl_comm, s->stream));
-  k_combine_scalars<<<1, 32, 0, s->stream>>>(s->d_all, s->nranks, s->d_glob); LAUNCH_CHECK();
+  k_combine_scalars<<<1, 32, 0, s->stream>>>(s->d_all, s->nranks, s->d_glob, s->d_flags); LAUNCH_CHECK();
   return 0;
 }
 

@@ -58,6 +58,21 @@
 // coefficient per lookup).  The kernels carry the flag as a template argument so that their symbols differ.
 // IMDB_EEAM=1 adds the extended-EAM terms (EEAM builds of the reference, src/imd_forces_nbl.c:591-610, 1090-1095,
 // 1181-1208): p_i = sum rho^2 in pass 1, a second embedding look-up M(p_i), and the dM terms in pass 2.
+// Timing experiments only (tools/build_variant.sh; results are WRONG with either of them, never part of the product):
+// IMDB_EXP_BCAST=C makes the C lanes of a group walk the list of the group's first atom, i.e. every gather
+// instruction touches 32/C distinct records -- the cost of a gather with C-fold broadcast at unchanged list length;
+// IMDB_EXP_KCONST pins the table interval to two rows -- look-ups without bank conflicts.
+#ifndef IMDB_EXP_BCAST
+#define IMDB_EXP_BCAST 1
+#endif
+#ifdef IMDB_EXP_KCONST
+#define EXP_K(k) ((k) = 100 + ((k) & 1))
+#else
+#define EXP_K(k) ((void) 0)
+#endif
+#ifndef IMDB_BRANCHFREE
+#define IMDB_BRANCHFREE 1
+#endif
 #ifndef IMDB_CUBIC
 #define IMDB_CUBIC 0
 #endif
@@ -107,6 +122,14 @@ __device__ __forceinline__ double4 ld_atom_tex(cudaTextureObject_t t, int j)
   return make_double4(__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(b.y, b.x), __hiloint2double(b.w, b.z));
 }
 
+// 16-byte shared-memory load by 32-bit shared-window address (no generic-address conversion in the inner loop)
+__device__ __forceinline__ double2 lds2(unsigned addr)
+{
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
 template <int L> __device__ __forceinline__ double lanes_sum(double v)
 {
 #pragma unroll
@@ -134,6 +157,9 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
   const double *pC = T.pairC, *rC = T.rhoC;
   const double2 *pCD = T.pairCD, *rCD = T.rhoCD;           // cubic modes: (c2,c3)
   constexpr bool FUSED = EAM && !MULTI && SHARED && !CUB;  // one 48-byte record per interval, see DevTables::fused
+  constexpr bool FAST1 = FUSED && TSMEM && !STRESS && !EE && IMDB_BRANCHFREE;   // the branch-free block body below
+  const unsigned s_tab = (unsigned) __cvta_generic_to_shared(smem_raw);
+  const unsigned k_max = (unsigned) (T.fused_rows - 1);
   const double2 *fT = T.fused;
   if (TSMEM && FUSED) {
     stage(smem_raw, T.fused, T.fused_rows * 48);
@@ -181,8 +207,9 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
     if (act) {
       xi = a.pos[i];
       if (MULTI) it = sorte_of(xi.w);
-      const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
-      const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
+      const long lslot = slot & ~(long) (IMDB_EXP_BCAST - 1);
+      const int nn = (int) ((a.nnbc[lslot / L] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
+      const int *row = a.nbl + (size_t) (lslot >> 5) * ((size_t) a.rows * 32) + (lslot & 31);
       // Software pipeline over the list: the D entries of a block are in registers when the block starts (they
       // were loaded during the previous block), their D position gathers are issued together, the next block's
       // entries are requested, and only then the arithmetic of the block runs.  The list stream comes from HBM
@@ -199,6 +226,37 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         }
 #pragma unroll
         for (int d = 0; d < FDEPTH; d++) jq[d] = (m + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
+        if (FAST1) {
+          // Benchmark path (single species, phi and rho on one grid, quadratic tables in shared memory): the D entries of
+          // a block are evaluated WITHOUT branches -- entries beyond the list end or outside the cut-offs run through
+          // the same arithmetic with a clamped table index and are masked out of the sums (adding +0.0 leaves every
+          // sum bit-identical to skipping the entry).  Straight-line code lets the D independent dependency chains
+          // (gather -> r2 -> index -> LDS -> polynomials) overlap inside one warp; with the branchy form every entry
+          // waited out its own chain (5 warps per scheduler cannot hide that), see profiles/README.md round 2.
+#pragma unroll
+          for (int d = 0; d < FDEPTH; d++) {
+            const bool valid = m + d * L < nn;
+            const double4 xj = xq[d];
+            const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const bool inp = valid && r2 <= p_end0;                                  // :493
+            const bool inr = valid && r2 < r_end0;                                   // :588
+            double t = fma(r2, p_is0, p_nb0);                                        // (r2 - begin) * invstep
+            if (t < 0.0) { t = 0.0; if (inp || inr) is_short = 1; }
+            const double tk = __dadd_rz(t, IMDB_TWO52);
+            // entries beyond the cut-off index past the table: clamp the row (they are masked out below)
+            const unsigned rec = s_tab + 48u * min((unsigned) __double2loint(tk), k_max);
+            const double chi = t - (tk - IMDB_TWO52);
+            const double2 a0 = lds2(rec), a1 = lds2(rec + 16), a2 = lds2(rec + 32);    // (phi c0,c1) (phi c2, rho c2) (rho c0,c1)
+            double pot = tab_val(a0, a1.x, chi), grad = tab_grad(a0, a1.x, chi, p_is0 + p_is0), rv = tab_val(a2, a1.y, chi);
+            pot = inp ? pot : 0.0; grad = inp ? grad : 0.0; rv = inr ? rv : 0.0;
+            fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
+            ee += pot;
+            vir = fma(r2, grad, vir);
+            rh += rv;
+          }
+          continue;
+        }
 #pragma unroll
         for (int d = 0; d < FDEPTH; d++) {
         if (m + d * L >= nn) break;
@@ -211,7 +269,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         if (!(inp || inr)) continue;
         int k = 0, kr = 0; double chi = 0.0, chir = 0.0;
         const double pis = MULTI ? T.pair.invstep[col] : p_is0;
-        if (inp || SHARED) tab_index_fast(r2, MULTI ? -T.pair.begin[col] * pis : p_nb0, pis, k, chi, is_short);
+        if (inp || SHARED) { tab_index_fast(r2, MULTI ? -T.pair.begin[col] * pis : p_nb0, pis, k, chi, is_short); EXP_K(k); }
         if (EAM) {
           if (SHARED) { kr = k; chir = chi; }
           else if (inr) { const double ris = MULTI ? T.rho.invstep[col] : r_is0;
@@ -301,6 +359,9 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const double2 *rH = T.rhoH;
   const double *rH3 = T.rhoH3;                       // cubic modes: rho'/2 = h1 + chi*(h2 + chi*h3)
+  constexpr bool FAST2 = !MULTI && !EE && !CUB && !STRESS && TSMEM && IMDB_BRANCHFREE;
+  const unsigned s_tab = (unsigned) __cvta_generic_to_shared(smem_raw);
+  const unsigned k_max = (unsigned) (T.rho.nrows - 1);
   if (TSMEM) {
     const int nr = T.rho.nrows * T.rho.ncols;
     stage(smem_raw, T.rhoH, nr * 16);
@@ -329,8 +390,9 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       const int it = MULTI ? sorte_of(xi.w) : 0;
       const double dFi = MULTI ? a.dF[i] : xi.w;
       const double dMi = EE ? a.dM[i] : 0.0;
-      const int nn = (int) ((a.nnbc[i] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
-      const int *row = a.nbl + (size_t) (slot >> 5) * ((size_t) a.rows * 32) + (slot & 31);
+      const long lslot = slot & ~(long) (IMDB_EXP_BCAST - 1);
+      const int nn = (int) ((a.nnbc[lslot / L] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
+      const int *row = a.nbl + (size_t) (lslot >> 5) * ((size_t) a.rows * 32) + (lslot & 31);
       int jq[FDEPTH2];                                    // software pipeline as in pass 1
 #pragma unroll
       for (int d = 0; d < FDEPTH2; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
@@ -347,6 +409,27 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
         }
 #pragma unroll
         for (int d = 0; d < FDEPTH2; d++) jq[d] = (m + (FDEPTH2 + d) * L < nn) ? __ldcs(row + (FDEPTH2 + d) * 32) : -1;
+        if (FAST2) {
+          // branch-free block body, see pass 1
+#pragma unroll
+          for (int d = 0; d < FDEPTH2; d++) {
+            const bool valid = m + d * L < nn;
+            const double4 xj = xq[d];
+            const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const bool in = valid && r2 < r_end0;                                    // :1172
+            double t = fma(r2, r_is0, r_nb0);
+            if (t < 0.0) { t = 0.0; if (in) is_short = 1; }
+            const double tk = __dadd_rz(t, IMDB_TWO52);
+            const double2 h = lds2(s_tab + 16u * min((unsigned) __double2loint(tk), k_max));
+            const double chi = t - (tk - IMDB_TWO52);
+            double grad = (dFi + xj.w) * fma(chi, h.y, h.x);                         // 0.5*(dF_i+dF_j)*rho' (:1203)
+            grad = in ? grad : 0.0;
+            fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
+            vir = fma(r2, grad, vir);
+          }
+          continue;
+        }
 #pragma unroll
         for (int d = 0; d < FDEPTH2; d++) {
         if (m + d * L >= nn) break;
@@ -359,6 +442,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           if (!(r2 < r_end0)) continue;                    // :1172
           int k; double chi;
           tab_index_fast(r2, r_nb0, r_is0, k, chi, is_short);
+          EXP_K(k);
           if (!EE) {
             const double2 h = rH[k];
             const double hs = CUB ? fma(chi, rH3[k], h.y) : h.y;

@@ -164,9 +164,9 @@ struct imdb200_sim {
   double *d_glob;      // the same summed over ranks (== d_scal on one rank)
   double *d_all;       // [nranks][SC_COUNT] all-gather target
   double *h_scal;      // pinned mirror of d_glob
-  double *d_partial;   // per-block partial sums
+  double *d_partial; size_t partial_bytes;   // per-block partial sums
   int *d_flags, *h_flags;
-  int press_calc, is_short;
+  int press_calc, is_short, short_warned;
   long long nactive;   // sum of the restriction components over all atoms (3N by default)
   int nactive_dirty;   // atoms or restrictions changed: recount at the next rebuild / step
   // NPT_iso: barostat friction, twice the global kinetic energy after the last step (< 0: unknown), external pressure,
@@ -192,7 +192,7 @@ struct imdb200_sim {
 #define NBIN_EXTRA 29   // 27 leave directions + 1 dropped + 1 spare (exclusive-scan total)
 
 enum { SC_EPOT = 0, SC_VIRIAL, SC_EKIN, SC_EKIN2, SC_MAXD2, SC_ETA, SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX,
-       SC_PXY, SC_EKIN1, SC_COUNT = 16 };
+       SC_PXY, SC_EKIN1, SC_SHORT, SC_COUNT = 16 };   // SC_SHORT: is_short of any rank (max); slot 15 is scratch
 enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_NSEND, FL_BADTYPE, FL_CELLFULL, FL_COUNT = 8 };
 
 // ---- error handling --------------------------------------------------------------------------------
@@ -217,6 +217,7 @@ __host__ __device__ inline size_t nbl_index(long i, int m, int L, int R)
 int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_pot_table *embed,
                   const imdb200_pot_table *rho);
 void tables_free(imdb200_sim *s);
+void tables_set_cellsz0(imdb200_sim *s, double cz);   // new interaction range: cell grid and list cut-off are re-derived
 int tables_pair_int(imdb200_sim *s, int which, int col, long n, const double *r2, double *pot, double *grad);
 int tables_upload_emod(imdb200_sim *s, const imdb200_pot_table *emod);   // EEAM energy modification term
 int tables_upload_adp(imdb200_sim *s, const imdb200_pot_table *u, const imdb200_pot_table *w);   // ADP u(r), w(r)

@@ -1,5 +1,17 @@
 // tables.cu -- potential tables: pot_table_t (src/types.h:416-428) -> derived device tables.
 #include "internal.cuh"
+
+// cellsz = max end of the radial tables (src/imd_potential.c:364, 406).  The cell size, the cell grid, the halo plan and
+// the list cut-off (r2 < cellsz) all derive from it: when it changes they are derived again at the next
+// geom_make_box (init_cells adds the margin once to a cellsz of 0, src/imd_geom_3d.c:122-126).
+void tables_set_cellsz0(imdb200_sim *s, double cz)
+{
+  if (cz == s->cellsz0 && s->geom.cellsz != 0.0) return;
+  s->cellsz0 = cz;
+  s->geom.cellsz = 0.0;
+  for (int d = 0; d < 3; d++) { s->min_height[d] = 0.0; s->max_height[d] = 0.0; }   // forces init_cells
+  s->have_valid_nbl = 0;
+}
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -233,7 +245,7 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
   const size_t limit = 128 * 1024;
   T.smem1 = bytes1 <= limit ? (int) bytes1 : 0;
   T.smem2 = (bytes2 && bytes2 <= limit) ? (int) bytes2 : 0;
-  s->cellsz0 = cz;
+  tables_set_cellsz0(s, cz);
   s->have_tabs = 1;
   return 0;
 }
@@ -293,10 +305,12 @@ int tables_upload_adp(imdb200_sim *s, const imdb200_pot_table *u, const imdb200_
   TRY(upload_adp_one(s, 9, u, T.adpu, &T.adpuK));
   TRY(upload_adp_one(s, 10, w, T.adpw, &T.adpwK));
   // radial tables take part in cellsz = max end (src/imd_potential.c:406)
+  double cz = s->cellsz0;
   for (int col = 0; col < nt * nt; col++) {
-    if (u->end[col] > s->cellsz0) s->cellsz0 = u->end[col];
-    if (w->end[col] > s->cellsz0) s->cellsz0 = w->end[col];
+    if (u->end[col] > cz) cz = u->end[col];
+    if (w->end[col] > cz) cz = w->end[col];
   }
+  tables_set_cellsz0(s, cz);
   T.have_adp = 1;
   return 0;
 }

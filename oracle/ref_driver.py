@@ -218,6 +218,7 @@ def run_protocol(sim, spec):
     out["start"] = sim.atoms()
     if getattr(sim, "has_npt", False):
         out["npt_start"] = sim.npt()
+    out["nbl_count0"] = sim.nbl_count      # builds before the protocol (thermalisation); the protocol's share = nbl_count - this
     out["box"] = sim.box()
     out["celldims"] = sim.celldims()
     out["cellsz"] = sim.cellsz

@@ -61,17 +61,21 @@ def case_fixture(name, grid, rank):
     return sim
 
 
-def case_migration(grid, rank):
-    """Hot crystal, 16 384 atoms, 120 steps: atoms change domains; compare with the same run on ONE GPU."""
+def case_migration(grid, rank, pbc=(1, 1, 1)):
+    """Hot crystal, 16 384 atoms, 120 steps: atoms change domains; compare with the same run on ONE GPU.
+    pbc = (1, 1, 0): a slab with free surfaces in z; split along z, an atom that moves from the upper into the lower
+    domain must be handed DOWN although (me + 1) % 2 names the same rank (cells.cu, k_wrap_bin)."""
     tmp = tempfile.mkdtemp(prefix=f"mig{rank}_")
     tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
     ort, box = synth.fcc_lattice((16, 16, 16), synth.CU_A0)
+    if pbc[2] == 0:
+        box = box.copy(); box[2, 2] *= 1.5; ort = ort + np.array([0.0, 0.0, 0.25 * 16 * synth.CU_A0])   # vacuum above and below
     n = len(ort)
     m = np.full(n, synth.CU_MASS)
     p = synth.maxwell_momenta(n, m, 0.35, 7)          # ~4000 K: diffusion across the domain faces
     num, typ = np.arange(n, dtype=np.int32), np.zeros(n, np.int32)
     kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"],
-              ensemble="nve", timestep=0.001)
+              ensemble="nve", timestep=0.001, pbc=pbc)
     sim = idist.create(1, box, cpu_dim=grid, device=int(os.environ.get("LOCAL_RANK", "0")), **kw)
     sim.set_atoms(num, typ, m, ort, p)
     counts = []
@@ -152,6 +156,8 @@ def main():
         sim = case_fixture(case.split(":", 1)[1], grid, rank)
     elif case == "migration":
         sim = case_migration(grid, rank)
+    elif case == "migration_slab":
+        sim = case_migration(grid, rank, pbc=(1, 1, 0))
     elif case == "send_forces":
         sim = case_send_forces(grid, rank)
     else:

@@ -34,6 +34,30 @@ def test_cuda_matches_reference_fixture(api, name, lanes, tmp_path):
     sim.close()
 
 
+@pytest.mark.parametrize("name,lanes", [("cu_big", 0), ("cu_big", 1), ("nial_big", 0), ("nial_big", 2)])
+def test_cuda_matches_large_reference_fixture(api, name, lanes, tmp_path):
+    """Parity at scale against the unmodified reference: 131 072 Cu atoms (19^3 cells, 60 steps, 5 list builds, the
+    benchmark's 2001/4001-row tables = the fused 96 KB table in shared memory) and 54 000 Ni-Al atoms under NVT
+    (14^3 cells, 4-column tables that stay in HBM/L1).  Neighbour set of every atom through its 64-bit hash, rebuild
+    decisions and list-build count exact, per-atom results of a 4 096-atom sample <= 1e-10 per component."""
+    g = common.load_golden(name)
+    sim = common.make_sim(api.IMDB200, g, str(tmp_path), lanes_per_atom=lanes)
+    out = common.run_protocol(sim, g)
+    errs = common.compare(out, g, full_list=True, rtol=1e-10, traj_rtol=1e-8)
+    assert np.array_equal(sim.celldims()[0], g["gdim"]) and sim.cellsz == float(g["cellsz"])
+    assert errs["nbl_builds"] == int(g["nbl_builds"]) >= 3
+    print(name, lanes, {k: f"{v:.1e}" for k, v in errs.items()})
+    sim.close()
+
+
+def test_parity_fixture_helper_single_rank(api):
+    """tools/parity_fixture.check (what bench.py --gpus N > 1 reports as `parity_check`) on one rank."""
+    from tools import parity_fixture as pf
+    for name in ("cu_long", "nial_nvt", "nial_big"):
+        r = pf.check(name, (1, 1, 1), 0)
+        assert r["ok"], r
+
+
 @pytest.mark.parametrize("lanes", [1, 8])
 @pytest.mark.parametrize("name", CUBIC_CASES)
 def test_cuda_cubic_interpolation_matches_reference_fixture(api, name, lanes, tmp_path):
@@ -78,23 +102,16 @@ def test_cuda_eeam_matches_reference_fixture(api, name, lanes, tmp_path):
     sim.close()
 
 
-@pytest.mark.xfail(strict=False, reason="NPT_iso on the device was written after this round's GPU budget was spent: it "
-                                         "compiles, its oracle twin passes the same fixture on the CPU, but it has not "
-                                         "run on a B200 yet (DESIGN.md section 8)")
 def test_cuda_npt_iso_matches_reference_fixture(api, tmp_path):
     """IMDB200_ENS_NPT_ISO against the reference's `npt_iso` build: xi, the pressure that drives it, eta, the breathing
     box and the trajectory (move_atoms_npt_iso, src/imd_integrate.c:1472-1729).  Runs in its own process
-    (tests/npt_worker.py): code that has never run on a GPU must not be able to take the CUDA context of the other
-    tests down with it."""
+    (tests/npt_worker.py).  Green on B200 since round 1 (GPUTEST_r01.json)."""
     import os, subprocess, sys
     r = subprocess.run([sys.executable, os.path.join(common.ROOT, "tests", "npt_worker.py"), str(tmp_path)],
                        capture_output=True, text=True, timeout=120, cwd=common.ROOT)
     assert r.returncode == 0 and "NPT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="the ADP kernels (forces_adp.cu) were written after this round's GPU budget was "
-                                         "spent: they compile, their oracle twin passes the same fixtures on the CPU, "
-                                         "but they have not run on a B200 yet (DESIGN.md section 8)")
 @pytest.mark.parametrize("name,lanes", [("cu_adp", 1), ("nial_adp", 4)])
 def test_cuda_adp_matches_reference_fixture(api, name, lanes, tmp_path):
     """imdb200_set_adp_tables against the reference's `adp` build: mu, lambda, the ADP energy and the dipole / quadrupole

@@ -51,12 +51,23 @@ def test_two_domains_peer_memory_halo(built_lib, name):
     _run("fixture:" + name, (2, 1, 1), 29620, env={"IMDB200_HALO_P2P": "1"})
 
 
+@pytest.mark.parametrize("name", ["cu_big", "nial_big"])
+def test_two_domains_match_large_reference_fixture(built_lib, name):
+    """131 072 Cu / 54 000 Ni-Al atoms on two domains against the unmodified single-process reference."""
+    _run("fixture:" + name, (2, 1, 1), 29622)
+
+
 def test_two_domains_split_along_z(built_lib):
     _run("fixture:cu_long", (1, 1, 2), 29612)
 
 
 def test_atoms_migrate_between_domains(built_lib):
     _run("migration", (2, 1, 1), 29613)
+
+
+def test_atoms_migrate_across_a_free_axis_split(built_lib):
+    """cpu_dim = (1,1,2) on a slab with free z surfaces: the leave direction must come from the coordinates."""
+    _run("migration_slab", (1, 1, 2), 29621)
 
 
 def test_send_forces_reverse_path(built_lib):
@@ -71,3 +82,5 @@ def test_four_domains(built_lib):
 def test_eight_domains(built_lib):
     _run("migration", (2, 2, 2), 29617)
     _run("send_forces", (2, 2, 2), 29618)
+    _run("fixture:cu_big", (2, 2, 2), 29623)
+    _run("fixture:nial_big", (2, 2, 2), 29624)

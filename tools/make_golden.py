@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 from imd_b200 import synth  # noqa: E402
 from oracle import ref_driver as rd  # noqa: E402
 from oracle.oracle import canonical_pairs  # noqa: E402
+from tools.parity_fixture import pair_hash  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -86,6 +87,15 @@ CASES = {
                          record=[0, 29], press=False, variant="ber", extra=dict(tau_berendsen=0.05, endtemp=0.09)),
     "cu_long": dict(kind="cu", ncell=(7, 5, 6), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
                     record=[0, 59], press=False, variant="eam"),
+    # Parity at scale: 131 072 Cu atoms (19^3 cells) with the benchmark's full-resolution tables
+    # (2001 / 4001 rows, the 96 KB fused table of the single-species kernels) over 60 steps with several rebuilds, and
+    # 54 000 Ni-Al atoms (B2, 4-column tables that do not fit in shared memory) under NVT.  `big`: the start state is
+    # stored in full, per-atom results only for a seeded sample of 4 096 atoms, the neighbour set as one 64-bit hash
+    # per atom (tools/parity_fixture.pair_hash) -- small files, same pinning power.
+    "cu_big": dict(kind="cu", ncell=(32, 32, 32), ensemble="nve", starttemp=0.12, warm=30, nsteps=60,
+                   record=[0, 59], press=False, variant="eam", big=True, fullres=True),
+    "nial_big": dict(kind="nial", ncell=(30, 30, 30), ensemble="nvt", starttemp=0.06, warm=30, nsteps=40,
+                     record=[0, 39], press=False, variant="eam", big=True, fullres=True),
 }
 
 
@@ -107,8 +117,9 @@ def make_case(name, c):
     if c.get("adp"):
         pu, pw = synth.make_adp_tables(tmp, nt=2 if c["kind"] == "nial" else 1)
         c = dict(c, extra=dict(c.get("extra") or {}, adp_upotfile=pu, adp_wpotfile=pw))
+    res = dict() if c.get("fullres") else dict(nr=601, nrho=801)
     if c["kind"] == "cu":
-        tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+        tabs = synth.make_eam_tables(tmp, "cu", **res)
         p = synth.cu_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
                            tables=tabs, extra=c.get("extra"))
         ntypes = 1
@@ -130,7 +141,7 @@ def make_case(name, c):
                     "deform_shift 1 0.012 0.0 0.0\n")
         ntypes = 1
     elif c["kind"] == "nial":
-        tabs = synth.make_eam_tables(tmp, "nial", nr=601, nrho=801)
+        tabs = synth.make_eam_tables(tmp, "nial", **res)
         p = synth.nial_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"],
                              tables=tabs, extra=c.get("extra"))
         ntypes = 2
@@ -196,19 +207,41 @@ def make_case(name, c):
     g["eta"] = np.array([f["after"]["eta"] for f in out["frames"]])
     g["valid"] = np.array([f["valid"] for f in out["frames"]])
     g["nbl_count"] = out["nbl_count"]
+    g["nbl_builds"] = out["nbl_count"] - out["nbl_count0"]       # list builds of the protocol itself
+    big = bool(c.get("big"))
+    sel = slice(None)
+    if big:
+        # atoms() is sorted by NUMMER: the sample is a set of positions in that order
+        sel = np.sort(np.random.default_rng(2024).choice(out["natoms"], 4096, replace=False)).astype(np.int32)
+        g["sample"] = sel
+        g["final:ort"] = out["final"]["ort"][sel]
+        del g["final:impuls"]
     for s in c["record"]:
         a = out["frames"][s]["atoms"]
         for k in ("kraft", "poteng", "rho", "dF", "presstens", "ort") + (("eam_p", "dM") if c.get("eeam") else ()) \
                 + (("adp_mu", "adp_lambda") if c.get("adp") else ()):
-            g[f"f{s}:{k}"] = a[k]
+            if big and k in ("presstens", "ort"):
+                continue
+            g[f"f{s}:{k}"] = a[k][sel]
         if c["press"]:
             g[f"f{s}:tot_presstens"] = out["frames"][s]["tot_presstens"]
     fr0 = out["frames"][0]
-    g["nbl"] = canonical_pairs(fr0["nbl_pairs"], fr0["nbl_shift"]).astype(np.int32)
+    rows = canonical_pairs(fr0["nbl_pairs"], fr0["nbl_shift"])
+    if big:
+        # symmetric closure of the half list, hashed per atom: by atom numbers alone (what a domain-decomposed run can
+        # report) and with the image shift of every entry folded in (single-domain runs)
+        full = np.concatenate([rows, np.column_stack([rows[:, 1], rows[:, 0], -rows[:, 2:]])])
+        g["nbl_len_full"] = len(full)
+        g["nbl_hash_nummer"], g["nbl_hash"] = pair_hash(full[:, 0], full[:, 1])
+        code = (full[:, 2] + 1) + 3 * (full[:, 3] + 1) + 9 * (full[:, 4] + 1)
+        _, g["nbl_hash_shift"] = pair_hash(full[:, 0], full[:, 1] * 27 + code)
+        g["nbl_hash_nummer"] = g["nbl_hash_nummer"].astype(np.int32)
+    else:
+        g["nbl"] = rows.astype(np.int32)
     os.makedirs(GOLD, exist_ok=True)
     path = os.path.join(GOLD, name + ".npz")
     np.savez_compressed(path, **g)
-    print(f"{name}: {out['natoms']} atoms, cells {g['gdim']}, {len(g['nbl'])} pairs, "
+    print(f"{name}: {out['natoms']} atoms, cells {g['gdim']}, {len(rows)} pairs, {g['nbl_builds']} builds in the protocol, "
           f"{out['nbl_count']} list builds, {os.path.getsize(path) / 1024:.0f} kB")
 
 
