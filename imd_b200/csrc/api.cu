@@ -26,6 +26,16 @@ int imdb_fail(int code, const char *fmt, ...)
   return code;
 }
 
+// StepCtl::disp2 <- max squared displacement since the list build (the global SC_MAXD2), or 0 right after a build
+__global__ void k_snapshot_disp2(StepCtl *ctl, const double *glob, int reset) { ctl->disp2 = reset ? 0.0 : glob[SC_MAXD2]; }
+
+int step_snapshot_disp2(imdb200_sim *s, int reset)
+{
+  k_snapshot_disp2<<<1, 1, 0, s->stream>>>(s->d_ctl, s->d_glob, reset);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" {
 
 void imdb200_destroy(imdb200_sim *s);
@@ -60,6 +70,12 @@ static int create_device_state(imdb200_sim *s)
   CUDA_TRY(cudaMemset(s->d_flags, 0, FL_COUNT * sizeof(int)));
   CUDA_TRY(cudaMallocHost(&s->h_flags, FL_COUNT * sizeof(int)));
   for (int i = 0; i < 16; i++) CUDA_TRY(cudaEventCreate(&s->ev[i]));
+  const StepCtl ctl0 = {1, 0, -1.0};               // gate open, displacement unknown
+  CUDA_TRY(cudaMalloc(&s->d_ctl, sizeof(StepCtl)));
+  CUDA_TRY(cudaMemcpy(s->d_ctl, &ctl0, sizeof(ctl0), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&s->d_slot, 3 * sizeof(StepSlot)));
+  CUDA_TRY(cudaMallocHost(&s->h_slot, 3 * sizeof(StepSlot)));
+  for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_slot[i], cudaEventDisableTiming));
   return 0;
 }
 
@@ -116,6 +132,10 @@ void imdb200_destroy(imdb200_sim *s)
   for (void *p : ptrs) if (p) cudaFree(p);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->h_flags) cudaFreeHost(s->h_flags);
+  if (s->d_ctl) cudaFree(s->d_ctl);
+  if (s->d_slot) cudaFree(s->d_slot);
+  if (s->h_slot) cudaFreeHost(s->h_slot);
+  for (int i = 0; i < 3; i++) if (s->ev_slot[i]) cudaEventDestroy(s->ev_slot[i]);
   for (int i = 0; i < 16; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   free(s);
@@ -255,6 +275,25 @@ int imdb200_set_atoms(imdb200_sim *s, long n, const int *nummer, const int *sort
 }
 
 // ---- the step loop ------------------------------------------------------------------------------------
+// End of one queued step of imdb200_run: check_nblist's decision (src/imd_forces_nbl.c:2036) taken on the device.
+// An executed step (gate open) publishes its scalars and closes the gate when the list has become invalid, which
+// turns the kernels of the step queued behind it into no-ops; a gated step reports executed = 0.
+__global__ void k_step_end(StepCtl *ctl, const double *glob, const int *flags, double lim2, StepSlot *out)
+{
+  const int t = threadIdx.x;
+  const int open = ctl->gate;
+  __syncwarp();
+  if (t < SC_COUNT) out->scal[t] = glob[t];
+  if (t < FL_COUNT) out->flags[t] = flags[t];
+  if (t == 0) {
+    const int valid = open && !(glob[SC_MAXD2] > lim2);
+    out->executed = open;
+    out->valid = valid;
+    if (open) { ctl->disp2 = glob[SC_MAXD2]; ctl->gate = valid; }
+  }
+}
+__global__ void k_open_gate(StepCtl *ctl) { ctl->gate = 1; }
+
 static int fetch_scalars(imdb200_sim *s)
 {
   TRY(comm_sync_scalars(s));     // MPI_Allreduce sites: every rank sees the sums over all domains
@@ -332,7 +371,7 @@ int imdb200_move_atoms(imdb200_sim *s)
   if (s->cfg.ensemble == IMDB200_ENS_NPT_ISO) TRY(move_npt(s));
   else { TRY(integrate_move(s)); TRY(fetch_scalars(s)); }
   s->disp2 = s->h_scal[SC_MAXD2];
-  return 0;
+  return step_snapshot_disp2(s, 0);
 }
 
 int imdb200_set_npt_state(imdb200_sim *s, double xi, double Ekin_old, double pressure_ext)
@@ -357,7 +396,7 @@ int imdb200_check_nblist(imdb200_sim *s)
   TRY(fetch_scalars(s));
   s->disp2 = s->h_scal[SC_MAXD2];
   apply_check(s);
-  return 0;
+  return step_snapshot_disp2(s, 0);
 }
 
 int imdb200_fix_cells(imdb200_sim *s) { TRY(ready(s)); s->have_valid_nbl = 0; return cells_rebuild(s); }
@@ -377,9 +416,109 @@ int imdb200_set_eta(imdb200_sim *s, double eta)
 }
 int imdb200_set_temperature(imdb200_sim *s, double t) { if (!s) return IMDB200_ERR_ARG; s->cfg.temperature = t; return 0; }
 
+// One step of imdb200_run, queued without waiting for anything: forces, move_atoms, check_nblist on the device,
+// results into result slot `slot`.  `built`: the list was rebuilt just before (the ghost positions are current).
+static int queue_step(imdb200_sim *s, int slot, bool built)
+{
+  cudaEvent_t *ev = s->ev + 5 * slot;
+  if (!built) { cudaEventRecord(ev[0], s->stream); TRY(comm_ghost_pos(s)); }       // send_cells(copy_cell,...) (:314)
+  cudaEventRecord(ev[1], s->stream);
+  // single-species EAM: move_atoms + check_nblist ride in the tail of pass 2 (bit-identical, one kernel less)
+  const int fuse = forces_can_fuse_move(s);
+  s->fuse_step = fuse; s->zero_before_move = !fuse;
+  TRY(forces_pass1(s));
+  cudaEventRecord(ev[2], s->stream);
+  if (s->tabs.have_eam) {
+    TRY(comm_ghost_dF(s));                                                         // send_cells(copy_dF,...) (:1115)
+    if (s->tabs.have_eeam) TRY(comm_ghost_dM(s));
+    TRY(forces_pass2(s, fuse));
+  } else s->maxd2_zeroed = 0;
+  cudaEventRecord(ev[3], s->stream);
+  if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
+  s->fuse_step = 0; s->zero_before_move = 0;
+  cudaEventRecord(ev[4], s->stream);
+  TRY(comm_sync_scalars(s));                  // the MPI_Allreduce sites: every rank sees the sums and the global maximum
+  const double lim = 0.5 * s->cfg.nbl_margin;
+  k_step_end<<<1, 32, 0, s->stream>>>(s->d_ctl, s->d_glob, s->d_flags, lim * lim, s->d_slot + slot); LAUNCH_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(s->h_slot + slot, s->d_slot + slot, sizeof(StepSlot), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaEventRecord(s->ev_slot[slot], s->stream));
+  return 0;
+}
+
+// The host looks at a finished step: scalars, flags, timers, and whether the list survived it.
+static int retire_step(imdb200_sim *s, int slot, bool built, double rebuild_ms, int *executed)
+{
+  CUDA_TRY(cudaEventSynchronize(s->ev_slot[slot]));
+  const StepSlot &r = s->h_slot[slot];
+  *executed = r.executed;
+  if (!r.executed) return 0;                    // it was queued behind a step that invalidated the list: nothing happened
+  memcpy(s->h_scal, r.scal, sizeof(r.scal));
+  memcpy(s->h_flags, r.flags, sizeof(r.flags));
+  if (s->h_flags[FL_SHORT]) s->is_short = 1;
+  s->eta = s->h_scal[SC_ETA];
+  s->disp2 = s->h_scal[SC_MAXD2];
+  if (!r.valid) s->have_valid_nbl = 0;
+  cudaEvent_t *ev = s->ev + 5 * slot;
+  float ms;
+  if (built) s->t_ms[0] += rebuild_ms; else { cudaEventElapsedTime(&ms, ev[0], ev[1]); s->t_ms[4] += ms; }
+  cudaEventElapsedTime(&ms, ev[1], ev[2]); s->t_ms[1] += ms;
+  cudaEventElapsedTime(&ms, ev[2], ev[3]); s->t_ms[2] += ms;
+  cudaEventElapsedTime(&ms, ev[3], ev[4]); s->t_ms[3] += ms;
+  s->t_ms[5] += built ? 1.0 : 0.0;
+  s->t_ms[6] += 1.0;
+  return 0;
+}
+
+// main_loop (src/imd_main_3d.c:155-870) for nve / nvt, resident on the device.  The host never waits for the step it
+// has just queued: it queues the next one first and then looks at the previous one (scalars, rebuild decision).  The
+// decision itself is taken on the device (k_step_end); when a step invalidates the list, the step already queued
+// behind it finds the gate closed and does nothing, the host rebuilds the list and queues it again.
+static int run_async(imdb200_sim *s, int nsteps)
+{
+  int done = 0, inflight = 0, head = 0, tail = 0;
+  bool built[3] = {false, false, false};
+  double reb_ms[3] = {0.0, 0.0, 0.0};
+  int rc = 0;
+  while (done < nsteps && rc == 0) {
+    bool fresh = false;
+    double rms = 0.0;
+    if (!s->have_valid_nbl) {                  // only reached with nothing in flight
+      cudaEventRecord(s->ev[15], s->stream);
+      if ((rc = cells_rebuild(s)) != 0) break; // fix_cells, send_cells, make_nblist (:304-317); synchronises
+      k_open_gate<<<1, 1, 0, s->stream>>>(s->d_ctl); g_kernel_launches++;
+      cudaEventRecord(s->ev[14], s->stream);
+      cudaEventSynchronize(s->ev[14]);
+      float ms; cudaEventElapsedTime(&ms, s->ev[15], s->ev[14]); rms = ms;
+      fresh = true;
+    }
+    while (inflight < 2 && done + inflight < nsteps && rc == 0) {
+      built[head] = fresh; reb_ms[head] = rms; fresh = false;
+      rc = queue_step(s, head, built[head]);
+      head = (head + 1) % 3; inflight++;
+    }
+    if (rc) break;
+    int executed = 0;
+    rc = retire_step(s, tail, built[tail], reb_ms[tail], &executed);
+    tail = (tail + 1) % 3; inflight--;
+    done += executed;
+    if (rc == 0 && !s->have_valid_nbl)         // what is still queued will find the gate closed: drain it
+      while (inflight > 0 && rc == 0) { rc = retire_step(s, tail, false, 0.0, &executed); tail = (tail + 1) % 3; inflight--; done += executed; }
+  }
+  // leave the gate open for the stand-alone calls (the host flag have_valid_nbl carries the decision from here on)
+  cudaStreamSynchronize(s->stream);
+  k_open_gate<<<1, 1, 0, s->stream>>>(s->d_ctl); g_kernel_launches++;
+  return rc;
+}
+
 int imdb200_run(imdb200_sim *s, int nsteps)
 {
   TRY(ready(s));
+  if (s->cfg.ensemble != IMDB200_ENS_NPT_ISO && !s->tabs.have_adp) {
+    TRY(run_async(s, nsteps));
+    if (s->is_short && !s->short_warned && s->rank == 0) { fprintf(stderr, "Short distance!\n"); s->short_warned = 1; }
+    return 0;
+  }
+  // npt_iso (the host advances the barostat between the force and the move kernels) and ADP: one step at a time
   for (int k = 0; k < nsteps; k++) {
     const bool rebuild = !s->have_valid_nbl;
     cudaEventRecord(s->ev[0], s->stream);
@@ -388,22 +527,21 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     cudaEventRecord(s->ev[1], s->stream);
     TRY(forces_pass1(s));
     cudaEventRecord(s->ev[2], s->stream);
-    // single-species EAM: move_atoms + check_nblist ride in the tail of pass 2 (bit-identical, one kernel less)
-    const int fuse = forces_can_fuse_move(s);
     if (s->tabs.have_adp) TRY(forces_adp_pass1(s));
     if (s->tabs.have_eam) {
       TRY(comm_ghost_dF(s));
       if (s->tabs.have_eeam) TRY(comm_ghost_dM(s));
       if (s->tabs.have_adp) TRY(forces_adp_halo(s));
-      TRY(forces_pass2(s, fuse));
+      TRY(forces_pass2(s, 0));
       if (s->tabs.have_adp) TRY(forces_adp_pass2(s));
     }
     cudaEventRecord(s->ev[3], s->stream);
     if (s->cfg.ensemble == IMDB200_ENS_NPT_ISO) { TRY(fetch_scalars(s)); TRY(move_npt(s)); }   // virial first, see move_npt
-    else if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
+    else TRY(integrate_move(s));
     cudaEventRecord(s->ev[4], s->stream);
-    if (s->cfg.ensemble != IMDB200_ENS_NPT_ISO) TRY(fetch_scalars(s));   // one sync per step: the host decides about the rebuild
+    if (s->cfg.ensemble != IMDB200_ENS_NPT_ISO) TRY(fetch_scalars(s));
     s->disp2 = s->h_scal[SC_MAXD2];
+    TRY(step_snapshot_disp2(s, 0));
     apply_check(s);
     float ms;
     cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); s->t_ms[rebuild ? 0 : 4] += ms;

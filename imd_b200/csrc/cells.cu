@@ -760,6 +760,7 @@ int cells_rebuild(imdb200_sim *s)
   CUDA_TRY(cudaStreamSynchronize(st));
   s->nbl_len = (long long) len;
   s->disp2 = 0.0;                 // NBL_POS == ORT
+  TRY(step_snapshot_disp2(s, 1));
   s->skin_all = 0;
   s->have_valid_nbl = 1;
   s->nbl_count++;

@@ -70,8 +70,13 @@
 #else
 #define EXP_K(k) ((void) 0)
 #endif
+// branch-free block bodies (see FAST1 / FAST2 below): measured on B200 at 4 M atoms, pass 1 1.368 -> 1.330 ms,
+// pass 2 1.054 -> 1.201 ms (its body is too short to gain from overlap, the masking costs more) -- on for pass 1 only
 #ifndef IMDB_BRANCHFREE
 #define IMDB_BRANCHFREE 1
+#endif
+#ifndef IMDB_BRANCHFREE2
+#define IMDB_BRANCHFREE2 0
 #endif
 #ifndef IMDB_CUBIC
 #define IMDB_CUBIC 0
@@ -102,7 +107,9 @@ struct FArgs {
   cudaTextureObject_t tpos, tposdf;   // the same atom records as linear int4 textures (two texels per atom)
   int use_tex;                        // 0: the atom arrays exceed the 1-D linear texture limit, every gather on the LSU path
   const unsigned long long *nnbc;
-  int cls_shift;                 // NBL_CBITS * (highest skin class to walk)
+  int cls_fixed;                 // highest skin class to walk, or -1: from ctl->disp2 (skin_class_of)
+  double cls_w;                  // width of a skin class
+  const StepCtl *ctl;
   long n_own;
   int rows;                      // max_nb / L
   double *presstens; long pstride;
@@ -153,6 +160,8 @@ template <int NT, int L, bool EAM, bool MULTI, bool SHARED, bool STRESS, bool TS
 __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  STEP_GATE(a.ctl);
+  const int cls_shift = NBL_CBITS * (a.cls_fixed >= 0 ? a.cls_fixed : skin_class_of(a.ctl->disp2, a.cls_w));
   const double2 *pAB = T.pairAB, *rAB = T.rhoAB;
   const double *pC = T.pairC, *rC = T.rhoC;
   const double2 *pCD = T.pairCD, *rCD = T.rhoCD;           // cubic modes: (c2,c3)
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
       xi = a.pos[i];
       if (MULTI) it = sorte_of(xi.w);
       const long lslot = slot & ~(long) (IMDB_EXP_BCAST - 1);
-      const int nn = (int) ((a.nnbc[lslot / L] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
+      const int nn = (int) ((a.nnbc[lslot / L] >> cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (lslot >> 5) * ((size_t) a.rows * 32) + (lslot & 31);
       // Software pipeline over the list: the D entries of a block are in registers when the block starts (they
       // were loaded during the previous block), their D position gathers are issued together, the next block's
@@ -357,9 +366,11 @@ template <int NT, int L, bool MULTI, bool STRESS, bool TSMEM, bool FUSE, bool CU
 __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  STEP_GATE(a.ctl);
+  const int cls_shift = NBL_CBITS * (a.cls_fixed >= 0 ? a.cls_fixed : skin_class_of(a.ctl->disp2, a.cls_w));
   const double2 *rH = T.rhoH;
   const double *rH3 = T.rhoH3;                       // cubic modes: rho'/2 = h1 + chi*(h2 + chi*h3)
-  constexpr bool FAST2 = !MULTI && !EE && !CUB && !STRESS && TSMEM && IMDB_BRANCHFREE;
+  constexpr bool FAST2 = !MULTI && !EE && !CUB && !STRESS && TSMEM && IMDB_BRANCHFREE2;
   const unsigned s_tab = (unsigned) __cvta_generic_to_shared(smem_raw);
   const unsigned k_max = (unsigned) (T.rho.nrows - 1);
   if (TSMEM) {
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       const double dFi = MULTI ? a.dF[i] : xi.w;
       const double dMi = EE ? a.dM[i] : 0.0;
       const long lslot = slot & ~(long) (IMDB_EXP_BCAST - 1);
-      const int nn = (int) ((a.nnbc[lslot / L] >> a.cls_shift) & ((1u << NBL_CBITS) - 1));
+      const int nn = (int) ((a.nnbc[lslot / L] >> cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (lslot >> 5) * ((size_t) a.rows * 32) + (lslot & 31);
       int jq[FDEPTH2];                                    // software pipeline as in pass 1
 #pragma unroll
@@ -536,9 +547,12 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 // (replaces the MPI_Allreduce operand build-up of src/imd_forces_nbl.c:1975-1994 on one rank)
 // ----------------------------------------------------------------------------------------------------
 struct Slots { int s[8]; };
-__global__ void k_reduce_partials(const double *partial, int nblocks, int nv, double *scal, Slots slots, int accumulate_mask)
+__global__ void k_reduce_partials(const double *partial, int nblocks, int nv, double *scal, Slots slots, int accumulate_mask,
+                                  const StepCtl *ctl, int zero_maxd2)
 {
   __shared__ double sm[256];
+  STEP_GATE(ctl);
+  if (zero_maxd2 && threadIdx.x == 0) scal[SC_MAXD2] = 0.0;     // the kernel that follows accumulates the new maximum
   for (int v = 0; v < nv; v++) {
     double x = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += 256) x += partial[(size_t) b * nv + v];
@@ -550,11 +564,11 @@ __global__ void k_reduce_partials(const double *partial, int nblocks, int nv, do
   }
 }
 
-int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask)
+int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask, int zero_maxd2)
 {
   Slots sl;
   for (int i = 0; i < 8; i++) sl.s[i] = i < nvals ? slots[i] : 0;
-  k_reduce_partials<<<1, 256, 0, s->stream>>>(s->d_partial, nblocks, nvals, s->d_scal, sl, accumulate_mask);
+  k_reduce_partials<<<1, 256, 0, s->stream>>>(s->d_partial, nblocks, nvals, s->d_scal, sl, accumulate_mask, s->d_ctl, zero_maxd2);
   LAUNCH_CHECK();
   return 0;
 }
@@ -564,16 +578,12 @@ int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int 
 // ----------------------------------------------------------------------------------------------------
 // launch wrappers: pick the template instance
 // ----------------------------------------------------------------------------------------------------
-// Highest list group a force call has to walk (see NBL_CLASSES in internal.cuh).  Group q >= 1 holds pairs with
-// build distance r_b > rc + (q-1) w; |r - r_b| <= 2 dmax, so they are out of reach while 2 dmax <= (q-1) w.
-static int skin_class(const imdb200_sim *s)
+// Highest list group a force call has to walk: fixed by the host when the displacement bound is void (skin skipping
+// off, box or positions changed outside move_atoms since the build), else the kernels derive it from StepCtl::disp2
+// (skin_class_of, internal.cuh).
+static int skin_class_fixed(const imdb200_sim *s)
 {
-  if (!s->skin_skip || s->skin_all || s->disp2 < 0.0) return NBL_CLASSES;
-  if (s->disp2 == 0.0) return 0;
-  const double w = s->cfg.nbl_margin / NBL_CLASSES;
-  const double reach = 2.0 * sqrt(s->disp2) * (1.0 + 1e-9) + 1e-12;
-  const int c = (int) floor(reach / w) + 1;
-  return c < NBL_CLASSES ? c : NBL_CLASSES;
+  return (!s->skin_skip || s->skin_all) ? NBL_CLASSES : -1;
 }
 
 #if IMDB_BASE_TU
@@ -620,7 +630,7 @@ static FArgs make_args(imdb200_sim *s)
   FArgs a;
   a.tpos = s->tex_pos; a.tposdf = s->tex_posdf; a.use_tex = s->tex_ok;
   a.pos = s->pos; a.posdf = s->posdf; a.frc = s->frc; a.rho = s->rho; a.dF = s->dF; a.eam_p = s->eam_p; a.dM = s->dM; a.nbl = s->nbl; a.nnbc = s->nnbc;
-  a.cls_shift = NBL_CBITS * skin_class(s);
+  a.cls_fixed = skin_class_fixed(s); a.cls_w = s->cfg.nbl_margin / NBL_CLASSES; a.ctl = s->d_ctl;
   a.n_own = s->n_own; a.rows = s->max_nb / s->lanes;
   a.presstens = s->presstens; a.pstride = s->cap_atoms;
   a.partial = s->d_partial; a.flags = s->d_flags;
@@ -715,7 +725,9 @@ int IMPL(forces_pass1)(imdb200_sim *s)
     default: return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
   }
   const int slots[2] = {SC_EPOT, SC_VIRIAL};
-  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 2, slots, 0);
+  // fuse_step (imdb200_run): SC_MAXD2 is cleared here, in stream order before pass 2, whose fused integrator
+  // accumulates the new maximum (a kernel, not a memset, so that a gated step leaves it alone)
+  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 2, slots, 0, s->fuse_step);
 }
 
 int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
@@ -723,7 +735,6 @@ int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
   TRY(forces_textures(s));
   FArgs a = make_args(s);
   if (fuse && !forces_can_fuse_move(s)) return imdb_fail(IMDB200_ERR_ARG, "fused move_atoms is not available in this configuration");
-  if (fuse) CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
   switch (s->lanes) {
     case 1: TRY(launch2_L<1>(s, a, fuse)); break;
     case 2: TRY(launch2_L<2>(s, a, fuse)); break;
@@ -740,5 +751,6 @@ int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
     return reduce_finish(s, nb, 3, slots, 1);            // the virial adds to pass 1's, the kinetic sums replace
   }
   const int slots[1] = {SC_VIRIAL};
-  return reduce_finish(s, nb, 1, slots, 1);
+  s->maxd2_zeroed = s->zero_before_move;
+  return reduce_finish(s, nb, 1, slots, 1, s->zero_before_move);
 }

@@ -15,6 +15,7 @@ struct IArgs {
   const double *scal;
   double *partial;
   unsigned long long *maxd2;
+  const StepCtl *ctl;
 };
 
 #define IBLOCK 256
@@ -34,6 +35,7 @@ __device__ __forceinline__ double block_max(double v)
 template <bool NVT, bool STRESS, bool RESTR>
 __global__ void __launch_bounds__(IBLOCK) k_move_atoms(IArgs a)
 {
+  STEP_GATE(a.ctl);
   const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
   double red[2] = {0.0, 0.0};
   double d2 = 0.0;
@@ -80,8 +82,9 @@ __global__ void k_check_nblist(const double4 *pos, const double *nblpos, long ns
 // share of tot_kin_energy is linear in E_kin_1/2, so it is formed here and summed with the rest; eta is
 // advanced from the GLOBAL E_kin_2 and comes out identical on every rank.
 __global__ void k_nvt_finish(double *scal, const double *glob, double dt, double nactive, double temperature,
-                             double isq_tau_eta)
+                             double isq_tau_eta, const StepCtl *ctl)
 {
+  STEP_GATE(ctl);
   scal[SC_EKIN] = (scal[SC_EKIN1] + scal[SC_EKIN2]) / 4.0;
   const double e2 = glob[SC_EKIN2];
   const double ttt = nactive * temperature;
@@ -108,8 +111,12 @@ int integrate_move(imdb200_sim *s)
   a.n = s->n_own; a.dt = s->cfg.timestep;
   a.scal = s->d_scal; a.partial = s->d_partial;
   a.maxd2 = (unsigned long long *) (s->d_scal + SC_MAXD2);
+  a.ctl = s->d_ctl;
   const int nb = cdiv(s->n_own, IBLOCK);
-  CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
+  // SC_MAXD2 starts from 0: cleared by the reduction kernel behind pass 2 inside imdb200_run (zero_before_move), by a
+  // memset for the stand-alone call
+  if (!s->maxd2_zeroed) CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
+  s->maxd2_zeroed = 0;
   const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT, st = s->press_calc != 0, re = s->n_restr > 0;
 #define GO(N, S, R) k_move_atoms<N, S, R><<<nb, IBLOCK, 0, s->stream>>>(a)
   if (nvt) { if (st) { if (re) GO(true, true, true); else GO(true, true, false); }
@@ -129,7 +136,7 @@ int integrate_finish(imdb200_sim *s, int nb)
     if (nb > 0) { const int slots[2] = {SC_EKIN1, SC_EKIN2}; TRY(reduce_finish(s, nb, 2, slots, 0)); }
     TRY(comm_sync_scalars(s));    // MPI_Allreduce of E_kin_1/2 (src/imd_integrate.c:1104-1130)
     k_nvt_finish<<<1, 1, 0, s->stream>>>(s->d_scal, s->d_glob, s->cfg.timestep, (double) s->nactive,
-                                         s->cfg.temperature, s->cfg.isq_tau_eta);
+                                         s->cfg.temperature, s->cfg.isq_tau_eta, s->d_ctl);
     LAUNCH_CHECK();
   } else if (nb > 0) {
     const int slots[2] = {SC_EKIN, SC_EKIN2};

@@ -166,6 +166,15 @@ struct imdb200_sim {
   double *h_scal;      // pinned mirror of d_glob
   double *d_partial; size_t partial_bytes;   // per-block partial sums
   int *d_flags, *h_flags;
+  // device-side step control (api.cu, run_async): gate = 0 turns every kernel of a step into a no-op (a step that was
+  // queued before the host knew that the previous one invalidated the list); disp2 = max squared displacement since the
+  // list build as of the end of the previous step, from which the force kernels pick the skin classes to walk
+  struct StepCtl *d_ctl;
+  int maxd2_zeroed;                  // SC_MAXD2 was cleared by the reduction kernel behind pass 2 (zero_before_move)
+  int zero_before_move;              // imdb200_run, unfused step: ask that reduction kernel to clear it
+  int fuse_step;                     // the step being queued runs move_atoms in the tail of pass 2
+  struct StepSlot *d_slot, *h_slot;   // per-step results, ring of 3 (device + pinned mirror)
+  cudaEvent_t ev_slot[3];
   int press_calc, is_short, short_warned;
   long long nactive;   // sum of the restriction components over all atoms (3N by default)
   int nactive_dirty;   // atoms or restrictions changed: recount at the next rebuild / step
@@ -194,6 +203,9 @@ struct imdb200_sim {
 enum { SC_EPOT = 0, SC_VIRIAL, SC_EKIN, SC_EKIN2, SC_MAXD2, SC_ETA, SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX,
        SC_PXY, SC_EKIN1, SC_SHORT, SC_COUNT = 16 };   // SC_SHORT: is_short of any rank (max); slot 15 is scratch
 enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_NSEND, FL_BADTYPE, FL_CELLFULL, FL_COUNT = 8 };
+
+struct StepCtl { int gate; int pad; double disp2; };
+struct StepSlot { int executed, valid; int flags[FL_COUNT]; double scal[SC_COUNT]; };
 
 // ---- error handling --------------------------------------------------------------------------------
 int imdb_fail(int code, const char *fmt, ...);
@@ -268,7 +280,8 @@ int integrate_move(imdb200_sim *s);           // move_atoms_nve/nvt + check_nbli
 int integrate_move_npt(imdb200_sim *s);       // move_atoms_npt_iso + check_nblist fused; integrate_npt_after_fetch follows the scalar fetch
 int integrate_npt_dyn_pressure(imdb200_sim *s);   // calc_dyn_pressure into SC_EKIN2 (local share)
 int integrate_npt_after_fetch(imdb200_sim *s);
-int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask);
+int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask, int zero_maxd2 = 0);
+int step_snapshot_disp2(imdb200_sim *s, int reset);   // StepCtl::disp2 <- SC_MAXD2 of the global block (reset: 0)
 
 // ---- device helpers ------------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -331,6 +344,20 @@ __device__ __forceinline__ double4 image_pos(double4 p, int code, const Geom &g)
   if (sy) { double f = (double) sy; p.x = __dadd_rn(p.x, f * g.box[1][0]); p.y = __dadd_rn(p.y, f * g.box[1][1]); p.z = __dadd_rn(p.z, f * g.box[1][2]); }
   if (sx) { double f = (double) sx; p.x = __dadd_rn(p.x, f * g.box[0][0]); p.y = __dadd_rn(p.y, f * g.box[0][1]); p.z = __dadd_rn(p.z, f * g.box[0][2]); }
   return p;
+}
+
+// a kernel of a queued step whose list turned out invalid does nothing (StepCtl::gate)
+#define STEP_GATE(ctl) do { if ((ctl) != nullptr && (ctl)->gate == 0) return; } while (0)
+
+// Highest list group a force call has to walk (NBL_CLASSES above).  Group q >= 1 holds pairs with build distance
+// r_b > rc + (q-1) w; |r - r_b| <= 2 dmax, so they are out of reach while 2 dmax <= (q-1) w.  d2 = dmax^2 (< 0: unknown).
+__device__ __forceinline__ int skin_class_of(double d2, double w)
+{
+  if (d2 == 0.0) return 0;
+  if (!(d2 > 0.0)) return NBL_CLASSES;
+  const double reach = 2.0 * sqrt(d2) * (1.0 + 1e-9) + 1e-12;
+  const int c = (int) floor(reach / w) + 1;
+  return c < NBL_CLASSES ? c : NBL_CLASSES;
 }
 
 __device__ __forceinline__ double2 ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
