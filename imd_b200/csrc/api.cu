@@ -421,6 +421,7 @@ int imdb200_set_temperature(imdb200_sim *s, double t) { if (!s) return IMDB200_E
 static int queue_step(imdb200_sim *s, int slot, bool built)
 {
   cudaEvent_t *ev = s->ev + 5 * slot;
+  s->p2p_step = !built;                        // the exchanges of a step with a list build stay on the NCCL path
   if (!built) { cudaEventRecord(ev[0], s->stream); TRY(comm_ghost_pos(s)); }       // send_cells(copy_cell,...) (:314)
   cudaEventRecord(ev[1], s->stream);
   // single-species EAM: move_atoms + check_nblist ride in the tail of pass 2 (bit-identical, one kernel less)

@@ -82,12 +82,13 @@ int geom_make_box(imdb200_sim *s)
 // =====================================================================================================
 // per-atom array capacity
 // =====================================================================================================
-template <typename T> static int regrow(T **p, long old_n, long new_cap)
+// exported: peers may have this array mapped over CUDA IPC (comm_p2p.cu) -- the old allocation is parked, not freed
+template <typename T> static int regrow(T **p, long old_n, long new_cap, imdb200_sim *exported = nullptr)
 {
   T *q = nullptr;
   CUDA_TRY(cudaMalloc(&q, new_cap * sizeof(T)));
   if (*p && old_n > 0) CUDA_TRY(cudaMemcpy(q, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice));
-  if (*p) cudaFree(*p);
+  if (*p && !(exported && comm_p2p_defer_free(exported, *p))) cudaFree(*p);
   *p = q;
   return 0;
 }
@@ -102,10 +103,10 @@ int cells_ensure_capacity(imdb200_sim *s, long need)
   TRY(regrow(&s->mom, n, cap)); TRY(regrow(&s->mom_alt, 0, cap));
   TRY(regrow(&s->frc, n, cap)); TRY(regrow(&s->posdf, 0, cap));
   TRY(regrow(&s->nummer, n, cap)); TRY(regrow(&s->nummer_alt, 0, cap));
-  TRY(regrow(&s->rho, n, cap)); TRY(regrow(&s->dF, n, cap));
+  TRY(regrow(&s->rho, n, cap)); TRY(regrow(&s->dF, n, cap, s));
   TRY(regrow(&s->eam_p, 0, cap)); TRY(regrow(&s->dM, 0, cap));
   TRY(regrow(&s->cellid, n, cap)); TRY(regrow(&s->cellid_alt, 0, cap)); TRY(regrow(&s->perm, 0, cap));
-  TRY(regrow(&s->gsrc, 0, cap)); TRY(regrow(&s->ghost_num, 0, cap)); TRY(regrow(&s->ghost_raw, 0, cap));
+  TRY(regrow(&s->gsrc, 0, cap)); TRY(regrow(&s->ghost_num, 0, cap)); TRY(regrow(&s->ghost_raw, 0, cap, s));
   TRY(regrow(&s->posf, 0, cap));
   // SoA blocks whose stride is the capacity: contents are rebuilt before use
   if (s->nblpos) cudaFree(s->nblpos);

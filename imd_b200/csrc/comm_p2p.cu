@@ -3,9 +3,9 @@
 // with stream memory operations (cuStreamWriteValue64 / cuStreamWaitValue64), so no communication kernel competes
 // with the persistent force CTAs and no SM spins while it waits.
 //
-// STATUS: OFF by default (environment IMDB200_HALO_P2P=1 switches it on at imdb200_comm_init); written after this
-// round's GPU minutes were spent -- it compiles, it has NOT run on a GPU yet.  tests/test_multi_gpu.py holds it against
-// the same fixtures as the NCCL path in an xfail(strict=False) test of its own.
+// STATUS: off by default (environment IMDB200_HALO_P2P=1 switches it on at imdb200_comm_init, on every rank or on none:
+// the ranks agree on it).  Green on 2 B200s against the same reference fixtures as the NCCL path
+// (tests/test_multi_gpu.py::test_two_domains_peer_memory_halo, profiles/r2_pytest_mgpu_2.log).
 //
 // Replaces, for the steps between two list builds: send_cells(copy_cell, pack_cell, unpack_cell) and
 // send_cells(copy_dF, pack_dF, unpack_dF) (src/imd_comm_force_3d.c:222-396, 726-778, 1031-1060).  The step with a list
@@ -45,6 +45,7 @@ static int driver_load(void)
 struct P2PRecord {
   cudaIpcMemHandle_t h_raw, h_dF, h_flags;
   long long n_own;
+  int regrown, pad0;                   // this rank re-allocated an exported buffer since the last setup
   int recv_off[P2P_MAXRANKS];          // where rank r's slice starts in MY ghost region, -1: r sends nothing to me
   int pad[2];
 };
@@ -58,6 +59,7 @@ struct P2PPeer {
 };
 
 struct P2PState {
+  void *graveyard[16]; int n_grave;    // exported buffers that were re-allocated: freed once every peer has unmapped them
   unsigned long long *flags;           // mine
   P2PRecord *d_rec;                    // [nranks + 1]: all-gather target + my record behind it
   P2PPeer peer[26];
@@ -86,9 +88,11 @@ extern "C" int comm_p2p_enable(imdb200_sim *s)
 {
   const char *e = getenv("IMDB200_HALO_P2P");
   s->p2p_on = 0;
-  if (!e || atoi(e) == 0 || s->nranks <= 1) return 0;
-  if (s->nranks > P2P_MAXRANKS) return 0;
-  TRY(driver_load());
+  if (s->nranks <= 1) return 0;
+  // every rank must take the same path (a rank without it would skip the all-gathers of comm_p2p_setup): agree first
+  long long want = (e && atoi(e) != 0 && s->nranks <= P2P_MAXRANKS && driver_load() == 0) ? 1 : 0, all = 0;
+  TRY(comm_allgather_ll(s, want, &all));
+  if (all != s->nranks) return 0;
   P2PState *st = (P2PState *) calloc(1, sizeof(P2PState));
   if (!st) return imdb_fail(IMDB200_ERR_COMM, "out of memory");
   CUDA_TRY(cudaMalloc(&st->flags, 2 * P2P_MAXRANKS * sizeof(unsigned long long)));
@@ -99,10 +103,22 @@ extern "C" int comm_p2p_enable(imdb200_sim *s)
   return 0;
 }
 
+// cells.cu re-allocates a per-atom array that peers may have mapped (ghost_raw, dF): the old allocation must outlive
+// their mappings (freeing exported memory before the importer closes it is undefined), so it is parked here and
+// freed at the end of the next comm_p2p_setup, after every peer has re-mapped.  Returns 1 when it took the pointer.
+int comm_p2p_defer_free(imdb200_sim *s, void *ptr)
+{
+  P2PState *st = (P2PState *) s->p2p;
+  if (!s->p2p_on || !st || !ptr || st->n_grave >= 16) return 0;
+  st->graveyard[st->n_grave++] = ptr;
+  return 1;
+}
+
 void comm_p2p_free(imdb200_sim *s)
 {
   P2PState *st = (P2PState *) s->p2p;
   if (!st) return;
+  for (int i = 0; i < st->n_grave; i++) cudaFree(st->graveyard[i]);
   for (int q = 0; q < 26; q++) {
     P2PPeer &P = st->peer[q];
     if (P.raw) cudaIpcCloseMemHandle(P.raw);
@@ -139,6 +155,7 @@ int comm_p2p_setup(imdb200_sim *s, int (*allgather)(imdb200_sim *, const void *,
   CUDA_TRY(cudaIpcGetMemHandle(&mine.h_dF, s->dF));
   CUDA_TRY(cudaIpcGetMemHandle(&mine.h_flags, st->flags));
   mine.n_own = s->n_own;
+  mine.regrown = st->n_grave > 0;
   for (int r = 0; r < P2P_MAXRANKS; r++) mine.recv_off[r] = -1;
   for (int q = 0; q < s->n_peers; q++) mine.recv_off[s->peers[q].peer] = s->peers[q].recv_cnt ? s->peers[q].recv_off : -1;
   P2PRecord *d_mine = st->d_rec + s->nranks;
@@ -165,6 +182,16 @@ int comm_p2p_setup(imdb200_sim *s, int (*allgather)(imdb200_sim *, const void *,
     P.n_own = all[r].n_own;
     P.recv_off = all[r].recv_off[s->rank];
     if (s->peers[q].send_cnt && P.recv_off < 0) return imdb_fail(IMDB200_ERR_COMM, "peer %d does not expect the slice rank %d sends", r, s->rank);
+  }
+  // a rank re-allocated exported memory: once EVERY rank is past its re-mapping (a second, empty collective is the
+  // barrier) the old allocations have no importer left and can go
+  int any_regrown = 0;
+  for (int r = 0; r < s->nranks; r++) any_regrown |= all[r].regrown;
+  if (any_regrown) {
+    long long one = 1, sum = 0;
+    TRY(comm_allgather_ll(s, one, &sum));
+    for (int i = 0; i < st->n_grave; i++) cudaFree(st->graveyard[i]);
+    st->n_grave = 0;
   }
   st->ready = 1;
   return 0;

@@ -65,6 +65,20 @@
 #ifndef IMDB_EXP_BCAST
 #define IMDB_EXP_BCAST 1
 #endif
+#ifndef IMDB_EXP_SKIP
+#define IMDB_EXP_SKIP 0          // experiment: every IMDB_EXP_SKIP-th neighbour is not gathered (what a gather mask would save)
+#endif
+// list rows are requested two blocks ahead instead of one (the rows stream from HBM: ~1 us under load)
+#ifndef IMDB_PF2
+#define IMDB_PF2 0
+#endif
+// double-buffered gathers: see the comment at GATHER1
+#ifndef IMDB_DB
+#define IMDB_DB 0
+#endif
+#ifndef IMDB_EXP_NOGATHER
+#define IMDB_EXP_NOGATHER 0
+#endif
 #ifdef IMDB_EXP_KCONST
 #define EXP_K(k) ((k) = 100 + ((k) & 1))
 #else
@@ -226,15 +240,43 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
       int jq[FDEPTH];
 #pragma unroll
       for (int d = 0; d < FDEPTH; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
-      for (int m = sub; m < nn; m += FDEPTH * L, row += FDEPTH * 32) {
-        double4 xq[FDEPTH];
+#if IMDB_PF2
+      int jn[FDEPTH];                                     // the list rows of the block after the next one
 #pragma unroll
-        for (int d = 0; d < FDEPTH; d++) {
-          const int j = jq[d] >= 0 ? jq[d] : (int) i;
-          xq[d] = (d < IMDB_TEX1 && a.use_tex) ? ld_atom_tex(a.tpos, j) : ld_atom(a.pos + j);
-        }
+      for (int d = 0; d < FDEPTH; d++) jn[d] = (sub + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
+#endif
+#if IMDB_EXP_NOGATHER   // experiment: neighbour positions made up from the index, no memory access (arithmetic + table floor)
+#define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { const int j_ = jq[d]; \
+          X[d] = j_ >= 0 ? make_double4(xi.x + 1.0 + (j_ & 7) * 0.3, xi.y + ((j_ >> 3) & 7) * 0.3, xi.z + ((j_ >> 6) & 7) * 0.3, xi.w) : xi; }
+#else
+#define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { \
+          if (jq[d] >= 0) X[d] = (d < IMDB_TEX1 && a.use_tex) ? ld_atom_tex(a.tpos, jq[d]) : ld_atom(a.pos + jq[d]); else X[d] = xi; }
+#endif
+#if IMDB_DB
+      // Double buffering: the gathers of block b+1 are in flight while block b is evaluated (its own were issued one
+      // iteration earlier), so a warp overlaps the L2 round trip of its gathers with its own arithmetic.
+      double4 xq[FDEPTH];
+      GATHER1(xq)
+#pragma unroll
+      for (int d = 0; d < FDEPTH; d++) jq[d] = (sub + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
+#endif
+      for (int m = sub; m < nn; m += FDEPTH * L, row += FDEPTH * 32) {
+#if IMDB_DB
+        double4 xn[FDEPTH];
+        GATHER1(xn)
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) jq[d] = (m + (2 * FDEPTH + d) * L < nn) ? __ldcs(row + (2 * FDEPTH + d) * 32) : -1;
+#else
+        double4 xq[FDEPTH];
+        GATHER1(xq)
+#if IMDB_PF2
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) { jq[d] = jn[d]; jn[d] = (m + (2 * FDEPTH + d) * L < nn) ? __ldcs(row + (2 * FDEPTH + d) * 32) : -1; }
+#else
 #pragma unroll
         for (int d = 0; d < FDEPTH; d++) jq[d] = (m + (FDEPTH + d) * L < nn) ? __ldcs(row + (FDEPTH + d) * 32) : -1;
+#endif
+#endif
         if (FAST1) {
           // Benchmark path (single species, phi and rho on one grid, quadratic tables in shared memory): the D entries of
           // a block are evaluated WITHOUT branches -- entries beyond the list end or outside the cut-offs run through
@@ -264,8 +306,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
             vir = fma(r2, grad, vir);
             rh += rv;
           }
-          continue;
-        }
+        } else
 #pragma unroll
         for (int d = 0; d < FDEPTH; d++) {
         if (m + d * L >= nn) break;
@@ -308,7 +349,12 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
           if (EE) ph = fma(rv, rv, ph);                      // eam_p += rho_h*rho_h (:591-593)
         }
         }
+#if IMDB_DB
+#pragma unroll
+        for (int d = 0; d < FDEPTH; d++) xq[d] = xn[d];
+#endif
       }
+#undef GATHER1
     }
     if (L > 1) {
       fx = lanes_sum<L>(fx); fy = lanes_sum<L>(fy); fz = lanes_sum<L>(fz);
@@ -407,19 +453,47 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       int jq[FDEPTH2];                                    // software pipeline as in pass 1
 #pragma unroll
       for (int d = 0; d < FDEPTH2; d++) jq[d] = (sub + d * L < nn) ? __ldcs(row + d * 32) : -1;
+#if IMDB_PF2
+      int jn[FDEPTH2];
+#pragma unroll
+      for (int d = 0; d < FDEPTH2; d++) jn[d] = (sub + (FDEPTH2 + d) * L < nn) ? __ldcs(row + (FDEPTH2 + d) * 32) : -1;
+#endif
+      // the TEX share is issued first (longer latency) and consumed last (entries FDEPTH2-IMDB_TEX2 .. FDEPTH2-1)
+#if IMDB_EXP_NOGATHER
+#define GATHER2(X, JC) _Pragma("unroll") for (int d = 0; d < FDEPTH2; d++) { const int j_ = jq[d]; if (MULTI || EE) JC[d] = j_ >= 0 ? j_ : (int) i; \
+          X[d] = j_ >= 0 ? make_double4(xi.x + 1.0 + (j_ & 7) * 0.3, xi.y + ((j_ >> 3) & 7) * 0.3, xi.z + ((j_ >> 6) & 7) * 0.3, xi.w) : xi; }
+#else
+#define GATHER2(X, JC) _Pragma("unroll") for (int dd = 0; dd < FDEPTH2; dd++) { const int d = FDEPTH2 - 1 - dd; \
+          const int j = jq[d] >= 0 ? jq[d] : (int) i; if (MULTI || EE) JC[d] = j; \
+          if (jq[d] >= 0) X[d] = (d >= FDEPTH2 - IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j); \
+          else X[d] = xi; }
+#endif
+#if IMDB_DB
+      double4 xq[FDEPTH2];
+      int jc[(MULTI || EE) ? FDEPTH2 : 1];
+      GATHER2(xq, jc)
+#pragma unroll
+      for (int d = 0; d < FDEPTH2; d++) jq[d] = (sub + (FDEPTH2 + d) * L < nn) ? __ldcs(row + (FDEPTH2 + d) * 32) : -1;
+#endif
       for (int m = sub; m < nn; m += FDEPTH2 * L, row += FDEPTH2 * 32) {
+#if IMDB_DB
+        double4 xn[FDEPTH2];
+        int jcn[(MULTI || EE) ? FDEPTH2 : 1];
+        GATHER2(xn, jcn)
+#pragma unroll
+        for (int d = 0; d < FDEPTH2; d++) jq[d] = (m + (2 * FDEPTH2 + d) * L < nn) ? __ldcs(row + (2 * FDEPTH2 + d) * 32) : -1;
+#else
         double4 xq[FDEPTH2];
         int jc[(MULTI || EE) ? FDEPTH2 : 1];
+        GATHER2(xq, jc)
+#if IMDB_PF2
 #pragma unroll
-        for (int dd = 0; dd < FDEPTH2; dd++) {
-          // the TEX share is issued first (longer latency) and consumed last (entries FDEPTH2-IMDB_TEX2 .. FDEPTH2-1)
-          const int d = FDEPTH2 - 1 - dd;
-          const int j = jq[d] >= 0 ? jq[d] : (int) i;
-          xq[d] = (d >= FDEPTH2 - IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j);
-          if (MULTI || EE) jc[d] = j;
-        }
+        for (int d = 0; d < FDEPTH2; d++) { jq[d] = jn[d]; jn[d] = (m + (2 * FDEPTH2 + d) * L < nn) ? __ldcs(row + (2 * FDEPTH2 + d) * 32) : -1; }
+#else
 #pragma unroll
         for (int d = 0; d < FDEPTH2; d++) jq[d] = (m + (FDEPTH2 + d) * L < nn) ? __ldcs(row + (FDEPTH2 + d) * 32) : -1;
+#endif
+#endif
         if (FAST2) {
           // branch-free block body, see pass 1
 #pragma unroll
@@ -439,8 +513,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
             fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
             vir = fma(r2, grad, vir);
           }
-          continue;
-        }
+        } else
 #pragma unroll
         for (int d = 0; d < FDEPTH2; d++) {
         if (m + d * L >= nn) break;
@@ -496,7 +569,12 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
                       s0 = fma(dx, gx, s0); s1 = fma(dy, gy, s1); s2 = fma(dz, gz, s2);
                       s3 = fma(dy, gz, s3); s4 = fma(dz, gx, s4); s5 = fma(dx, gy, s5); }
         }
+#if IMDB_DB
+#pragma unroll
+        for (int d = 0; d < FDEPTH2; d++) { xq[d] = xn[d]; if (MULTI || EE) jc[d] = jcn[d]; }
+#endif
       }
+#undef GATHER2
     }
     if (L > 1) {
       fx = lanes_sum<L>(fx); fy = lanes_sum<L>(fy); fz = lanes_sum<L>(fz); vir = lanes_sum<L>(vir);

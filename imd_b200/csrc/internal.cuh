@@ -187,7 +187,7 @@ struct imdb200_sim {
   double t_ms[8];
   // comm
   void *nccl_comm; int rank, nranks;
-  // halo exchange over peer memory (comm_p2p.cu; off unless IMDB200_HALO_P2P=1, not yet run on a GPU)
+  // halo exchange over peer memory (comm_p2p.cu; off unless IMDB200_HALO_P2P=1)
   int p2p_on, p2p_step; void *p2p;   // p2p_step: this exchange belongs to a step without a list build
 };
 
@@ -252,6 +252,7 @@ int comm_reverse_add(imdb200_sim *s, double *field, int ncomp, long stride);  //
 int comm_sync_scalars(imdb200_sim *s);        // the MPI_Allreduce sites
 extern "C" int comm_p2p_enable(imdb200_sim *s);
 void comm_p2p_free(imdb200_sim *s);
+int comm_p2p_defer_free(imdb200_sim *s, void *ptr);   // 1: the peer-memory halo keeps ptr until its importers have unmapped it
 int comm_p2p_setup(imdb200_sim *s, int (*allgather)(imdb200_sim *, const void *, void *, size_t));
 int comm_p2p_ready(const imdb200_sim *s);
 int comm_p2p_positions(imdb200_sim *s);

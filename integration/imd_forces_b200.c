@@ -14,6 +14,14 @@
  * IMD_B200_SYNC steps (environment variable, default 1 = every step, 0 = only when a writer is due), so
  * that the unmodified writers see current data.
  *
+ * Builds with homdef / deform in the target name: IMD's lin_deform and deform_sample (src/imd_deform.c:35-119, 232-269)
+ * edit the host cells, which the device never sees.  They are not in the force-engine file, so they cannot be replaced
+ * by a second definition; the binding is linked with  -Wl,--wrap=lin_deform,--wrap=deform_sample  and the wrappers
+ * below run IMD's own routine (box, host copy) and then the device's (imdb200_lin_deform / imdb200_deform_sample).
+ * stress builds: per-atom PRESSTENS is downloaded whenever do_press_calc is set, so that calc_tot_presstens
+ * (src/imd_main_3d.c:2069-2130) and the Press_xx.. columns of the .eng file (src/imd_io.c:2474-2480) work unchanged.
+ * npt builds: ensemble npt_iso runs on the device (xi, pressure_ext, Ekin_old and the breathing box are mirrored back).
+ *
  * Build (oracle/Makefile, target _ref/imd_b200_dropin):
  *   gcc -DNVE -DNVT -DEAM2 -DNBL ... <IMD core sources> integration/imd_forces_b200.c \
  *       -Iinclude -Limd_b200 -limd_b200 -Wl,-rpath,'$ORIGIN/../../imd_b200' -lm
@@ -28,11 +36,21 @@ static void (*imd_move_atoms)(void) = NULL;   /* what the ensemble keyword selec
 static long   b200_n = 0;
 static int   *b_num = NULL, *b_sorte = NULL, *b_vsorte = NULL, *b_cell = NULL, *b_slot = NULL, *num2idx = NULL;
 static double *b_masse = NULL, *b_ort = NULL, *b_impuls = NULL, *b_kraft = NULL, *b_poteng = NULL, *b_rho = NULL;
+#ifdef STRESS_TENS
+static double *b_press = NULL;
+#endif
 static int    num_max = 0, sync_int = 1;
 
 static void b200_fatal(const char *msg) { error((char *) msg); }   /* IMD's abort convention, src/imd_misc.c:78 */
 
 static void b200_check(int rc) { if (rc) error((char *) imdb200_last_error()); }
+
+static void *b200_realloc(void *p, size_t bytes)
+{
+  void *q = realloc(p, bytes ? bytes : 1);
+  if (q == NULL) error("imd_b200: out of host memory");
+  return q;
+}
 
 /* is one of IMD's writers due at this step?  (src/imd_main_3d.c:690-694) */
 static int output_due(int step)
@@ -56,12 +74,15 @@ static void b200_upload(void)
   for (k = 0; k < NCELLS; k++) n += CELLPTR(k)->n;
   if (n != b200_n) {
     b200_n = n;
-    b_num = realloc(b_num, n * sizeof(int)); b_sorte = realloc(b_sorte, n * sizeof(int));
-    b_vsorte = realloc(b_vsorte, n * sizeof(int)); b_cell = realloc(b_cell, n * sizeof(int));
-    b_slot = realloc(b_slot, n * sizeof(int));
-    b_masse = realloc(b_masse, n * sizeof(double)); b_ort = realloc(b_ort, 3 * n * sizeof(double));
-    b_impuls = realloc(b_impuls, 3 * n * sizeof(double)); b_kraft = realloc(b_kraft, 3 * n * sizeof(double));
-    b_poteng = realloc(b_poteng, n * sizeof(double)); b_rho = realloc(b_rho, n * sizeof(double));
+    b_num = b200_realloc(b_num, n * sizeof(int)); b_sorte = b200_realloc(b_sorte, n * sizeof(int));
+    b_vsorte = b200_realloc(b_vsorte, n * sizeof(int)); b_cell = b200_realloc(b_cell, n * sizeof(int));
+    b_slot = b200_realloc(b_slot, n * sizeof(int));
+    b_masse = b200_realloc(b_masse, n * sizeof(double)); b_ort = b200_realloc(b_ort, 3 * n * sizeof(double));
+    b_impuls = b200_realloc(b_impuls, 3 * n * sizeof(double)); b_kraft = b200_realloc(b_kraft, 3 * n * sizeof(double));
+    b_poteng = b200_realloc(b_poteng, n * sizeof(double)); b_rho = b200_realloc(b_rho, n * sizeof(double));
+#ifdef STRESS_TENS
+    b_press = b200_realloc(b_press, 6 * n * sizeof(double));
+#endif
   }
   n = 0; num_max = 0;
   for (k = 0; k < NCELLS; k++) {
@@ -74,17 +95,21 @@ static void b200_upload(void)
       if (b_num[n] > num_max) num_max = b_num[n];
     }
   }
-  num2idx = realloc(num2idx, (num_max + 1) * sizeof(int));
+  num2idx = b200_realloc(num2idx, ((size_t) num_max + 1) * sizeof(int));
   for (n = 0; n < b200_n; n++) num2idx[b_num[n]] = (int) n;
   b200_check(imdb200_set_atoms(b200, b200_n, b_num, b_sorte, b_vsorte, b_masse, b_ort, b_impuls));
 }
 
 /* write device results back into IMD's cells; the device order is cell-sorted, atoms are matched by NUMMER */
-static void b200_download(int forces, int state)
+static void b200_download(int forces, int state, int press)
 {
   long n, got; 
   static int *d_num = NULL; static long d_cap = 0;
-  if (d_cap < b200_n) { d_cap = b200_n; d_num = realloc(d_num, d_cap * sizeof(int)); }
+  double *pt = NULL;
+  if (d_cap < b200_n) { d_cap = b200_n; d_num = b200_realloc(d_num, d_cap * sizeof(int)); }
+#ifdef STRESS_TENS
+  if (press) pt = b_press;
+#endif
   got = imdb200_get_atoms(b200, d_num, NULL, NULL, NULL, state ? b_ort : NULL, state ? b_impuls : NULL,
                           forces ? b_kraft : NULL, forces ? b_poteng : NULL,
 #ifdef EAM2
@@ -92,7 +117,8 @@ static void b200_download(int forces, int state)
 #else
                           NULL,
 #endif
-                          NULL, NULL, NULL);
+                          NULL, pt, NULL);
+  if (got < 0) error((char *) imdb200_last_error());
   if (got != b200_n) error("imd_b200: atom count changed on the device");
   for (n = 0; n < got; n++) {
     int a = num2idx[d_num[n]];
@@ -108,6 +134,12 @@ static void b200_download(int forces, int state)
       EAM_RHO(p,i) = b_rho[n];
 #endif
     }
+#ifdef STRESS_TENS
+    if (pt) {      /* device order: xx yy zz yz zx xy (include/imd_b200.h) */
+      PRESSTENS(p,i,xx) = pt[6*n]; PRESSTENS(p,i,yy) = pt[6*n+1]; PRESSTENS(p,i,zz) = pt[6*n+2];
+      PRESSTENS(p,i,yz) = pt[6*n+3]; PRESSTENS(p,i,zx) = pt[6*n+4]; PRESSTENS(p,i,xy) = pt[6*n+5];
+    }
+#endif
   }
 }
 
@@ -122,12 +154,41 @@ static void b200_scalars(int forces, int kinetic)
   last_nbl_len = (int) (sc.nbl_len / 2);        /* the reference counts each pair once */
 }
 
+/* the device's box -> IMD's box_x/y/z (+ make_box for tbox, volume, heights) */
+static void b200_mirror_box(void)
+{
+  double b[9];
+  b200_check(imdb200_get_box(b200, b));
+  box_x.x = b[0]; box_x.y = b[1]; box_x.z = b[2];
+  box_y.x = b[3]; box_y.y = b[4]; box_y.z = b[5];
+  box_z.x = b[6]; box_z.y = b[7]; box_z.z = b[8];
+  make_box();
+}
+
+#ifdef NPT_iso
+/* what move_atoms_npt_iso leaves in IMD's globals (src/imd_integrate.c:1509, 1691-1727) */
+static void b200_mirror_npt(void)
+{
+  double st[4];
+  b200_check(imdb200_get_npt_state(b200, st));
+  xi.x = st[0]; Ekin_old = st[1]; pressure = st[2]; pressure_ext.x = st[3];
+  b200_mirror_box();
+}
+#endif
+
 /* (*move_atoms)() = move_atoms_nve / move_atoms_nvt (src/imd_integrate.c:32, 891) */
 static void b200_move_atoms(void)
 {
+  int press = 0;
   b200_check(imdb200_move_atoms(b200));
   b200_scalars(0, 1);
-  if (sync_due(steps)) b200_download(0, 1);      /* writers run after move_atoms of the same step (src/imd_main_3d.c:690-694) */
+#ifdef NPT_iso
+  if (ensemble == ENS_NPT_ISO) b200_mirror_npt();
+#endif
+#ifdef STRESS_TENS
+  press = do_press_calc;                         /* kinetic part added by move_atoms: the tensor is complete now */
+#endif
+  if (sync_due(steps) || press) b200_download(0, sync_due(steps), press);   /* writers run after move_atoms of the same step (src/imd_main_3d.c:690-694) */
 }
 
 static void b200_init(void)
@@ -144,7 +205,15 @@ static void b200_init(void)
   cfg.pbc_dirs[0] = pbc_dirs.x; cfg.pbc_dirs[1] = pbc_dirs.y; cfg.pbc_dirs[2] = pbc_dirs.z;
   cfg.nbl_margin = nbl_margin; cfg.nbl_size = nbl_size; cfg.timestep = timestep;
   cfg.ensemble = (ensemble == ENS_NVT) ? IMDB200_ENS_NVT : IMDB200_ENS_NVE;
-  if (ensemble != ENS_NVE && ensemble != ENS_NVT) error("imd_b200 supports ensemble nve and nvt");
+#ifdef NPT_iso
+  if (ensemble == ENS_NPT_ISO) {                 /* src/imd_integrate.c:1493-1496, 1720-1727 */
+    if (use_curr_pressure) error("imd_b200: use_curr_pressure is not supported with ensemble npt_iso");
+    cfg.ensemble = IMDB200_ENS_NPT_ISO;
+    cfg.xi = xi.x; cfg.isq_tau_xi = isq_tau_xi; cfg.pressure_ext = pressure_ext.x;
+    cfg.d_pressure = (pressure_end.x - pressure_ext.x) / (steps_max - steps_min);
+  } else
+#endif
+  if (ensemble != ENS_NVE && ensemble != ENS_NVT) error("imd_b200 supports the ensembles nve, nvt and npt_iso");
   cfg.temperature = temperature; cfg.eta = eta; cfg.isq_tau_eta = isq_tau_eta;
   /* `4point` / `spline` make targets (src/Makefile:1694-1701, src/potaccess.h:24-36) */
 #if defined(FOURPOINT)
@@ -160,7 +229,7 @@ static void b200_init(void)
 #ifdef EEAM   /* `eeam` make targets: energy modification term M(p), src/imd_potential.c:82-85 */
   b200_check(imdb200_set_eeam_table(b200, (imdb200_pot_table *) &emod_pot));
 #endif
-#ifdef ADP    /* `adp` make targets: u(r), w(r), src/imd_potential.c:87-92 (device side not yet run on a GPU) */
+#ifdef ADP    /* `adp` make targets: u(r), w(r), src/imd_potential.c:87-92 */
   b200_check(imdb200_set_adp_tables(b200, (imdb200_pot_table *) &adp_upot, (imdb200_pot_table *) &adp_wpot));
 #endif
 #else
@@ -182,11 +251,39 @@ void calc_forces(int steps)
 #ifdef NVT
   if (ensemble == ENS_NVT) b200_check(imdb200_set_temperature(b200, temperature));   /* increment_temperature() */
 #endif
+#ifdef STRESS_TENS
+  b200_check(imdb200_set_press_calc(b200, do_press_calc));   /* src/imd_main_3d.c:184-190 */
+#endif
   b200_check(imdb200_calc_forces(b200, steps));
   b200_scalars(1, 0);
   nfc++;
-  if (sync_due(steps)) b200_download(1, 0);
+  if (sync_due(steps)) b200_download(1, 0, 0);
 }
+
+#ifdef HOMDEF
+/* void lin_deform(vektor dx, vektor dy, vektor dz, real scale)  (src/imd_deform.c:35-119), linked with --wrap */
+void __real_lin_deform(vektor dx, vektor dy, vektor dz, real scale);
+void __wrap_lin_deform(vektor dx, vektor dy, vektor dz, real scale)
+{
+  double ax[3], ay[3], az[3];
+  if (b200 == NULL) { __real_lin_deform(dx, dy, dz, scale); return; }    /* before the first calc_forces: host state only */
+  ax[0] = dx.x; ax[1] = dx.y; ax[2] = dx.z; ay[0] = dy.x; ay[1] = dy.y; ay[2] = dy.z; az[0] = dz.x; az[1] = dz.y; az[2] = dz.z;
+  b200_check(imdb200_lin_deform(b200, ax, ay, az, scale));
+  b200_mirror_box();                                                     /* IMD's box follows the device's, bit for bit */
+  b200_scalars(0, 0);
+}
+#endif
+
+#ifdef DEFORM
+/* void deform_sample(void)  (src/imd_deform.c:232-269), linked with --wrap; main_loop calls check_nblist right after it */
+void __real_deform_sample(void);
+void __wrap_deform_sample(void)
+{
+  if (b200 == NULL) { __real_deform_sample(); return; }
+  b200_check(imdb200_deform_sample(b200, deform_size, (double *) deform_shift, shear_def, (double *) deform_shear,
+                                   (double *) deform_base));
+}
+#endif
 
 /* void check_nblist(void)  (src/imd_forces_nbl.c:2007-2037) */
 void check_nblist(void)

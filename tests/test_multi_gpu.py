@@ -42,13 +42,17 @@ def test_two_domains_deformation_and_restrictions(built_lib, name):
     _run("fixture:" + name, (2, 1, 1), 29619)
 
 
-@pytest.mark.xfail(strict=False, reason="the peer-memory halo (comm_p2p.cu, IMDB200_HALO_P2P=1) was written after this "
-                                         "round's GPU budget was spent and has not run on a GPU yet")
 @pytest.mark.parametrize("name", ["cu_long", "nial_nvt"])
 def test_two_domains_peer_memory_halo(built_lib, name):
     """The same fixtures with the halo exchanged by direct stores into the neighbour's ghost region and stream memory
     operations instead of NCCL messages; separate processes anyway (torchrun)."""
     _run("fixture:" + name, (2, 1, 1), 29620, env={"IMDB200_HALO_P2P": "1"})
+
+
+def test_peer_memory_halo_in_the_device_resident_loop(built_lib):
+    """imdb200_run with the peer-memory halo: hot crystal, atoms migrate, buffers are re-planned at every rebuild; the
+    trajectory must equal the single-GPU one (the same check as test_atoms_migrate_between_domains)."""
+    _run("migration", (2, 1, 1), 29625, env={"IMDB200_HALO_P2P": "1"})
 
 
 @pytest.mark.parametrize("name", ["cu_big", "nial_big"])
