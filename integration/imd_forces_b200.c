@@ -60,6 +60,9 @@ static int output_due(int step)
 #ifdef FORCE
   if (force_int > 0 && step % force_int == 0) return 1;
 #endif
+#ifdef FNORM   /* deform / relaxation builds print sqrt(fnorm/nactive) and sqrt(f_max2) in every .eng line (src/imd_io.c:2413-2414) */
+  if (eng_int > 0 && step % eng_int == 0) return 1;
+#endif
   if (dist_int > 0 && step % dist_int == 0) return 1;
   if (pic_int > 0 && step % pic_int == 0) return 1;
   return 0;
@@ -180,6 +183,23 @@ static void b200_mirror_npt(void)
 static void b200_move_atoms(void)
 {
   int press = 0;
+#ifdef FNORM
+  /* fnorm = sum F^2 and f_max2 = largest squared force component, of the restricted forces, as move_atoms_nve/nvt form
+     them (src/imd_integrate.c:192-205, 1005-1013); from the forces calc_forces has just written into the cells */
+  if (sync_due(steps)) {
+    int k, i; real f2 = 0.0, m2 = 0.0;
+    for (k = 0; k < NCELLS; k++) {
+      cell *p = CELLPTR(k);
+      for (i = 0; i < p->n; i++) {
+        vektor *r = restrictions + VSORTE(p,i);
+        real fx = KRAFT(p,i,X) * r->x, fy = KRAFT(p,i,Y) * r->y, fz = KRAFT(p,i,Z) * r->z;
+        f2 += fx * fx + fy * fy + fz * fz;
+        m2 = MAX(m2, MAX(fx * fx, MAX(fy * fy, fz * fz)));
+      }
+    }
+    fnorm = f2; f_max2 = m2;
+  }
+#endif
   b200_check(imdb200_move_atoms(b200));
   b200_scalars(0, 1);
 #ifdef NPT_iso
@@ -257,7 +277,9 @@ void calc_forces(int steps)
   b200_check(imdb200_calc_forces(b200, steps));
   b200_scalars(1, 0);
   nfc++;
-  if (sync_due(steps)) b200_download(1, 0, 0);
+  /* positions too: lin_deform / deform_sample of this step moved them on the device after the last download, and the
+     .force dump is written between calc_forces and move_atoms (src/imd_main_3d.c:426-431) */
+  if (sync_due(steps)) b200_download(1, 1, 0);
 }
 
 #ifdef HOMDEF

@@ -65,3 +65,100 @@ def test_imd_main_with_b200_engine_matches_serial_imd(built_lib, tmp_path, ensem
     assert np.max(np.abs(d)) < 1e-8                      # positions
     assert np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-7  # velocities
     assert np.max(np.abs(cg[:, 9] - cc[:, 9])) < 1e-8      # per-atom Epot
+
+
+FULL = ("imd_b200_dropin_full", "imd_ref_serial_full")
+
+
+def _pair_run(tmp, tabs, *, exes=FULL, ncell=(10, 10, 10), restart=None, **kw):
+    outs = {}
+    for name, exe in zip(("gpu", "cpu"), exes):
+        assert os.path.exists(os.path.join(REF, exe)), f"oracle/_ref/{exe} missing: run `make -C oracle ref` where /root/reference exists"
+        p = synth.cu_param(tmp, ncell=ncell, name=name, tables=tabs, **kw)
+        if restart is None:
+            outs[name] = _run(exe, p, tmp)
+        else:
+            r = subprocess.run([os.path.join(REF, exe), "-p", p, "-r", str(restart)], capture_output=True, text=True, cwd=tmp,
+                               timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            outs[name] = r.stdout
+    return outs
+
+
+def _force_file(path):
+    rows = np.loadtxt(path, comments="#")            # type x y z fx fy fz, written BEFORE the move (src/imd_io.c:1927-1950)
+    o = np.lexsort((rows[:, 3], rows[:, 2], rows[:, 1]))
+    return rows[o]
+
+
+def test_full_binding_homdef_stress_force_dump(built_lib, tmp_path):
+    """IMD built with homdef + stress + force around the engine: lin_deform reaches the device through --wrap
+    (src/imd_main_3d.c:293-299 -> imdb200_lin_deform), the box columns and Press_xx..Press_xy of the .eng file
+    (src/imd_io.c:2474-2480, calc_tot_presstens on the downloaded per-atom tensor) and the .force dump
+    (src/imd_io.c:1886-1950) come out of IMD's own writers and match the unmodified serial IMD."""
+    tmp = str(tmp_path)
+    tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+    extra = dict(eng_int=1, checkpt_int=24, force_int=12, lindef_interval=4, lindef_size=2.0e-3,
+                 lindef_x=[1.0, 0.2, 0.0], lindef_y=[0.0, -0.4, 0.0], lindef_z=[0.3, 0.0, 0.2])
+    _pair_run(tmp, tabs, ensemble="nve", maxsteps=24, starttemp=0.08, extra=extra)
+    eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
+    assert eg.shape == ec.shape and len(eg) == 25 and eg.shape[1] >= 11
+    # columns: time Epot T fnorm fmax pressure volume eta box_x.x box_y.y box_z.z box_y.x box_x.z Press_xx yy zz yz xz xy
+    assert eg.shape[1] == 19
+    for col in range(1, eg.shape[1]):
+        scale = max(np.max(np.abs(ec[:, col])), 1e-300)
+        tol = 2e-6 if col in (5, 6) else 1e-8            # pressure and volume are printed with %e only
+        assert np.max(np.abs(eg[:, col] - ec[:, col])) <= tol * scale, (col, eg[:3, col], ec[:3, col])
+    # box columns moved (the deformation really happened), forces and stress columns are not empty
+    assert np.ptp(ec[:, 8]) > 0 and np.max(np.abs(ec[:, -6:])) > 0 and np.min(ec[1:, 3]) > 0
+    fscale = max(np.max(np.abs(_force_file(os.path.join(tmp, f"cpu.{k:05d}.force"))[:, 4:7])) for k in (1, 2))
+    assert fscale > 0.1
+    for k in (0, 1, 2):                                # dump 0 is the perfect lattice: forces are rounding noise there
+        fg, fc = _force_file(os.path.join(tmp, f"gpu.{k:05d}.force")), _force_file(os.path.join(tmp, f"cpu.{k:05d}.force"))
+        assert fg.shape == fc.shape
+        tol = 1e-10 if k == 0 else 1e-7
+        assert np.max(np.abs(fg[:, 1:4] - fc[:, 1:4])) <= tol * 40.0
+        assert np.max(np.abs(fg[:, 4:7] - fc[:, 4:7])) <= tol * fscale
+
+
+def test_full_binding_npt_iso(built_lib, tmp_path):
+    """ensemble npt_iso through the binding: xi, the external pressure ramp and the breathing box live on the device and
+    are mirrored into IMD's globals after every move_atoms (src/imd_integrate.c:1472-1729)."""
+    tmp = str(tmp_path)
+    tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+    extra = dict(eng_int=1, checkpt_int=30, endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.5, pressure_start=0.02, pressure_end=0.03)
+    _pair_run(tmp, tabs, ensemble="npt_iso", maxsteps=30, starttemp=0.08, extra=extra)
+    eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
+    assert eg.shape == ec.shape and len(eg) == 31
+    # columns: time Epot T fnorm fmax pressure volume eta box_x.x box_y.y box_z.z Press_xx .. Press_xy
+    assert eg.shape[1] == 17 and np.ptp(ec[:, 8]) > 0   # the box breathes
+    for col in list(range(1, 5)) + list(range(8, 17)):
+        assert np.max(np.abs(eg[:, col] - ec[:, col])) <= 1e-8 * np.max(np.abs(ec[:, col])), col
+    for col in (5, 6, 7):                                 # pressure, volume, eta*tau_eta are printed with %e only
+        assert np.max(np.abs(eg[:, col] - ec[:, col])) <= 2e-6 * np.max(np.abs(ec[:, col])), col
+    cg, cc = _chkpt(os.path.join(tmp, "gpu.00001.chkpt")), _chkpt(os.path.join(tmp, "cpu.00001.chkpt"))
+    assert cg.shape == cc.shape and np.array_equal(cg[:, 0], cc[:, 0])
+    assert np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-7
+
+
+def test_restart_from_checkpoint(built_lib, tmp_path):
+    """Restart `-r 1` (src/imd_param.c:3829-3872, .itr + checkpoint readers src/imd_io_3d.c:949-1086): 15 steps, checkpoint 1,
+    then both binaries continue from THEIR OWN checkpoint for 15 more steps; the engine is fed by IMD's own reader."""
+    tmp = str(tmp_path)
+    tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+    extra = dict(eng_int=1, checkpt_int=15)
+    _pair_run(tmp, tabs, exes=("imd_b200_dropin", "imd_ref_serial_eam"), ensemble="nvt", maxsteps=15, starttemp=0.08, extra=extra)
+    for n in ("gpu", "cpu"):
+        assert os.path.exists(os.path.join(tmp, f"{n}.00001.chkpt")) and os.path.exists(os.path.join(tmp, f"{n}.00001.itr"))
+    _pair_run(tmp, tabs, exes=("imd_b200_dropin", "imd_ref_serial_eam"), restart=1, ensemble="nvt", maxsteps=30, starttemp=0.08,
+              extra=extra)
+    eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
+    assert eg.shape == ec.shape and len(eg) >= 30 and eg[-1, 0] > 0.029
+    assert np.max(np.abs(eg[:, 1] - ec[:, 1]) / np.abs(ec[:, 1])) <= 1e-8
+    assert np.max(np.abs(eg[:, 2] - ec[:, 2]) / np.abs(ec[:, 2])) <= 1e-8
+    cg, cc = _chkpt(os.path.join(tmp, "gpu.00002.chkpt")), _chkpt(os.path.join(tmp, "cpu.00002.chkpt"))
+    assert cg.shape == cc.shape and np.array_equal(cg[:, 0], cc[:, 0])
+    box = 10 * synth.CU_A0
+    d = cg[:, 3:6] - cc[:, 3:6]
+    d -= box * np.round(d / box)
+    assert np.max(np.abs(d)) < 1e-7 and np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-6
