@@ -56,7 +56,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state", "imdb200_set_adp_tables", "imdb200_get_adp",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state", "imdb200_set_adp_tables", "imdb200_get_adp", "imdb200_device_count", "imdb200_set_berendsen",
 ]
 
 _lib = None
@@ -89,6 +89,7 @@ def load_library():
     L.imdb200_set_skin_skip.argtypes = [vp, C.c_int]
     L.imdb200_set_eta.argtypes = [vp, C.c_double]
     L.imdb200_set_temperature.argtypes = [vp, C.c_double]
+    L.imdb200_set_berendsen.argtypes = [vp, C.c_double, C.c_double]
     L.imdb200_lin_deform.argtypes = [vp, vp, vp, vp, C.c_double]
     L.imdb200_deform_sample.argtypes = [vp, C.c_double, vp, vp, vp, vp]
     L.imdb200_get_scalars.argtypes = [vp, C.POINTER(Scalars)]
@@ -321,6 +322,10 @@ class IMDB200:
     def set_skin_skip(self, on=True):
         """on=False: walk every stored list entry like the reference (test hook; results are bit-identical)."""
         _chk(self.L.imdb200_set_skin_skip(self.h, int(on)))
+
+    def set_berendsen(self, tauber, tot_kin_energy=0.0):
+        """Berendsen variant of NVE (`ber` builds): tau_berendsen and the kinetic energy of the previous step."""
+        _chk(self.L.imdb200_set_berendsen(self.h, float(tauber), float(tot_kin_energy)))
 
     def set_eta(self, eta):
         _chk(self.L.imdb200_set_eta(self.h, float(eta)))

@@ -42,6 +42,7 @@ void imdb200_destroy(imdb200_sim *s);
 const char *imdb200_last_error(void) { return g_err; }
 void imdb200_set_error_handler(void (*h)(const char *)) { g_handler = h; }
 long long imdb200_kernel_launches(void) { return g_kernel_launches; }
+int imdb200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 
 void imdb200_default_config(imdb200_config *c)
 {
@@ -412,6 +413,22 @@ int imdb200_set_eta(imdb200_sim *s, double eta)
   CUDA_TRY(cudaSetDevice(s->cfg.device));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &eta, sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+int imdb200_set_berendsen(imdb200_sim *s, double tauber, double tot_kin_energy)
+{
+  if (!s) return IMDB200_ERR_ARG;
+  if (s->cfg.ensemble != IMDB200_ENS_NVE && tauber > 0.0) return imdb_fail(IMDB200_ERR_ARG, "the Berendsen variant belongs to ensemble nve");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->tauber = tauber;
+  s->h_scal[SC_EKIN] = tot_kin_energy;
+  // the kinetic energy the previous move_atoms left, as every rank sees it (the GLOBAL value enters the scale factor)
+  CUDA_TRY(cudaMemcpy(s->d_glob + SC_EKIN, &tot_kin_energy, sizeof(double), cudaMemcpyHostToDevice));
+  if (s->d_glob != s->d_scal) {
+    const double mine = s->rank == 0 ? tot_kin_energy : 0.0;      // the local blocks are summed over the ranks
+    CUDA_TRY(cudaMemcpy(s->d_scal + SC_EKIN, &mine, sizeof(double), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 int imdb200_set_temperature(imdb200_sim *s, double t) { if (!s) return IMDB200_ERR_ARG; s->cfg.temperature = t; return 0; }

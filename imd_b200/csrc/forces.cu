@@ -135,6 +135,7 @@ struct FArgs {
   const double *scal;
   unsigned long long *maxd2;
   double dt; int nvt;
+  const double *glob; double nactive, temperature, tauber;   // Berendsen variant of NVE (integrate_atom)
 };
 
 __device__ __forceinline__ double4 ld_atom_tex(cudaTextureObject_t t, int j)
@@ -435,6 +436,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   const long s_end = min(total, (long) (blockIdx.x + 1) * per);
   double red[3] = {0.0, 0.0, 0.0};                  // virial, and with FUSE the two kinetic-energy sums
   double d2max = 0.0;
+  // FUSE: SC_EKIN still holds the previous step's kinetic energy here (this step's is written by the reduction behind us)
+  const double ber_cc = FUSE ? berendsen_cc(a.glob[SC_EKIN], a.nactive, a.temperature, a.dt, a.tauber) : 1.0;
   int is_short = 0;
   for (long slot = (long) blockIdx.x * per + threadIdx.x; slot < s_end; slot += NT) {
     const long i = slot / L;
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
         double rk[2];
         const double nx = a.nblpos[i], ny = a.nblpos[a.nstride + i], nz = a.nblpos[2 * a.nstride + i];
         const double d2 = a.nvt ? integrate_atom<true>(x, p, f, a.dt, a.scal[SC_ETA], 1.0, 1.0, 1.0, nx, ny, nz, rk)
-                                : integrate_atom<false>(x, p, f, a.dt, 0.0, 1.0, 1.0, 1.0, nx, ny, nz, rk);
+                                : integrate_atom<false>(x, p, f, a.dt, 0.0, 1.0, 1.0, 1.0, nx, ny, nz, rk, ber_cc);
         a.mom[i] = p;
         double *xw = reinterpret_cast<double *>(a.pos_rw + i);   // .w (the types) stays as it is
         *reinterpret_cast<double2 *>(xw) = make_double2(x.x, x.y);
@@ -715,6 +718,7 @@ static FArgs make_args(imdb200_sim *s)
   a.pos_rw = s->pos; a.mom = s->mom; a.nblpos = s->nblpos; a.nstride = s->cap_atoms; a.scal = s->d_scal;
   a.maxd2 = (unsigned long long *) (s->d_scal + SC_MAXD2);
   a.dt = s->cfg.timestep; a.nvt = s->cfg.ensemble == IMDB200_ENS_NVT;
+  a.glob = s->d_glob; a.nactive = (double) s->nactive; a.temperature = s->cfg.temperature; a.tauber = s->tauber;
   return a;
 }
 

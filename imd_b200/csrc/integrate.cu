@@ -16,6 +16,7 @@ struct IArgs {
   double *partial;
   unsigned long long *maxd2;
   const StepCtl *ctl;
+  const double *glob; double nactive, temperature, tauber;   // Berendsen: previous tot_kin_energy (global), target
 };
 
 #define IBLOCK 256
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(IBLOCK) k_move_atoms(IArgs a)
   const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
   double red[2] = {0.0, 0.0};
   double d2 = 0.0;
+  const double cc = NVT ? 1.0 : berendsen_cc(a.glob[SC_EKIN], a.nactive, a.temperature, a.dt, a.tauber);
   if (i < a.n) {
     double4 x = a.pos[i], p = a.mom[i], f = a.frc[i];
     const double m = p.w, dt = a.dt;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(IBLOCK) k_move_atoms(IArgs a)
     }
     const double eta = NVT ? a.scal[SC_ETA] : 0.0;
     const double nx = a.nblpos[i], ny = a.nblpos[a.nstride + i], nz = a.nblpos[2 * a.nstride + i];
-    d2 = integrate_atom<NVT>(x, p, f, dt, eta, rx, ry, rz, nx, ny, nz, red);
+    d2 = integrate_atom<NVT>(x, p, f, dt, eta, rx, ry, rz, nx, ny, nz, red, cc);
     a.mom[i] = p;
     a.pos[i] = x;
     if (STRESS) {                                                      // :410-433
@@ -112,6 +114,7 @@ int integrate_move(imdb200_sim *s)
   a.scal = s->d_scal; a.partial = s->d_partial;
   a.maxd2 = (unsigned long long *) (s->d_scal + SC_MAXD2);
   a.ctl = s->d_ctl;
+  a.glob = s->d_glob; a.nactive = (double) s->nactive; a.temperature = s->cfg.temperature; a.tauber = s->tauber;
   const int nb = cdiv(s->n_own, IBLOCK);
   // SC_MAXD2 starts from 0: cleared by the reduction kernel behind pass 2 inside imdb200_run (zero_before_move), by a
   // memset for the stand-alone call

@@ -182,6 +182,7 @@ struct imdb200_sim {
   // the pressure the last step used
   double npt_xi, npt_ekin_old, npt_pressure_ext, npt_pressure;
   double eta;
+  double tauber;       // > 0: Berendsen variant of NVE (imdb200_set_berendsen)
   // timers
   cudaEvent_t ev[16];
   double t_ms[8];
@@ -382,10 +383,21 @@ __device__ __forceinline__ double warp_sum(double v)
 // check_nblist (src/imd_forces_nbl.c:2007-2037).  Shared by k_move_atoms and by the fused tail of k_pass2 so that
 // imdb200_run and the separate calls produce bit-identical trajectories.  f is the (restricted) force, rx..rz the
 // restriction vector of the atom's virtual type, red[0..1] the kinetic-energy partial sums, returns |x - nbl_pos|^2.
+// Berendsen variant of NVE (`ber` builds, src/imd_integrate.c:44-53): scale factor of the momenta from the kinetic
+// energy the PREVIOUS move_atoms left; tauber <= 0: plain NVE (factor 1).
+__host__ __device__ inline double berendsen_cc(double tot_kin_energy, double nactive, double temperature, double dt, double tauber)
+{
+  if (!(tauber > 0.0)) return 1.0;
+  const double kb = 8.6174101569719990e-06;
+  double cc = 1. - dt / tauber * ((2.0 * tot_kin_energy / nactive + kb) / (temperature + kb) - 1.);
+  if (cc < 0.5) cc = 0.5; else if (cc > 2.0) cc = 2.0;
+  return sqrt(cc);
+}
+
 template <bool NVT>
 __device__ __forceinline__ double integrate_atom(double4 &x, double4 &p, const double4 &f, double dt, double eta,
                                                  double rx, double ry, double rz, double nx, double ny, double nz,
-                                                 double (&red)[2])
+                                                 double (&red)[2], double cc = 1.0)
 {
   const double m = p.w;
   if (!NVT) {
@@ -394,6 +406,7 @@ __device__ __forceinline__ double integrate_atom(double4 &x, double4 &p, const d
     const double k2 = p.x * p.x + p.y * p.y + p.z * p.z;
     red[0] = (k1 + k2) / (4 * m);                                   // :329-335
     red[1] = 0.0;
+    p.x *= cc; p.y *= cc; p.z *= cc;                                // BER :341-350 (after the energy, before the move)
   } else {
     const double reibung = 1.0 - eta * dt / 2.0;                    // :907
     const double eins_d_reib = 1.0 / (1.0 + eta * dt / 2.0);        // :908

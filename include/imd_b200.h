@@ -92,6 +92,8 @@ const char *imdb200_last_error(void);
 void        imdb200_set_error_handler(void (*handler)(const char *msg));
 /* number of kernels this library has launched in this process (bench.py: gpu_launches) */
 long long   imdb200_kernel_launches(void);
+/* number of sm_100 devices this process sees (MPI builds: device = rank % count; no reference counterpart) */
+int         imdb200_device_count(void);
 
 /* ---- setup ------------------------------------------------------------------------------ */
 /* replaces: globals filled by read_parameters() + make_box() + init_cells()
@@ -174,6 +176,11 @@ int  imdb200_invalidate_nblist(imdb200_sim *sim);         /* have_valid_nbl = 0 
 int  imdb200_set_skin_skip(imdb200_sim *sim, int on);
 int  imdb200_set_eta(imdb200_sim *sim, double eta);
 int  imdb200_set_temperature(imdb200_sim *sim, double temperature);
+/* replaces: the BER branch of move_atoms_nve in `ber` builds (src/imd_integrate.c:44-53, 341-350) and the parameter
+   tau_berendsen (global tauber).  tauber > 0 switches the Berendsen scaling of the momenta on (ensemble nve; the target is
+   imdb200_set_temperature's); tot_kin_energy is what the previous move_atoms left (IMD's global of that name), it drives
+   the first scale factor.  tauber <= 0 switches it off. */
+int  imdb200_set_berendsen(imdb200_sim *sim, double tauber, double tot_kin_energy);
 
 /* replaces: lin_deform(dx,dy,dz,scale) (src/imd_deform.c:35-119) incl. make_box() */
 int  imdb200_lin_deform(imdb200_sim *sim, const double dx[3], const double dy[3],

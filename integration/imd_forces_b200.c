@@ -22,6 +22,12 @@
  * (src/imd_main_3d.c:2069-2130) and the Press_xx.. columns of the .eng file (src/imd_io.c:2474-2480) work unchanged.
  * npt builds: ensemble npt_iso runs on the device (xi, pressure_ext, Ekin_old and the breathing box are mirrored back).
  *
+ * MPI builds (imd_mpi_*, one rank per GPU): cpu_dim / my_coord are IMD's own (setup_mpi_topology,
+ * src/imd_geom_mpi_3d.c:32-90), rank 0 creates the ncclUniqueId and MPI_Bcast carries it, every rank uploads the atoms
+ * IMD distributed to it.  Halo exchange, atom migration and the reductions then run inside the library; because atoms
+ * change ranks there, the host cells are refilled from what the device reports at every download (b200_rebin) instead
+ * of being matched by NUMMER.
+ *
  * Build (oracle/Makefile, target _ref/imd_b200_dropin):
  *   gcc -DNVE -DNVT -DEAM2 -DNBL ... <IMD core sources> integration/imd_forces_b200.c \
  *       -Iinclude -Limd_b200 -limd_b200 -Wl,-rpath,'$ORIGIN/../../imd_b200' -lm
@@ -103,12 +109,68 @@ static void b200_upload(void)
   b200_check(imdb200_set_atoms(b200, b200_n, b_num, b_sorte, b_vsorte, b_masse, b_ort, b_impuls));
 }
 
+#ifdef MPI
+/* MPI builds: atoms migrate between GPUs inside the library, so the set of atoms of this rank changes.  The host cells
+   are emptied and refilled from the device's arrays; every atom goes into the cell IMD's own cell_coord /
+   local_cell_coord (src/imd_geom_3d.c:1054-1074, src/imd_geom_mpi_3d.c:119-128) assign it, clamped into the real cells
+   (positions are only wrapped at list builds, an atom may sit a skin's width outside its domain). */
+static int *r_num = NULL, *r_sorte = NULL, *r_vsorte = NULL;
+static double *r_masse = NULL, *r_ort = NULL, *r_impuls = NULL, *r_kraft = NULL, *r_poteng = NULL, *r_rho = NULL, *r_press = NULL;
+static long r_cap = 0;
+
+static void b200_rebin(int press)
+{
+  long n = imdb200_natoms_local(b200), a, got; int k;
+  if (n > r_cap) {
+    r_cap = n + n / 8 + 64;
+    r_num = b200_realloc(r_num, r_cap * sizeof(int)); r_sorte = b200_realloc(r_sorte, r_cap * sizeof(int));
+    r_vsorte = b200_realloc(r_vsorte, r_cap * sizeof(int)); r_masse = b200_realloc(r_masse, r_cap * sizeof(double));
+    r_ort = b200_realloc(r_ort, 3 * r_cap * sizeof(double)); r_impuls = b200_realloc(r_impuls, 3 * r_cap * sizeof(double));
+    r_kraft = b200_realloc(r_kraft, 3 * r_cap * sizeof(double)); r_poteng = b200_realloc(r_poteng, r_cap * sizeof(double));
+    r_rho = b200_realloc(r_rho, r_cap * sizeof(double)); r_press = b200_realloc(r_press, 6 * r_cap * sizeof(double));
+  }
+  got = imdb200_get_atoms(b200, r_num, r_sorte, r_vsorte, r_masse, r_ort, r_impuls, r_kraft, r_poteng, r_rho, NULL,
+                          press ? r_press : NULL, NULL);
+  if (got != n) error(got < 0 ? (char *) imdb200_last_error() : "imd_b200: atom count changed during the download");
+  for (k = 0; k < nallcells; k++) (cell_array + k)->n = 0;
+  for (a = 0; a < n; a++) {
+    ivektor c = local_cell_coord(cell_coord(r_ort[3*a], r_ort[3*a+1], r_ort[3*a+2]));
+    cell *p; int i;
+    c.x = c.x < 1 ? 1 : (c.x > cell_dim.x - 2 ? cell_dim.x - 2 : c.x);
+    c.y = c.y < 1 ? 1 : (c.y > cell_dim.y - 2 ? cell_dim.y - 2 : c.y);
+    c.z = c.z < 1 ? 1 : (c.z > cell_dim.z - 2 ? cell_dim.z - 2 : c.z);
+    p = PTR_VV(cell_array, c, cell_dim);
+    if (p->n >= p->n_max) alloc_cell(p, p->n_max + incrsz);
+    i = p->n++;
+    NUMMER(p,i) = r_num[a]; SORTE(p,i) = r_sorte[a]; VSORTE(p,i) = r_vsorte[a]; MASSE(p,i) = r_masse[a];
+    ORT(p,i,X) = r_ort[3*a]; ORT(p,i,Y) = r_ort[3*a+1]; ORT(p,i,Z) = r_ort[3*a+2];
+    IMPULS(p,i,X) = r_impuls[3*a]; IMPULS(p,i,Y) = r_impuls[3*a+1]; IMPULS(p,i,Z) = r_impuls[3*a+2];
+    KRAFT(p,i,X) = r_kraft[3*a]; KRAFT(p,i,Y) = r_kraft[3*a+1]; KRAFT(p,i,Z) = r_kraft[3*a+2];
+    POTENG(p,i) = r_poteng[a];
+#ifdef EAM2
+    EAM_RHO(p,i) = r_rho[a];
+#endif
+#ifdef STRESS_TENS
+    if (press) {
+      PRESSTENS(p,i,xx) = r_press[6*a]; PRESSTENS(p,i,yy) = r_press[6*a+1]; PRESSTENS(p,i,zz) = r_press[6*a+2];
+      PRESSTENS(p,i,yz) = r_press[6*a+3]; PRESSTENS(p,i,zx) = r_press[6*a+4]; PRESSTENS(p,i,xy) = r_press[6*a+5];
+    }
+#endif
+  }
+}
+#endif
+
 /* write device results back into IMD's cells; the device order is cell-sorted, atoms are matched by NUMMER */
 static void b200_download(int forces, int state, int press)
 {
   long n, got; 
   static int *d_num = NULL; static long d_cap = 0;
   double *pt = NULL;
+#ifdef MPI
+  (void) n; (void) got; (void) d_num; (void) d_cap; (void) pt; (void) forces; (void) state;
+  b200_rebin(press);
+  return;
+#endif
   if (d_cap < b200_n) { d_cap = b200_n; d_num = b200_realloc(d_num, d_cap * sizeof(int)); }
 #ifdef STRESS_TENS
   if (press) pt = b_press;
@@ -241,7 +303,24 @@ static void b200_init(void)
 #elif defined(SPLINE)
   cfg.interpolation = IMDB200_INTERP_SPLINE;
 #endif
+#ifdef MPI
+  { /* one rank per GPU: the process grid is IMD's, the device is the rank's share of this node's GPUs */
+    int ndev = imdb200_device_count();
+    if (ndev < 1) error("imd_b200: no CUDA device");
+    cfg.cpu_dim[0] = cpu_dim.x; cfg.cpu_dim[1] = cpu_dim.y; cfg.cpu_dim[2] = cpu_dim.z;
+    cfg.my_coord[0] = my_coord.x; cfg.my_coord[1] = my_coord.y; cfg.my_coord[2] = my_coord.z;
+    cfg.device = myid % ndev;
+  }
+#endif
   b200_check(imdb200_create(&cfg, &b200));
+#ifdef MPI
+  if (num_cpus > 1) {
+    char id[128];
+    if (myid == 0) b200_check(imdb200_comm_unique_id(id));
+    MPI_Bcast(id, 128, MPI_CHAR, 0, MPI_COMM_WORLD);
+    b200_check(imdb200_comm_init(b200, id, myid, num_cpus));
+  }
+#endif
   /* pot_table_t (src/types.h:416-428) and imdb200_pot_table have the same layout */
 #ifdef EAM2
   b200_check(imdb200_set_potentials(b200, (imdb200_pot_table *) &pair_pot, (imdb200_pot_table *) &embed_pot,

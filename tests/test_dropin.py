@@ -162,3 +162,33 @@ def test_restart_from_checkpoint(built_lib, tmp_path):
     d = cg[:, 3:6] - cc[:, 3:6]
     d -= box * np.round(d / box)
     assert np.max(np.abs(d)) < 1e-7 and np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-6
+
+
+def test_mpi_binding_two_ranks(built_lib, tmp_path):
+    """IMD's own MPI main() (setup_mpi_topology, per-rank atom distribution, rank-0 writers) around the engine, one rank per
+    GPU on oracle/shmpi: cpu_dim / my_coord from IMD's globals, ncclUniqueId by MPI_Bcast, halo / migration / reductions
+    inside the library, host cells refilled from the device at every download.  Against the unmodified SERIAL IMD."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    tmp = str(tmp_path)
+    tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+    exe = os.path.join(REF, "imd_b200_dropin_mpi")
+    assert os.path.exists(exe), "oracle/_ref/imd_b200_dropin_mpi missing: run `make -C oracle ref` where /root/reference exists"
+    common_kw = dict(ncell=(12, 10, 10), ensemble="nvt", maxsteps=40, starttemp=0.25, tables=tabs)
+    pg = synth.cu_param(tmp, name="gpu", extra=dict(eng_int=1, checkpt_int=40, cpu_dim=[2, 1, 1]), **common_kw)
+    r = subprocess.run([exe, "-p", pg], capture_output=True, text=True, cwd=tmp, timeout=600, env=dict(os.environ, SHMPI_NP="2"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    pc = synth.cu_param(tmp, name="cpu", extra=dict(eng_int=1, checkpt_int=40), **common_kw)
+    _run("imd_ref_serial_eam", pc, tmp)
+    eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
+    assert eg.shape == ec.shape and len(eg) == 41
+    assert abs(eg[0, 1] - ec[0, 1]) <= 1e-12 * abs(ec[0, 1])
+    assert np.max(np.abs(eg[:, 1] - ec[:, 1]) / np.abs(ec[:, 1])) <= 1e-8
+    assert np.max(np.abs(eg[:, 2] - ec[:, 2]) / np.abs(ec[:, 2])) <= 1e-8
+    cg, cc = _chkpt(os.path.join(tmp, "gpu.00001.chkpt")), _chkpt(os.path.join(tmp, "cpu.00001.chkpt"))
+    assert cg.shape == cc.shape and np.array_equal(cg[:, 0], cc[:, 0]), "atoms lost or duplicated between the ranks"
+    box = np.array([12, 10, 10]) * synth.CU_A0
+    d = cg[:, 3:6] - cc[:, 3:6]
+    d -= box * np.round(d / box)
+    assert np.max(np.abs(d)) < 1e-6 and np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-5

@@ -122,6 +122,35 @@ def test_cuda_adp_matches_reference_fixture(api, name, lanes, tmp_path):
     assert r.returncode == 0 and "ADP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("mode", ["stepwise", "run"])
+def test_cuda_berendsen_matches_reference_fixture(api, mode, tmp_path):
+    """imdb200_set_berendsen against the reference's `ber` build: Berendsen scaling of the momenta inside move_atoms_nve,
+    driven by the kinetic energy of the previous step (src/imd_integrate.c:44-53, 341-350); stepwise calls and the
+    device-resident loop (scaling in the fused tail of pass 2)."""
+    g = common.load_golden("cu_berendsen")
+    paths = common.write_tables(g, str(tmp_path))
+    sim = api.IMDB200(1, g["box"], pair=paths["pair"], embed=paths["embed"], rho=paths["rho"], ensemble="nve",
+                      timestep=float(g["timestep"]), temperature=float(g["temperature"]))
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"])
+    sim.set_berendsen(float(g["tau_berendsen"]), float(g["ekin_start"]))
+    n = int(g["nsteps"])
+    if mode == "stepwise":
+        for s in range(n):
+            sim.calc_forces(s)
+            tol = 1e-10 if s == 0 else 1e-8
+            assert abs(sim.scalars()["tot_pot_energy"] - g["epot"][s]) <= tol * abs(g["epot"][s]), s
+            sim.move_atoms()
+            sim.check_nblist()
+            assert abs(sim.scalars()["tot_kin_energy"] - g["ekin"][s]) <= tol * abs(g["ekin"][s]), s
+            assert sim.have_valid_nbl == int(g["valid"][s])
+    else:
+        sim.run(n)
+        assert abs(sim.scalars()["tot_kin_energy"] - g["ekin"][-1]) <= 1e-8 * abs(g["ekin"][-1])
+    a = sim.atoms()
+    assert np.max(np.abs(a["impuls"] - g["final:impuls"])) <= 1e-8 * np.max(np.abs(g["final:impuls"]))
+    sim.close()
+
+
 def test_cuda_cubic_run_loop_equals_stepwise_calls(api, tmp_path):
     """imdb200_run (fused integrator) and the separate calls stay bit-identical in the cubic kernels too."""
     g = common.load_golden("cu_spline")
