@@ -439,18 +439,40 @@ static int queue_step(imdb200_sim *s, int slot, bool built)
 {
   cudaEvent_t *ev = s->ev + 5 * slot;
   s->p2p_step = !built;                        // the exchanges of a step with a list build stay on the NCCL path
-  if (!built) { cudaEventRecord(ev[0], s->stream); TRY(comm_ghost_pos(s)); }       // send_cells(copy_cell,...) (:314)
-  cudaEventRecord(ev[1], s->stream);
   // single-species EAM: move_atoms + check_nblist ride in the tail of pass 2 (bit-identical, one kernel less)
   const int fuse = forces_can_fuse_move(s);
+  // Overlapped halo (peer-memory exchange + boundary-first order): every pass runs its boundary warps first, their
+  // results go straight into the neighbours' ghost regions, and the interior warps run while the data is in flight;
+  // the wait sits in front of the next kernel that reads images.
+  const int split = comm_p2p_ready(s) && forces_split_possible(s);
+  if (!built) {
+    cudaEventRecord(ev[0], s->stream);
+    if (split && s->pos_sent_early) { TRY(comm_p2p_end(s, 0)); TRY(comm_ghost_pos_finish(s)); }   // sent during pass 2 of the last step
+    else TRY(comm_ghost_pos(s));                                                   // send_cells(copy_cell,...) (:314)
+  }
+  s->pos_sent_early = 0;
+  cudaEventRecord(ev[1], s->stream);
   s->fuse_step = fuse; s->zero_before_move = !fuse;
-  TRY(forces_pass1(s));
-  cudaEventRecord(ev[2], s->stream);
-  if (s->tabs.have_eam) {
-    TRY(comm_ghost_dF(s));                                                         // send_cells(copy_dF,...) (:1115)
-    if (s->tabs.have_eeam) TRY(comm_ghost_dM(s));
-    TRY(forces_pass2(s, fuse));
-  } else s->maxd2_zeroed = 0;
+  if (split) {
+    s->split_part = 1; TRY(forces_pass1(s));
+    TRY(comm_p2p_begin(s, 1));                                                     // F' of the boundary atoms on its way ...
+    s->split_part = 2; TRY(forces_pass1(s));                                       // ... while the interior is evaluated
+    s->split_part = 0;
+    cudaEventRecord(ev[2], s->stream);
+    TRY(comm_p2p_end(s, 1)); TRY(comm_ghost_dF_finish(s));
+    s->split_part = 1; TRY(forces_pass2(s, fuse));                                 // boundary atoms: forces, move_atoms
+    TRY(comm_p2p_begin(s, 0)); s->pos_sent_early = 1;                              // their new positions for the next step
+    s->split_part = 2; TRY(forces_pass2(s, fuse));
+    s->split_part = 0;
+  } else {
+    TRY(forces_pass1(s));
+    cudaEventRecord(ev[2], s->stream);
+    if (s->tabs.have_eam) {
+      TRY(comm_ghost_dF(s));                                                       // send_cells(copy_dF,...) (:1115)
+      if (s->tabs.have_eeam) TRY(comm_ghost_dM(s));
+      TRY(forces_pass2(s, fuse));
+    } else s->maxd2_zeroed = 0;
+  }
   cudaEventRecord(ev[3], s->stream);
   if (fuse) TRY(integrate_finish(s, 0)); else TRY(integrate_move(s));
   s->fuse_step = 0; s->zero_before_move = 0;
@@ -494,6 +516,7 @@ static int retire_step(imdb200_sim *s, int slot, bool built, double rebuild_ms, 
 static int run_async(imdb200_sim *s, int nsteps)
 {
   int done = 0, inflight = 0, head = 0, tail = 0;
+  s->pos_sent_early = 0;                       // the caller may have changed positions or box since the last call
   bool built[3] = {false, false, false};
   double reb_ms[3] = {0.0, 0.0, 0.0};
   int rc = 0;

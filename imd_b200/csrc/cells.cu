@@ -692,6 +692,57 @@ int cells_count_nactive(imdb200_sim *s)
   return 0;
 }
 
+// ---- boundary-first warp order (see imdb200_sim::worder) -----------------------------------------------
+// a warp of 32 thread slots (32/L atoms) is a boundary warp when one of its atoms sits in the outermost layer of owned
+// cells: only those atoms have images in their lists, and only they are sent to neighbours
+__global__ void k_warp_flags(const int *cellid, long n_own, int L, Geom g, long n_warps, int *wflag)
+{
+  const long w = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (w >= n_warps) return;
+  const long a0 = w * 32 / L, a1 = min(n_own, (w * 32 + 31) / L + 1);
+  int f = 0;
+  for (long i = a0; i < a1 && !f; i++) {
+    const int c = cellid[i];
+    const int cz = c % g.cdim[2], cy = (c / g.cdim[2]) % g.cdim[1], cx = c / (g.cdim[2] * g.cdim[1]);
+    f = cx == 1 || cx == g.cdim[0] - 2 || cy == 1 || cy == g.cdim[1] - 2 || cz == 1 || cz == g.cdim[2] - 2;
+  }
+  wflag[w] = f;
+}
+__global__ void k_warp_order(const int *wflag, const int *wscan, long n_warps, const int *n_boundary, int *worder)
+{
+  const long w = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (w >= n_warps) return;
+  const int before = wscan[w];                         // boundary warps in front of w
+  worder[wflag[w] ? before : *n_boundary + (int) (w - before)] = (int) w;
+}
+
+int cells_build_worder(imdb200_sim *s)
+{
+  s->n_bwarps = 0;
+  s->n_warps = (s->n_own * s->lanes + 31) / 32;
+  if (s->nranks == 1 || s->n_warps == 0) return 0;
+  cudaStream_t st = s->stream;
+  if (s->n_warps + 1 > s->worder_cap) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    void *old[] = {s->worder, s->wflag, s->wscan};
+    for (void *q : old) if (q) cudaFree(q);
+    s->worder_cap = s->n_warps + s->n_warps / 8 + 1024;
+    CUDA_TRY(cudaMalloc(&s->worder, s->worder_cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&s->wflag, s->worder_cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&s->wscan, s->worder_cap * sizeof(int)));
+  }
+  const int nb = cdiv(s->n_warps, 256);
+  k_warp_flags<<<nb, 256, 0, st>>>(s->cellid, s->n_own, s->lanes, s->geom, s->n_warps, s->wflag); LAUNCH_CHECK();
+  CUDA_TRY(cudaMemsetAsync(s->wflag + s->n_warps, 0, sizeof(int), st));
+  TRY(scan_exclusive(s, s->wflag, s->wscan, (int) s->n_warps + 1, nullptr));       // entry n_warps = number of boundary warps
+  k_warp_order<<<nb, 256, 0, st>>>(s->wflag, s->wscan, s->n_warps, s->wscan + s->n_warps, s->worder); LAUNCH_CHECK();
+  int nbw = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nbw, s->wscan + s->n_warps, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  s->n_bwarps = nbw;
+  return 0;
+}
+
 // fix_cells + send_cells + make_nblist, i.e. the `0 == have_valid_nbl` branch of calc_forces
 // (src/imd_forces_nbl.c:304-317)
 int cells_rebuild(imdb200_sim *s)
@@ -760,6 +811,7 @@ int cells_rebuild(imdb200_sim *s)
   CUDA_TRY(cudaMemcpyAsync(&len, d_len, sizeof(len), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   s->nbl_len = (long long) len;
+  TRY(cells_build_worder(s));
   s->disp2 = 0.0;                 // NBL_POS == ORT
   TRY(step_snapshot_disp2(s, 1));
   s->skin_all = 0;

@@ -417,6 +417,24 @@ int comm_ghost_pos(imdb200_sim *s)
   return 0;
 }
 
+// the images from what has arrived (the tail of comm_ghost_pos / comm_ghost_dF, for the overlapped peer-memory exchange)
+int comm_ghost_pos_finish(imdb200_sim *s)
+{
+  if (s->n_ghost == 0) return 0;
+  k_ghost_pos<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->pos, s->n_own, s->n_ghost, s->gsrc, s->ghost_raw,
+                                                              s->cellid + s->n_own, s->cell_code, s->geom);
+  LAUNCH_CHECK();
+  return 0;
+}
+int comm_ghost_dF_finish(imdb200_sim *s)
+{
+  if (s->n_ghost == 0) return 0;
+  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->tabs.ntypes == 1 ? s->posdf : nullptr, s->pos, s->n_own,
+                                                             s->n_ghost, s->gsrc);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // send_cells(copy_dF, pack_dF, unpack_dF): 2F'(rho) of the owners into the buffer cells
 int comm_ghost_dF(imdb200_sim *s)
 {

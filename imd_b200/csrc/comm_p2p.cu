@@ -3,8 +3,8 @@
 // with stream memory operations (cuStreamWriteValue64 / cuStreamWaitValue64), so no communication kernel competes
 // with the persistent force CTAs and no SM spins while it waits.
 //
-// STATUS: off by default (environment IMDB200_HALO_P2P=1 switches it on at imdb200_comm_init, on every rank or on none:
-// the ranks agree on it).  Green on 2 B200s against the same reference fixtures as the NCCL path
+// STATUS: on by default when every rank can map every other rank's memory (IMDB200_HALO_P2P=0 keeps the NCCL messages;
+// on every rank or on none: the ranks agree on it at imdb200_comm_init).  Green on 2 B200s against the same reference fixtures as the NCCL path
 // (tests/test_multi_gpu.py::test_two_domains_peer_memory_halo, profiles/r2_pytest_mgpu_2.log).
 //
 // Replaces, for the steps between two list builds: send_cells(copy_cell, pack_cell, unpack_cell) and
@@ -89,8 +89,24 @@ extern "C" int comm_p2p_enable(imdb200_sim *s)
   const char *e = getenv("IMDB200_HALO_P2P");
   s->p2p_on = 0;
   if (s->nranks <= 1) return 0;
-  // every rank must take the same path (a rank without it would skip the all-gathers of comm_p2p_setup): agree first
-  long long want = (e && atoi(e) != 0 && s->nranks <= P2P_MAXRANKS && driver_load() == 0) ? 1 : 0, all = 0;
+  // On by default where every rank can map every other rank's memory (one NVLink / NVSwitch node); IMDB200_HALO_P2P=0
+  // keeps the NCCL messages.  Every rank must take the same path (a rank without it would skip the all-gathers of
+  // comm_p2p_setup), so the ranks agree first: device ordinals are gathered, peer access is probed, the votes are summed.
+  long long want = ((!e || atoi(e) != 0) && s->nranks <= P2P_MAXRANKS && driver_load() == 0) ? 1 : 0, all = 0;
+  {
+    std::vector<long long> devs(s->nranks, -1);
+    for (int r = 0; r < s->nranks; r++) {                // rank r's device ordinal, one value per collective (all ranks take part)
+      long long v = 0;
+      TRY(comm_allgather_ll(s, s->rank == r ? (long long) s->cfg.device + 1 : 0, &v));
+      devs[r] = v - 1;
+    }
+    for (int r = 0; r < s->nranks && want; r++) {
+      if (r == s->rank) continue;
+      int can = 0;
+      if (devs[r] == s->cfg.device || cudaDeviceCanAccessPeer(&can, s->cfg.device, (int) devs[r]) != cudaSuccess || !can) want = 0;
+    }
+    cudaGetLastError();
+  }
   TRY(comm_allgather_ll(s, want, &all));
   if (all != s->nranks) return 0;
   P2PState *st = (P2PState *) calloc(1, sizeof(P2PState));
@@ -197,7 +213,9 @@ int comm_p2p_setup(imdb200_sim *s, int (*allgather)(imdb200_sim *, const void *,
   return 0;
 }
 
-static int exchange_p2p(imdb200_sim *s, int kind)
+// First half of an exchange: store my boundary values (kind 0: positions, 1: F') into every peer's ghost region and
+// tell the peer, in stream order, that my slice of exchange number `step` is complete in its memory.
+int comm_p2p_begin(imdb200_sim *s, int kind)
 {
   P2PState *st = (P2PState *) s->p2p;
   P2PTable tab;
@@ -216,13 +234,20 @@ static int exchange_p2p(imdb200_sim *s, int kind)
     LAUNCH_CHECK();
   }
   const unsigned long long step = ++st->step[kind];
-  // tell every peer that my slice of this exchange is complete in its memory ...
   for (int q = 0; q < st->npeer; q++) {
     unsigned long long *f = st->peer[q].flags + (size_t) kind * P2P_MAXRANKS + s->rank;
     if (g_cuWrite64(s->stream, (unsigned long long) (uintptr_t) f, step, 0u) != 0)
       return imdb_fail(IMDB200_ERR_COMM, "cuStreamWriteValue64 failed");
   }
-  // ... and wait, in stream order, until every peer has told me the same (CU_STREAM_WAIT_VALUE_GEQ = 0)
+  return 0;
+}
+
+// Second half: wait, in stream order and without occupying an SM, until every peer has told me the same
+// (CU_STREAM_WAIT_VALUE_GEQ = 0).  Whatever is queued between the two halves overlaps the transfer.
+int comm_p2p_end(imdb200_sim *s, int kind)
+{
+  P2PState *st = (P2PState *) s->p2p;
+  const unsigned long long step = st->step[kind];
   for (int q = 0; q < st->npeer; q++) {
     unsigned long long *f = st->flags + (size_t) kind * P2P_MAXRANKS + st->peer[q].rank;
     if (g_cuWait64(s->stream, (unsigned long long) (uintptr_t) f, step, 0u) != 0)
@@ -230,6 +255,8 @@ static int exchange_p2p(imdb200_sim *s, int kind)
   }
   return 0;
 }
+
+static int exchange_p2p(imdb200_sim *s, int kind) { TRY(comm_p2p_begin(s, kind)); return comm_p2p_end(s, kind); }
 
 int comm_p2p_ready(const imdb200_sim *s) { return s->p2p_on && s->p2p && ((const P2PState *) s->p2p)->ready; }
 int comm_p2p_positions(imdb200_sim *s) { return exchange_p2p(s, 0); }     // then k_ghost_pos, as after the NCCL exchange

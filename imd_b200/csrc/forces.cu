@@ -124,6 +124,8 @@ struct FArgs {
   int cls_fixed;                 // highest skin class to walk, or -1: from ctl->disp2 (skin_class_of)
   double cls_w;                  // width of a skin class
   const StepCtl *ctl;
+  int pblock0;                        // first block slot of this launch in the partial-sum array
+  const int *worder; long w0, wn;     // warps [w0, w0+wn) of the processing order (nullptr: identity, see imdb200_sim::worder)
   long n_own;
   int rows;                      // max_nb / L
   double *presstens; long pstride;
@@ -215,12 +217,13 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
   const double p_end0 = T.pair.end[0], p_is0 = T.pair.invstep[0], p_nb0 = -T.pair.begin[0] * T.pair.invstep[0];
   const double r_end0 = EAM ? T.rho.end[0] : 0.0, r_is0 = EAM ? T.rho.invstep[0] : 0.0,
                r_nb0 = EAM ? -T.rho.begin[0] * T.rho.invstep[0] : 0.0;
-  const long total = ((a.n_own * L + 31) / 32) * 32;                  // thread slots, whole warps
-  const long per = ((total + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
-  const long s_end = min(total, (long) (blockIdx.x + 1) * per);
+  // every CTA walks a contiguous run of the warp order: whole warps of 32 thread slots
+  const long per = (a.wn + gridDim.x - 1) / gridDim.x;
+  const long w_end = min(a.wn, (long) (blockIdx.x + 1) * per);
   double red[2] = {0.0, 0.0};
   int is_short = 0;
-  for (long slot = (long) blockIdx.x * per + threadIdx.x; slot < s_end; slot += NT) {
+  for (long wv = (long) blockIdx.x * per + (threadIdx.x >> 5); wv < w_end; wv += NT / 32) {
+    const long slot = (a.worder ? (long) a.worder[a.w0 + wv] : a.w0 + wv) * 32 + (threadIdx.x & 31);
     const long i = slot / L;
     const int sub = (int) (slot % L);
     const bool act = i < a.n_own;
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
     }
   }
   if (is_short) atomicExch(&a.flags[FL_SHORT], 1);
-  block_sum_store<2>(red, a.partial);
+  block_sum_store<2>(red, a.partial + (size_t) a.pblock0 * 2);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -431,15 +434,15 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   const int nt = T.ntypes;
   const double r_end0 = T.rho.end[0], r_is0 = T.rho.invstep[0], r_nb0 = -T.rho.begin[0] * T.rho.invstep[0];
   const double4 *gat = MULTI ? a.pos : a.posdf;      // single species: x,y,z,dF in one record
-  const long total = ((a.n_own * L + 31) / 32) * 32;
-  const long per = ((total + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
-  const long s_end = min(total, (long) (blockIdx.x + 1) * per);
+  const long per = (a.wn + gridDim.x - 1) / gridDim.x;
+  const long w_end = min(a.wn, (long) (blockIdx.x + 1) * per);
   double red[3] = {0.0, 0.0, 0.0};                  // virial, and with FUSE the two kinetic-energy sums
   double d2max = 0.0;
   // FUSE: SC_EKIN still holds the previous step's kinetic energy here (this step's is written by the reduction behind us)
   const double ber_cc = FUSE ? berendsen_cc(a.glob[SC_EKIN], a.nactive, a.temperature, a.dt, a.tauber) : 1.0;
   int is_short = 0;
-  for (long slot = (long) blockIdx.x * per + threadIdx.x; slot < s_end; slot += NT) {
+  for (long wv = (long) blockIdx.x * per + (threadIdx.x >> 5); wv < w_end; wv += NT / 32) {
+    const long slot = (a.worder ? (long) a.worder[a.w0 + wv] : a.w0 + wv) * 32 + (threadIdx.x & 31);
     const long i = slot / L;
     const int sub = (int) (slot % L);
     const bool act = i < a.n_own;
@@ -615,10 +618,10 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d2max = fmax(d2max, __shfl_xor_sync(0xffffffffu, d2max, o));
     if ((threadIdx.x & 31) == 0) atomicMax(a.maxd2, (unsigned long long) __double_as_longlong(d2max));
-    block_sum_store<3>(red, a.partial);
+    block_sum_store<3>(red, a.partial + (size_t) a.pblock0 * 3);
   } else {
     double r1[1] = {red[0]};
-    block_sum_store<1>(r1, a.partial);
+    block_sum_store<1>(r1, a.partial + (size_t) a.pblock0);
   }
 }
 
@@ -706,12 +709,27 @@ void forces_free_textures(imdb200_sim *s)
 }
 #endif
 
-static FArgs make_args(imdb200_sim *s)
+static int g_num_sms = 0;
+// CTAs of a launch over nw warps: persistent, at most one per SM
+static int part_blocks(imdb200_sim *s, long nw, int nt)
+{
+  if (!g_num_sms) { cudaDeviceProp p; cudaGetDeviceProperties(&p, s->cfg.device); g_num_sms = p.multiProcessorCount; }
+  const long need = (nw * 32 + nt - 1) / nt;
+  return (int) (need < g_num_sms ? (need > 0 ? need : 1) : g_num_sms);
+}
+
+static FArgs make_args(imdb200_sim *s, int nt)
 {
   FArgs a;
   a.tpos = s->tex_pos; a.tposdf = s->tex_posdf; a.use_tex = s->tex_ok;
   a.pos = s->pos; a.posdf = s->posdf; a.frc = s->frc; a.rho = s->rho; a.dF = s->dF; a.eam_p = s->eam_p; a.dM = s->dM; a.nbl = s->nbl; a.nnbc = s->nnbc;
   a.cls_fixed = skin_class_fixed(s); a.cls_w = s->cfg.nbl_margin / NBL_CLASSES; a.ctl = s->d_ctl;
+  const long nw = (s->n_own * s->lanes + 31) / 32;
+  a.worder = nullptr; a.w0 = 0; a.wn = nw;
+  if (s->split_part == 1) { a.worder = s->worder; a.w0 = 0; a.wn = s->n_bwarps; }
+  else if (s->split_part == 2) { a.worder = s->worder; a.w0 = s->n_bwarps; a.wn = nw - s->n_bwarps; }
+  // the per-block partial sums of the interior launch sit behind those of the boundary launch
+  a.pblock0 = s->split_part == 2 ? part_blocks(s, s->n_bwarps, nt) : 0;
   a.n_own = s->n_own; a.rows = s->max_nb / s->lanes;
   a.presstens = s->presstens; a.pstride = s->cap_atoms;
   a.partial = s->d_partial; a.flags = s->d_flags;
@@ -722,13 +740,19 @@ static FArgs make_args(imdb200_sim *s)
   return a;
 }
 
-static int g_num_sms = 0;
 static int grid_for(imdb200_sim *s, int nt)
 {
-  if (!g_num_sms) { cudaDeviceProp p; cudaGetDeviceProperties(&p, s->cfg.device); g_num_sms = p.multiProcessorCount; }
-  const long total = ((s->n_own * s->lanes + 31) / 32) * 32;
-  const long need = (total + nt - 1) / nt;
-  return (int) (need < g_num_sms ? need : g_num_sms);   // persistent: at most one CTA per SM
+  const long nw = (s->n_own * s->lanes + 31) / 32;
+  if (s->split_part == 1) return part_blocks(s, s->n_bwarps, nt);
+  if (s->split_part == 2) return part_blocks(s, nw - s->n_bwarps, nt);
+  return part_blocks(s, nw, nt);
+}
+// blocks whose partial sums the reduction behind a pass has to add up (both parts of a split pass)
+static int reduce_blocks(imdb200_sim *s, int nt)
+{
+  const long nw = (s->n_own * s->lanes + 31) / 32;
+  if (s->split_part == 2) return part_blocks(s, s->n_bwarps, nt) + part_blocks(s, nw - s->n_bwarps, nt);
+  return grid_for(s, nt);
 }
 
 template <typename K> static int launch_k(K kern, imdb200_sim *s, const FArgs &a, int nt, int smem)
@@ -780,6 +804,11 @@ int forces_can_fuse_move(const imdb200_sim *s)
 { return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0 &&
          s->cfg.ensemble != IMDB200_ENS_NPT_ISO && !s->tabs.have_adp; }
 
+// the passes can run boundary part first / interior part second when there is a boundary-first order and the
+// integrator rides in pass 2 (positions of the boundary atoms are final after its boundary part)
+int forces_split_possible(const imdb200_sim *s)
+{ return s->nranks > 1 && s->worder && s->n_bwarps > 0 && s->n_bwarps < s->n_warps && forces_can_fuse_move(s) && !s->tabs.have_eeam; }
+
 // forces.cu is compiled four times: quadratic / cubic table interpolation, each without / with the EEAM terms
 int forces_pass1(imdb200_sim *s)
 {
@@ -796,7 +825,7 @@ int forces_pass2(imdb200_sim *s, int fuse)
 int IMPL(forces_pass1)(imdb200_sim *s)
 {
   TRY(forces_textures(s));
-  FArgs a = make_args(s);
+  FArgs a = make_args(s, s->press_calc ? 512 : IMDB_NT);
   switch (s->lanes) {
     case 1: TRY(launch1_L<1>(s, a)); break;
     case 2: TRY(launch1_L<2>(s, a)); break;
@@ -806,16 +835,17 @@ int IMPL(forces_pass1)(imdb200_sim *s)
     case 32: TRY(launch1_L<32>(s, a)); break;
     default: return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
   }
+  if (s->split_part == 1) return 0;                      // the interior launch follows; one reduction over both
   const int slots[2] = {SC_EPOT, SC_VIRIAL};
   // fuse_step (imdb200_run): SC_MAXD2 is cleared here, in stream order before pass 2, whose fused integrator
   // accumulates the new maximum (a kernel, not a memset, so that a gated step leaves it alone)
-  return reduce_finish(s, grid_for(s, s->press_calc ? 512 : IMDB_NT), 2, slots, 0, s->fuse_step);
+  return reduce_finish(s, reduce_blocks(s, s->press_calc ? 512 : IMDB_NT), 2, slots, 0, s->fuse_step);
 }
 
 int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
 {
   TRY(forces_textures(s));
-  FArgs a = make_args(s);
+  FArgs a = make_args(s, s->press_calc ? 512 : IMDB_NT2);
   if (fuse && !forces_can_fuse_move(s)) return imdb_fail(IMDB200_ERR_ARG, "fused move_atoms is not available in this configuration");
   switch (s->lanes) {
     case 1: TRY(launch2_L<1>(s, a, fuse)); break;
@@ -826,7 +856,8 @@ int IMPL(forces_pass2)(imdb200_sim *s, int fuse)
     case 32: TRY(launch2_L<32>(s, a, fuse)); break;
     default: return imdb_fail(IMDB200_ERR_ARG, "lanes_per_atom must be a power of two <= 32");
   }
-  const int nb = grid_for(s, s->press_calc ? 512 : IMDB_NT2);
+  if (s->split_part == 1) return 0;
+  const int nb = reduce_blocks(s, s->press_calc ? 512 : IMDB_NT2);
   if (fuse) {
     const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT;
     const int slots[3] = {SC_VIRIAL, nvt ? SC_EKIN1 : SC_EKIN, SC_EKIN2};

@@ -170,6 +170,13 @@ struct imdb200_sim {
   // queued before the host knew that the previous one invalidated the list); disp2 = max squared displacement since the
   // list build as of the end of the previous step, from which the force kernels pick the skin classes to walk
   struct StepCtl *d_ctl;
+  // Boundary-first processing order of the force kernels (multi-GPU): worder lists the warps (32 thread slots each)
+  // whose atoms lie in the outermost layer of owned cells first, the interior ones behind them.  The boundary part
+  // of a pass runs as its own launch; what it produces is stored into the neighbours' ghost regions over NVLink
+  // (comm_p2p.cu) while the interior part runs, and the consumer waits for it only where it needs the images.
+  int *worder, *wflag, *wscan; long n_warps, n_bwarps, worder_cap;
+  int split_part;                    // which part the next force launch covers: 0 all, 1 boundary, 2 interior
+  int pos_sent_early;                // the boundary positions of the next step are already on their way (pass 2 of this one)
   int maxd2_zeroed;                  // SC_MAXD2 was cleared by the reduction kernel behind pass 2 (zero_before_move)
   int zero_before_move;              // imdb200_run, unfused step: ask that reduction kernel to clear it
   int fuse_step;                     // the step being queued runs move_atoms in the tail of pass 2
@@ -258,6 +265,12 @@ int comm_p2p_setup(imdb200_sim *s, int (*allgather)(imdb200_sim *, const void *,
 int comm_p2p_ready(const imdb200_sim *s);
 int comm_p2p_positions(imdb200_sim *s);
 int comm_p2p_dF(imdb200_sim *s);
+int comm_p2p_begin(imdb200_sim *s, int kind);     // kind 0 positions, 1 F': store my boundary values into the peers' ghost regions, signal
+int comm_p2p_end(imdb200_sim *s, int kind);       // wait until every peer has done the same towards me
+int comm_ghost_pos_finish(imdb200_sim *s);    // images from the raw copies (after comm_p2p_end(s, 0))
+int comm_ghost_dF_finish(imdb200_sim *s);
+int forces_split_possible(const imdb200_sim *s);
+int cells_build_worder(imdb200_sim *s);
 int comm_allgather_ll(imdb200_sim *s, long long mine, long long *all);
 
 int forces_pass1(imdb200_sim *s);             // pair + rho + embedding

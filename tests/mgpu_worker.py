@@ -106,6 +106,45 @@ def case_migration(grid, rank, pbc=(1, 1, 1)):
     return sim
 
 
+def case_overlap(grid, rank):
+    """imdb200_run over the process grid (overlapped peer-memory halo by default) against the same run on one GPU."""
+    tmp = tempfile.mkdtemp(prefix=f"ov{rank}_")
+    tabs = synth.make_eam_tables(tmp, "cu")
+    ort, box = synth.fcc_lattice((32, 32, 32), synth.CU_A0)
+    n = len(ort)
+    rng = np.random.default_rng(3)
+    ort = ort + rng.normal(0, 0.05, ort.shape)
+    m = np.full(n, synth.CU_MASS)
+    p = synth.maxwell_momenta(n, m, 0.12, 9)
+    num, typ = np.arange(n, dtype=np.int32), np.zeros(n, np.int32)
+    kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"],
+              ensemble="nve", timestep=0.001)
+    sim = idist.create(1, box, cpu_dim=grid, device=int(os.environ.get("LOCAL_RANK", "0")), **kw)
+    sim.set_atoms(num, typ, m, ort, p)
+    for _ in range(3):
+        sim.run(20)
+    a = idist.gather_atoms(sim)
+    sc = sim.scalars()
+    if rank == 0:
+        ref = api.IMDB200(1, box, device=0, **kw)
+        ref.set_atoms(num, typ, m, ort, p)
+        ref.run(60)
+        b = ref.atoms()
+        rs = ref.scalars()
+        assert np.array_equal(a["nummer"], b["nummer"])
+        d = a["ort"] - b["ort"]
+        frac = d @ np.linalg.inv(box)
+        d = (frac - np.round(frac)) @ box
+        print("overlap: max |dx|", np.abs(d).max(), "max |dp|", np.abs(a["impuls"] - b["impuls"]).max(), "builds", sim.nbl_count)
+        assert np.abs(d).max() < 1e-9 and np.abs(a["impuls"] - b["impuls"]).max() < 1e-10
+        assert np.max(np.abs(a["kraft"] - b["kraft"])) < 1e-8 * np.max(np.abs(b["kraft"]))
+        assert abs(sc["tot_pot_energy"] - rs["tot_pot_energy"]) < 1e-10 * abs(rs["tot_pot_energy"])
+        assert abs(sc["tot_kin_energy"] - rs["tot_kin_energy"]) < 1e-9 * abs(rs["tot_kin_energy"])
+        assert sim.nbl_count == ref.nbl_count and sim.nbl_count >= 3
+        ref.close()
+    return sim
+
+
 def case_send_forces(grid, rank):
     """send_forces analogue: every image carries 1.0; after the reverse exchange an owner holds the number of
     its images, which is fixed by the geometry: prod(1 + [low layer] + [high layer]) - 1 over the axes."""
@@ -160,6 +199,8 @@ def main():
         sim = case_migration(grid, rank, pbc=(1, 1, 0))
     elif case == "send_forces":
         sim = case_send_forces(grid, rank)
+    elif case == "overlap":
+        sim = case_overlap(grid, rank)
     else:
         raise SystemExit(f"unknown case {case}")
     dist.barrier()

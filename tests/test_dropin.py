@@ -175,11 +175,20 @@ def test_mpi_binding_two_ranks(built_lib, tmp_path):
     tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
     exe = os.path.join(REF, "imd_b200_dropin_mpi")
     assert os.path.exists(exe), "oracle/_ref/imd_b200_dropin_mpi missing: run `make -C oracle ref` where /root/reference exists"
-    common_kw = dict(ncell=(12, 10, 10), ensemble="nvt", maxsteps=40, starttemp=0.25, tables=tabs)
-    pg = synth.cu_param(tmp, name="gpu", extra=dict(eng_int=1, checkpt_int=40, cpu_dim=[2, 1, 1]), **common_kw)
-    r = subprocess.run([exe, "-p", pg], capture_output=True, text=True, cwd=tmp, timeout=600, env=dict(os.environ, SHMPI_NP="2"))
+    # every run starts from the same reference-written checkpoint (maxwell() draws its random numbers in rank-local cell
+    # order): a hot crystal, so that atoms cross the rank boundary
+    pt = synth.cu_param(tmp, ncell=(12, 10, 10), name="therm", ensemble="nvt", maxsteps=20, starttemp=0.25, tables=tabs,
+                        extra=dict(checkpt_int=20))
+    _run("imd_ref_serial_eam", pt, tmp)
+    chk = os.path.join(tmp, "therm.00001.chkpt")
+    assert os.path.exists(chk)
+    common_kw = dict(ncell=(12, 10, 10), ensemble="nvt", maxsteps=40, starttemp=0.25, tables=tabs, coordname=chk)
+    pg = synth.cu_param(tmp, name="gpu", extra=dict(eng_int=1, checkpt_int=40, box_from_header=1, cpu_dim=[2, 1, 1]), **common_kw)
+    r = subprocess.run([exe, "-p", pg], capture_output=True, text=True, cwd=tmp, timeout=600,
+                       env=dict(os.environ, SHMPI_NP="2", SHMPI_PIN="0"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    pc = synth.cu_param(tmp, name="cpu", extra=dict(eng_int=1, checkpt_int=40), **common_kw)
+    assert "MPI process array dimensions: 2 1 1" in r.stdout
+    pc = synth.cu_param(tmp, name="cpu", extra=dict(eng_int=1, checkpt_int=40, box_from_header=1), **common_kw)
     _run("imd_ref_serial_eam", pc, tmp)
     eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
     assert eg.shape == ec.shape and len(eg) == 41

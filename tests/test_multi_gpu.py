@@ -43,16 +43,22 @@ def test_two_domains_deformation_and_restrictions(built_lib, name):
 
 
 @pytest.mark.parametrize("name", ["cu_long", "nial_nvt"])
-def test_two_domains_peer_memory_halo(built_lib, name):
-    """The same fixtures with the halo exchanged by direct stores into the neighbour's ghost region and stream memory
-    operations instead of NCCL messages; separate processes anyway (torchrun)."""
-    _run("fixture:" + name, (2, 1, 1), 29620, env={"IMDB200_HALO_P2P": "1"})
+def test_two_domains_nccl_halo(built_lib, name):
+    """The halo is exchanged over peer memory by default (direct stores into the neighbour's ghost region, stream memory
+    operations as completion signal); IMDB200_HALO_P2P=0 keeps the NCCL messages: same fixtures."""
+    _run("fixture:" + name, (2, 1, 1), 29620, env={"IMDB200_HALO_P2P": "0"})
 
 
-def test_peer_memory_halo_in_the_device_resident_loop(built_lib):
-    """imdb200_run with the peer-memory halo: hot crystal, atoms migrate, buffers are re-planned at every rebuild; the
-    trajectory must equal the single-GPU one (the same check as test_atoms_migrate_between_domains)."""
-    _run("migration", (2, 1, 1), 29625, env={"IMDB200_HALO_P2P": "1"})
+def test_nccl_halo_in_the_device_resident_loop(built_lib):
+    """imdb200_run over NCCL messages (no overlap): hot crystal, atoms migrate; against the single-GPU trajectory."""
+    _run("migration", (2, 1, 1), 29625, env={"IMDB200_HALO_P2P": "0"})
+
+
+def test_overlapped_halo_matches_single_gpu_run(built_lib):
+    """The default multi-GPU loop: boundary warps first, their F' and new positions stored into the neighbours' ghost
+    regions while the interior warps run (imdb200_run, api.cu queue_step); 131 072 thermal Cu atoms, 60 steps with list
+    builds, against the same run on ONE GPU: positions, momenta, energies."""
+    _run("overlap", (2, 1, 1), 29626)
 
 
 @pytest.mark.parametrize("name", ["cu_big", "nial_big"])
@@ -81,6 +87,7 @@ def test_send_forces_reverse_path(built_lib):
 def test_four_domains(built_lib):
     _run("fixture:cu_long", (2, 2, 1), 29615)
     _run("migration", (2, 2, 1), 29616)
+    _run("overlap", (2, 2, 1), 29628)
 
 
 def test_eight_domains(built_lib):
@@ -88,3 +95,4 @@ def test_eight_domains(built_lib):
     _run("send_forces", (2, 2, 2), 29618)
     _run("fixture:cu_big", (2, 2, 2), 29623)
     _run("fixture:nial_big", (2, 2, 2), 29624)
+    _run("overlap", (2, 2, 2), 29627)
