@@ -13,6 +13,20 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <chrono>
+
+// IMDB200_DEBUG_REBUILD=1: wall-clock time of the sections of a list build on stderr (host waits included)
+static bool g_dbg_rebuild = getenv("IMDB200_DEBUG_REBUILD") != nullptr;
+struct RebuildClock {
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(imdb200_sim *s, const char *what) {
+    if (!g_dbg_rebuild) return;
+    cudaStreamSynchronize(s->stream);
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[rebuild rank %d] %-28s %8.3f ms\n", s->rank, what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
 
 // =====================================================================================================
 // host: box and cell grid
@@ -435,7 +449,7 @@ __device__ __forceinline__ double nbl_exact_r2(const BuildCtx &b, const Geom &g,
   return r2_exact(__dsub_rn(xj.x, b.xi.x), __dsub_rn(xj.y, b.xi.y), __dsub_rn(xj.z, b.xi.z));
 }
 
-template <int BS, bool W1>
+template <int BS, int WT>                                     // WT: words per cell as a compile-time constant (0: run time)
 __global__ void __launch_bounds__(BS)
 k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, int n_own, Geom g,
              const int *__restrict__ cellid, const int *__restrict__ cell_start, const int *__restrict__ cell_count,
@@ -444,7 +458,7 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
              int Wrt, float cutf, ClassT T, int *flags)
 {
   extern __shared__ unsigned bits[];                          // [27*W][BS]
-  const int W = W1 ? 1 : Wrt;                                 // the common case (cells of <= 32 atoms) without divisions
+  const int W = WT > 0 ? WT : Wrt;                            // cells of <= 32 / <= 64 atoms: no run-time divisions
   const int i = blockIdx.x * BS + threadIdx.x;
   int total = 0;
   if (i < n_own) {
@@ -610,15 +624,16 @@ static int launch_build(imdb200_sim *s, long n)
   if (s->cell_words < 1) s->cell_words = 1;
   const int W = s->cell_words;
   const size_t per_thread = (size_t) 27 * W * sizeof(unsigned);
-#define BUILD(BS, W1) do { \
+#define BUILD(BS, WT) do { \
     const size_t sm = per_thread * BS; \
-    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_build_nbl2<BS, W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm)); \
-    k_build_nbl2<BS, W1><<<cdiv(n > 0 ? n : 1, BS), BS, sm, st>>>(s->pos, s->posf, (int) n, g, s->cellid, s->cell_start, s->cell_count, \
+    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_build_nbl2<BS, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm)); \
+    k_build_nbl2<BS, WT><<<cdiv(n > 0 ? n : 1, BS), BS, sm, st>>>(s->pos, s->posf, (int) n, g, s->cellid, s->cell_start, s->cell_count, \
         s->cell_code, s->gsrc, s->ghost_raw, s->nbl, s->nnb, s->nnbc, max_nb, L, W, cutf, T, s->d_flags); \
     LAUNCH_CHECK(); } while (0)
-  if (W == 1) BUILD(128, true);
-  else if (per_thread * 128 <= 64 * 1024) BUILD(128, false);
-  else if (per_thread * 32 <= 200 * 1024) BUILD(32, false);
+  if (W == 1) BUILD(128, 1);
+  else if (W == 2) BUILD(128, 2);          // e.g. B2 Ni-Al: 17 atoms per cell on average, up to 54 where three lattice planes fall into a cell
+  else if (per_thread * 128 <= 64 * 1024) BUILD(128, 0);
+  else if (per_thread * 32 <= 200 * 1024) BUILD(32, 0);
   else return imdb_fail(IMDB200_ERR_CELLS, "cells of more than %d atoms do not fit the list build", 32 * W);
 #undef BUILD
   return 0;
@@ -754,7 +769,9 @@ int cells_rebuild(imdb200_sim *s)
   // ---- fix_cells: wrap into the box, bin, sort into cell order, hand atoms over to their new owners ----
   CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, FL_COUNT * sizeof(int), st));
   int *h_extra = s->h_starts;                 // pinned scratch: [0] atoms that stay, [1..28] extra bins
+  RebuildClock clk;
   TRY(bin_and_sort(s, s->n_own, s->need_filter, h_extra));
+  clk.lap(s, "bin_and_sort");
   long n = h_extra[0];
   s->need_filter = 0;
   if (s->nranks > 1) {
@@ -773,13 +790,16 @@ int cells_rebuild(imdb200_sim *s)
   s->n_own = n;
   if (s->nactive_dirty) TRY(cells_count_nactive(s));
   // ---- buffer cells: images of the boundary cells, ours or a neighbour's -----------------------------
+  clk.lap(s, "migrate");
   TRY(comm_setup_ghosts(s));
   TRY(comm_ghost_pos(s));
+  clk.lap(s, "ghost setup + positions");
   const int nb = cdiv(n > 0 ? n : 1, 256);
   // ---- make_nblist -------------------------------------------------------------------------------------
   const int L = s->lanes;
+  int overflow_max = 0;                         // largest per-atom count the build that overflowed has seen
   for (int attempt = 0; attempt < 3; attempt++) {
-    if (s->max_nb == 0 || attempt > 0) {
+    if (s->max_nb == 0) {
       // size the table from an exact count (estimate_nblist_size, src/imd_forces_nbl.c:74-128)
       CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
       k_build_nbl<<<cdiv(n, 128), 128, 0, st>>>(s->pos, n, g, s->cellid, s->cell_start, s->cell_count, s->cell_code,
@@ -787,18 +807,24 @@ int cells_rebuild(imdb200_sim *s)
       TRY(read_flags(s));
       int want = (int) (s->cfg.nbl_size * s->h_flags[FL_MAXNB]) + 2;
       TRY(alloc_nbl(s, want > 8 ? want : 8));
+    } else if (overflow_max > 0) {
+      // "neighbor table full": the build that overflowed has counted every atom's neighbours all the same
+      int want = (int) (s->cfg.nbl_size * overflow_max) + 2;
+      TRY(alloc_nbl(s, want > s->max_nb + 2 ? want : s->max_nb + 2));
     } else TRY(alloc_nbl(s, s->max_nb));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_MAXNB], 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_NBL_OVERFLOW], 0, sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(&s->d_flags[FL_CELLFULL], 0, sizeof(int), st));
     TRY(launch_build(s, n));
     TRY(read_flags(s));
+    clk.lap(s, "list build attempt");
     if (s->h_flags[FL_CELLFULL]) {               // a cell holds more atoms than the candidate bit words cover
       s->cell_words = (s->h_flags[FL_CELLFULL] + 31) / 32;
       attempt--;
       continue;
     }
     if (!s->h_flags[FL_NBL_OVERFLOW]) break;
+    overflow_max = s->h_flags[FL_MAXNB];
     if (attempt == 2) return imdb_fail(IMDB200_ERR_NBL, "neighbor table full - increase nbl_size");
   }
   // total list length (last_nbl_len, src/imd_forces_nbl.c:270)
@@ -811,7 +837,9 @@ int cells_rebuild(imdb200_sim *s)
   CUDA_TRY(cudaMemcpyAsync(&len, d_len, sizeof(len), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   s->nbl_len = (long long) len;
+  clk.lap(s, "length + nblpos");
   TRY(cells_build_worder(s));
+  clk.lap(s, "warp order");
   s->disp2 = 0.0;                 // NBL_POS == ORT
   TRY(step_snapshot_disp2(s, 1));
   s->skin_all = 0;

@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
   const double2 *pCD = T.pairCD, *rCD = T.rhoCD;           // cubic modes: (c2,c3)
   constexpr bool FUSED = EAM && !MULTI && SHARED && !CUB;  // one 48-byte record per interval, see DevTables::fused
   constexpr bool FAST1 = FUSED && TSMEM && !STRESS && !EE && IMDB_BRANCHFREE;   // the branch-free block body below
+  constexpr bool RAW = MULTI && TSMEM && !CUB;             // several species: raw samples of the distinct columns in shared memory
+  const double *rawP = nullptr, *rawR = nullptr;
   const unsigned s_tab = (unsigned) __cvta_generic_to_shared(smem_raw);
   const unsigned k_max = (unsigned) (T.fused_rows - 1);
   const double2 *fT = T.fused;
@@ -200,6 +202,14 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
     if (EAM) { stage(sAB + np, T.rhoAB, nr * 16); stage(sAB + 2 * np + nr, T.rhoCD, nr * 16); }
     __syncthreads();
     pAB = sAB; rAB = sAB + np; pCD = sAB + np + nr; rCD = sAB + 2 * np + nr;
+  } else if (TSMEM && RAW) {
+    // raw samples of the distinct columns: [phi (nrows+2) x nuP] [rho (nrows+2) x nuR], both padded to 16 bytes
+    const int npd = ((T.pair.nrows + 2) * T.nuP + 1) & ~1, nrd = EAM ? ((T.rho.nrows + 2) * T.nuR + 1) & ~1 : 0;
+    double *sP = reinterpret_cast<double *>(smem_raw);
+    stage(sP, T.rawP, npd * 8);
+    if (EAM) stage(sP + npd, T.rawR, nrd * 8);
+    __syncthreads();
+    rawP = sP; rawR = sP + npd;
   } else if (TSMEM) {
     // [phi (c0,c1)] [rho (c0,c1)] [phi c2] [rho c2]
     const int np = T.pair.nrows * T.pair.ncols, nr = EAM ? T.rho.nrows * T.rho.ncols : 0;
@@ -333,10 +343,19 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         if (FUSED) fmid = fT[3 * k + 1];                     // (phi c2, rho c2)
         if (inp) {
           const int e = MULTI ? k * T.pair.ncols + col : k;
-          const double2 ab = FUSED ? fT[3 * k] : pAB[e];
           double pot, grad;
+          if (RAW) {
+            // PAIR_INT2's own operands: p0, p1, p2 of rows k..k+2, dv = p1-p0, d2v = p2-2p1+p0 (src/potaccess.h:345-349);
+            // (c0,c1,c2) = (p0, dv - d2v/2, d2v/2) are what the coefficient tables hold, formed here with the same operations
+            const double *t = rawP + k * T.nuP + T.umapP[col];
+            const double p0 = t[0], p1 = t[T.nuP], p2 = t[2 * T.nuP];
+            const double c2 = 0.5 * ((p2 - 2 * p1) + p0), c1 = (p1 - p0) - c2;
+            pot = tab_val(make_double2(p0, c1), c2, chi); grad = tab_grad(make_double2(p0, c1), c2, chi, pis + pis);
+          } else {
+          const double2 ab = FUSED ? fT[3 * k] : pAB[e];
           if (CUB) { const double2 cd = pCD[e]; pot = tab_val3(ab, cd, chi); grad = tab_grad3(ab, cd, chi, pis + pis); }
           else { const double c2 = FUSED ? fmid.x : pC[e]; pot = tab_val(ab, c2, chi); grad = tab_grad(ab, c2, chi, pis + pis); }
+          }
           fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
           ee += pot;
           vir = fma(r2, grad, vir);
@@ -347,7 +366,13 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         if (inr) {
           const int e = MULTI ? kr * T.rho.ncols + col : kr;
           double rv;
-          if (CUB) rv = tab_val3(rAB[e], rCD[e], chir);
+          if (RAW) {
+            const double *t = rawR + kr * T.nuR + T.umapR[col];
+            const double p0 = t[0], p1 = t[T.nuR], p2 = t[2 * T.nuR];
+            const double c2 = 0.5 * ((p2 - 2 * p1) + p0), c1 = (p1 - p0) - c2;
+            rv = tab_val(make_double2(p0, c1), c2, chir);
+          }
+          else if (CUB) rv = tab_val3(rAB[e], rCD[e], chir);
           else rv = FUSED ? tab_val(fT[3 * kr + 2], fmid.y, chir) : tab_val(rAB[e], rC[e], chir);
           rh += rv;
           if (EE) ph = fma(rv, rv, ph);                      // eam_p += rho_h*rho_h (:591-593)

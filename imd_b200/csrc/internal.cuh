@@ -67,6 +67,13 @@ struct DevTables {
   int fused_rows;
   int have_eam, shared_grid, ntypes;
   int smem1, smem2;       // dynamic shared memory (bytes) to stage the pass-1 / pass-2 tables; 0 = leave in HBM/L1
+  // Several species, quadratic interpolation: pass 1 stages the RAW samples of the DISTINCT columns (phi_AB == phi_BA,
+  // rho depends on the neighbour's type only in standard EAM: 3 + 2 instead of 4 + 4 columns for two species), 8 bytes
+  // per sample instead of 24 per interval -- 80 KB for the 2001-row Ni-Al tables, which do not fit in coefficient form.
+  // The kernel forms dv, d2v from rows k, k+1, k+2 like PAIR_INT2 itself (src/potaccess.h:345-349).
+  const double *rawP, *rawR;          // [nrows+2][nuP], [nrows+2][nuR]
+  int nuP, nuR, raw_ok;               // distinct columns; raw_ok: smem1 holds the raw layout
+  signed char umapP[IMDB_MAXCOL], umapR[IMDB_MAXCOL];
 };
 
 // ---- geometry ------------------------------------------------------------------------------------

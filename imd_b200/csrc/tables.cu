@@ -240,10 +240,46 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
     T.fused_rows = nr;
     bytes1 = (size_t) nr * 48;
   }
+  if (nt > 1 && !cubic) {
+    // raw samples of the distinct columns (see DevTables::rawP): two columns are the same function when their headers
+    // and all their samples (pad rows included) agree bit for bit
+    auto distinct = [](const HostTab &h, signed char *umap, std::vector<double> &out) {
+      const imdb200_pot_table *pt = h.pt;
+      const int nc = pt->ncols; const size_t rows = (size_t) pt->maxsteps + 2;
+      int nu = 0, rep[IMDB_MAXCOL];
+      for (int c = 0; c < nc; c++) {
+        int u = -1;
+        for (int q = 0; q < nu && u < 0; q++) {
+          const int d = rep[q];
+          bool same = pt->begin[c] == pt->begin[d] && pt->end[c] == pt->end[d] && pt->invstep[c] == pt->invstep[d];
+          for (size_t r = 0; r < rows && same; r++) same = h.y[r * nc + c] == h.y[r * nc + d];
+          if (same) u = q;
+        }
+        if (u < 0) { u = nu; rep[nu++] = c; }
+        umap[c] = (signed char) u;
+      }
+      out.assign(rows * nu, 0.0);
+      for (size_t r = 0; r < rows; r++) for (int q = 0; q < nu; q++) out[r * nu + q] = h.y[r * nc + rep[q]];
+      return nu;
+    };
+    std::vector<double> rp, rr;
+    T.nuP = distinct(hp, T.umapP, rp);
+    if (rp.size() % 2) rp.push_back(0.0);                 // staged 16 bytes at a time
+    TRY(upload(s, 11, rp, &T.rawP));
+    size_t rawbytes = rp.size() * 8;
+    if (rho) {
+      T.nuR = distinct(hr, T.umapR, rr);
+      if (rr.size() % 2) rr.push_back(0.0);
+      // both raw blocks in one allocation slot would need a 13th slot: the rho block rides behind the fused slot (unused here)
+      TRY(upload(s, 6, rr, &T.rawR));
+      rawbytes += rr.size() * 8;
+    }
+    if (rawbytes <= 160 * 1024) { T.raw_ok = 1; bytes1 = rawbytes + 16; }
+  }
   // Tables are staged in shared memory when they leave at least ~100 KB of the 228 KB SM array to L1
   // (the position gathers live there); otherwise they stay in HBM and are served by L1/L2.
   const size_t limit = 128 * 1024;
-  T.smem1 = bytes1 <= limit ? (int) bytes1 : 0;
+  T.smem1 = (bytes1 <= limit || T.raw_ok) ? (int) bytes1 : 0;
   T.smem2 = (bytes2 && bytes2 <= limit) ? (int) bytes2 : 0;
   tables_set_cellsz0(s, cz);
   s->have_tabs = 1;
