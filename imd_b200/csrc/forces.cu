@@ -79,6 +79,10 @@
 #ifndef IMDB_EXP_NOGATHER
 #define IMDB_EXP_NOGATHER 0
 #endif
+// single-species pass 1 on raw table samples (32 KB of shared memory instead of 96 KB, eight more FP64 operations per pair)
+#ifndef IMDB_RAW1
+#define IMDB_RAW1 0
+#endif
 #ifdef IMDB_EXP_KCONST
 #define EXP_K(k) ((k) = 100 + ((k) & 1))
 #else
@@ -189,7 +193,10 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
   const unsigned s_tab = (unsigned) __cvta_generic_to_shared(smem_raw);
   const unsigned k_max = (unsigned) (T.fused_rows - 1);
   const double2 *fT = T.fused;
-  if (TSMEM && FUSED) {
+  if (TSMEM && FUSED && IMDB_RAW1 && FAST1) {
+    stage(smem_raw, T.fraw, (T.fused_rows + 2) * 16);
+    __syncthreads();
+  } else if (TSMEM && FUSED) {
     stage(smem_raw, T.fused, T.fused_rows * 48);
     __syncthreads();
     fT = reinterpret_cast<const double2 *>(smem_raw);
@@ -263,8 +270,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 #define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { const int j_ = jq[d]; \
           X[d] = j_ >= 0 ? make_double4(xi.x + 1.0 + (j_ & 7) * 0.3, xi.y + ((j_ >> 3) & 7) * 0.3, xi.z + ((j_ >> 6) & 7) * 0.3, xi.w) : xi; }
 #else
-#define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { \
-          if (jq[d] >= 0) X[d] = (d < IMDB_TEX1 && a.use_tex) ? ld_atom_tex(a.tpos, jq[d]) : ld_atom(a.pos + jq[d]); else X[d] = xi; }
+#define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { const int j_ = jq[d] >= 0 ? jq[d] : (int) i; \
+          X[d] = (d < IMDB_TEX1 && a.use_tex) ? ld_atom_tex(a.tpos, j_) : ld_atom(a.pos + j_); }
 #endif
 #if IMDB_DB
       // Double buffering: the gathers of block b+1 are in flight while block b is evaluated (its own were issued one
@@ -310,10 +317,20 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
             if (t < 0.0) { t = 0.0; if (inp || inr) is_short = 1; }
             const double tk = __dadd_rz(t, IMDB_TWO52);
             // entries beyond the cut-off index past the table: clamp the row (they are masked out below)
+#if IMDB_RAW1
+            const unsigned rec = s_tab + 16u * min((unsigned) __double2loint(tk), k_max);
+            const double chi = t - (tk - IMDB_TWO52);
+            const double2 q0 = lds2(rec), q1 = lds2(rec + 16), q2 = lds2(rec + 32);    // (phi, rho) of rows k, k+1, k+2
+            const double pc2 = 0.5 * ((q2.x - 2 * q1.x) + q0.x), pc1 = (q1.x - q0.x) - pc2;
+            const double rc2 = 0.5 * ((q2.y - 2 * q1.y) + q0.y), rc1 = (q1.y - q0.y) - rc2;
+            double pot = fma(chi, fma(chi, pc2, pc1), q0.x), grad = (p_is0 + p_is0) * fma(chi + chi, pc2, pc1),
+                   rv = fma(chi, fma(chi, rc2, rc1), q0.y);
+#else
             const unsigned rec = s_tab + 48u * min((unsigned) __double2loint(tk), k_max);
             const double chi = t - (tk - IMDB_TWO52);
             const double2 a0 = lds2(rec), a1 = lds2(rec + 16), a2 = lds2(rec + 32);    // (phi c0,c1) (phi c2, rho c2) (rho c0,c1)
             double pot = tab_val(a0, a1.x, chi), grad = tab_grad(a0, a1.x, chi, p_is0 + p_is0), rv = tab_val(a2, a1.y, chi);
+#endif
             pot = inp ? pot : 0.0; grad = inp ? grad : 0.0; rv = inr ? rv : 0.0;
             fx = fma(dx, grad, fx); fy = fma(dy, grad, fy); fz = fma(dz, grad, fz);
             ee += pot;
@@ -496,8 +513,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
 #else
 #define GATHER2(X, JC) _Pragma("unroll") for (int dd = 0; dd < FDEPTH2; dd++) { const int d = FDEPTH2 - 1 - dd; \
           const int j = jq[d] >= 0 ? jq[d] : (int) i; if (MULTI || EE) JC[d] = j; \
-          if (jq[d] >= 0) X[d] = (d >= FDEPTH2 - IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j); \
-          else X[d] = xi; }
+          X[d] = (d >= FDEPTH2 - IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j); }
 #endif
 #if IMDB_DB
       double4 xq[FDEPTH2];
@@ -798,7 +814,9 @@ template <typename K> static int launch_k(K kern, imdb200_sim *s, const FArgs &a
 template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 {
   const bool multi = s->tabs.ntypes > 1, ts = s->tabs.smem1 > 0;
-  const int sm = s->tabs.smem1;
+  // (the raw single-species layout is what the branch-free kernel instance stages: no stress, no EEAM terms)
+  const bool raw1 = IMDB_RAW1 && IMDB_BRANCHFREE && !multi && s->tabs.smem1_raw > 0 && s->tabs.fused && !s->press_calc && !EEAMC && !CUBIC;
+  const int sm = raw1 ? s->tabs.smem1_raw : s->tabs.smem1;
 #if IMDB_EEAM
   if (!s->tabs.have_eam) return imdb_fail(IMDB200_ERR_ARG, "EEAM needs EAM tables");
 #else

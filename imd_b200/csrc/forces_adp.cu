@@ -1,9 +1,8 @@
 // forces_adp.cu -- the angular-dependent terms of ADP builds (`#ifdef ADP` branches of calc_forces,
 // src/imd_forces_nbl.c:613-631, 919-929, 1096-1110, 1217-1255; tables adp_upot / adp_wpot, src/imd_potential.c:87-92).
 //
-// STATUS: written after this round's GPU minutes were spent -- compiles for sm_100a, the CPU restatement of the same
-// branches reproduces the reference's `adp` build, but these kernels have not run on a GPU
-// yet; tests/test_gpu_parity.py::test_cuda_adp_matches_reference_fixture is xfail(strict=False) until they have.
+// STATUS: green on B200 against fixtures of the reference's `adp` build, Cu and Ni-Al
+// (tests/test_gpu_parity.py::test_cuda_adp_matches_reference_fixture).
 //
 // The terms ride on top of the EAM passes as two kernels of their own, so the benchmark kernels are untouched:
 //   k_adp_pass1  after pass 1:  mu_i = sum_j u(r_ij) d_ij,  lambda_i = sum_j w(r_ij) d_ij (x) d_ij  (full list: every

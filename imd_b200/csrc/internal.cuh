@@ -65,6 +65,8 @@ struct DevTables {
   const double2 *fused;   // single species, phi and rho on one r^2 grid: [nrows][3] = (phi c0,c1) (phi c2, rho c2) (rho c0,c1),
                           // one 48-byte record per interval = three 16-byte loads per pair in pass 1
   int fused_rows;
+  const double2 *fraw;    // the same single-species case as raw samples: [fused_rows+2] = (phi_k, rho_k), 16 bytes per row
+  int smem1_raw;
   int have_eam, shared_grid, ntypes;
   int smem1, smem2;       // dynamic shared memory (bytes) to stage the pass-1 / pass-2 tables; 0 = leave in HBM/L1
   // Several species, quadratic interpolation: pass 1 stages the RAW samples of the DISTINCT columns (phi_AB == phi_BA,

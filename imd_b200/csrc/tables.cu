@@ -239,6 +239,14 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
     TRY(upload(s, 6, f, &T.fused));
     T.fused_rows = nr;
     bytes1 = (size_t) nr * 48;
+    // raw samples (phi_k, rho_k), pad rows included: a third of the shared memory, eight more FP64 operations per pair
+    std::vector<double2> fr((size_t) nr + 2, make_double2(0.0, 0.0));
+    for (int k = 0; k < nr + 2; k++) {
+      if (k < pair->maxsteps + 2) fr[k].x = hp.y[(size_t) k];
+      if (k < rho->maxsteps + 2) fr[k].y = hr.y[(size_t) k];
+    }
+    TRY(upload(s, 11, fr, &T.fraw));
+    T.smem1_raw = (int) (fr.size() * 16);
   }
   if (nt > 1 && !cubic) {
     // raw samples of the distinct columns (see DevTables::rawP): two columns are the same function when their headers

@@ -17,6 +17,18 @@
  *
  * Threading: one host thread (or process) per simulation handle / GPU, like one MPI rank per
  * domain in the reference.  Handles are independent.
+ *
+ * Numerical contract (BASELINE.json north_star; tests/common.py holds the bars):
+ *   bit-exact   the neighbour SET (every pair is tested with the reference's operands and rounding:
+ *               r2 = (dx*dx + dy*dy) + dz*dz without FMA, image positions added stage by stage), the cell grid,
+ *               the rebuild decisions of check_nblist and therefore nbl_count
+ *   <= 1e-10    forces, per-atom energies, rho, F', stress, Epot, virial, Ekin, eta -- per component, relative, with an
+ *               absolute floor of 1e-12 of the largest component.  Inside the force loops two operations deliberately
+ *               depart from the reference's rounding: r2 is formed with FMAs, and the table index (r2 - begin)*invstep
+ *               is one FMA (tab_index_fast, csrc/internal.cuh).  Both move k/chi only when the argument lies within an
+ *               ulp of a table node, where the interpolant is continuous: values change by ~1e-16 relative.  Sums run in
+ *               a different order than the reference's half list (every atom gathers its own full list): ~1e-13.
+ *   run to run  results are bit-reproducible (no floating-point atomics on any result; fixed reduction orders).
  */
 #ifndef IMD_B200_H
 #define IMD_B200_H
@@ -119,7 +131,8 @@ long imdb200_get_eeam(imdb200_sim *sim, double *eam_p, double *eam_dM);
 /* ADP builds (make targets with `adp`): dipole and quadrupole distortion functions u(r), w(r) -- adp_upot and
  * adp_wpot, read from `adp_upotfile` / `adp_wpotfile` with ntypes^2 columns in r^2 (src/imd_potential.c:87-92).
  * Call after imdb200_set_potentials; NULL, NULL switches the terms off.  Replaces the `#ifdef ADP` branches of
- * calc_forces (src/imd_forces_nbl.c:613-631, 919-929, 1096-1110, 1217-1255).  NOT YET RUN ON A GPU. */
+ * calc_forces (src/imd_forces_nbl.c:613-631, 919-929, 1096-1110, 1217-1255).  Green on B200 against the reference's `adp`
+ * build (tests/test_gpu_parity.py::test_cuda_adp_matches_reference_fixture). */
 int  imdb200_set_adp_tables(imdb200_sim *sim, const imdb200_pot_table *u, const imdb200_pot_table *w);
 /* ADP_MU [n][3] and ADP_LAMBDA [n][6] = xx yy zz yz zx xy of the owned atoms, in the order of imdb200_get_atoms */
 long imdb200_get_adp(imdb200_sim *sim, double *mu3, double *lambda6);
