@@ -64,10 +64,13 @@ struct orc_sim {
   /* NPT_iso (src/imd_integrate.c:1472-1729): barostat friction xi, twice the kinetic energy of the previous step,
      external pressure and its per-step increment, 1/tau_xi^2, the pressure the last step used */
   double xi, Ekin_old, pressure_ext, d_pressure, isq_tau_xi, pressure;
+  /* NPT_axial (src/imd_integrate.c:1747-1959): one barostat per axis; Ekin_old and isq_tau_xi are shared with NPT_iso */
+  double xi3[3], stress3[3], pext3[3], dpext3[3], dyn3[3]; int relax_dirs[3];
   double tauber;       /* > 0: Berendsen variant of NVE (`ber` builds, src/imd_integrate.c:44-53, 341-350) */
   int nvtypes; double *restr;
   /* results */
   double tot_pot_energy, tot_kin_energy, virial;
+  double vir[3];       /* vir_xx, vir_yy, vir_zz: what P_AXIAL builds accumulate instead of the scalar virial (src/imd_forces_nbl.c:548-556) */
   long nactive;
   int is_short;
 };
@@ -712,7 +715,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
   else send_cells_pos(s, 0);                                                          /* :314 */
   ntot = s->n + s->ng;
 
-  s->tot_pot_energy = 0.0; s->virial = 0.0; /* :319-331 */
+  s->tot_pot_energy = 0.0; s->virial = 0.0; s->vir[0] = s->vir[1] = s->vir[2] = 0.0; /* :319-331 */
   for (a = 0; a < ntot; a++) {              /* :333-401 */
     s->kraft[3 * a] = s->kraft[3 * a + 1] = s->kraft[3 * a + 2] = 0.0;
     for (i = 0; i < 6; i++) s->presstens[6 * a + i] = 0.0;
@@ -750,6 +753,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
           pot *= 0.5;
           ee += pot; s->poteng[ja] += pot;
           s->virial -= r2 * grad;
+          s->vir[0] -= dx * fx; s->vir[1] -= dy * fy; s->vir[2] -= dz * fz;   /* P_AXIAL :548-553 */
           if (do_press_calc) { /* :558-581 */
             fx *= 0.5; fy *= 0.5; fz *= 0.5;
             pp[0] -= dx * fx; s->presstens[6 * ja] -= dx * fx;         /* xx */
@@ -896,6 +900,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
             s->kraft[3 * ja] -= fx; s->kraft[3 * ja + 1] -= fy; s->kraft[3 * ja + 2] -= fz;
             ffx += fx; ffy += fy; ffz += fz;
             s->virial -= ((dx * fx) + (dy * fy)) + (dz * fz); /* :1280 */
+            s->vir[0] -= dx * fx; s->vir[1] -= dy * fy; s->vir[2] -= dz * fz;   /* P_AXIAL :1275-1279 */
             if (do_press_calc) { /* :1283-1304 */
               fx *= 0.5; fy *= 0.5; fz *= 0.5;
               pp[0] -= dx * fx; pp[1] -= dy * fy; pp[2] -= dz * fz;
@@ -925,6 +930,7 @@ void orc_calc_forces(orc_sim *s, int do_press_calc)
    visited in cell-traversal order like the reference so that the energy sums round alike */
 static void calc_dyn_pressure(orc_sim *s);
 static void move_atoms_npt_iso(orc_sim *s, int do_press_calc);
+static void move_atoms_npt_axial(orc_sim *s, int do_press_calc);
 
 void orc_move_atoms(orc_sim *s, int do_press_calc)
 {
@@ -933,6 +939,15 @@ void orc_move_atoms(orc_sim *s, int do_press_calc)
   if (s->ensemble == ORC_NPT_ISO) {
     if (s->Ekin_old < 0.0) { calc_dyn_pressure(s); if (s->isq_tau_xi == 0.0) s->xi = 0.0; }   /* :1493-1496 */
     move_atoms_npt_iso(s, do_press_calc);
+    return;
+  }
+  if (s->ensemble == ORC_NPT_AXIAL) {
+    if (s->Ekin_old < 0.0) {                                                          /* steps == steps_min :1756-1771 */
+      int d;
+      calc_dyn_pressure(s);
+      for (d = 0; d < 3; d++) { if (s->isq_tau_xi == 0.0) s->xi3[d] = 0.0; s->xi3[d] *= s->relax_dirs[d]; }
+    }
+    move_atoms_npt_axial(s, do_press_calc);
     return;
   }
   double cc = 1.0;
@@ -997,6 +1012,7 @@ static void calc_dyn_pressure(orc_sim *s)
       sx += P[0] * P[0] * tmp; sy += P[1] * P[1] * tmp; sz += P[2] * P[2] * tmp;
     }
   }
+  s->dyn3[0] = sx; s->dyn3[1] = sy; s->dyn3[2] = sz;
   s->Ekin_old = sx + sy; s->Ekin_old += sz;
 }
 
@@ -1041,6 +1057,71 @@ static void move_atoms_npt_iso(orc_sim *s, int do_press_calc)
   s->box_x.z *= ttt; s->box_y.z *= ttt; s->box_z.x *= ttt; s->box_z.y *= ttt; s->box_z.z *= ttt;
   make_box(s);
   s->pressure_ext += s->d_pressure;                                                  /* :1727 */
+}
+
+/* move_atoms_npt_axial, src/imd_integrate.c:1747-1959 */
+static void move_atoms_npt_axial(orc_sim *s, int do_press_calc)
+{
+  int c, i, d; const double dt = s->timestep;
+  double Ekin_new = 0.0, pfric[3], pifric[3], rfric[3], rifric[3], xi_old[3], ttt, tvec[3], dyn[3] = {0.0, 0.0, 0.0};
+  for (d = 0; d < 3; d++) s->stress3[d] = (s->dyn3[d] + s->vir[d]) / s->volume;      /* :1775-1779 */
+  ttt = dt * s->volume * s->isq_tau_xi / s->nactive;                                 /* :1782 */
+  for (d = 0; d < 3; d++) {
+    xi_old[d] = s->xi3[d]; s->xi3[d] += ttt * (s->stress3[d] - s->pext3[d]) * s->relax_dirs[d];   /* :1783-1787 */
+    pfric[d]  =        1.0 - (xi_old[d] + s->eta) * dt / 2.0;                        /* :1790-1803 */
+    pifric[d] = 1.0 / (1.0 + (s->xi3[d] + s->eta) * dt / 2.0);
+    rfric[d]  =        1.0 + (s->xi3[d]         ) * dt / 2.0;
+    rifric[d] = 1.0 / (1.0 - (s->xi3[d]         ) * dt / 2.0);
+  }
+  for (c = 0; c < s->ncells; c++) {
+    cellist *p = &s->cells[s->cnp[c]];
+    for (i = 0; i < p->n; i++) {
+      long a = p->idx[i];
+      double *P = s->impuls + 3 * a, *F = s->kraft + 3 * a, *X = s->ort + 3 * a, tmp = 1.0 / s->masse[a];
+      const double *R = s->restr + 3 * s->vsorte[a];
+      if (do_press_calc) {                                                           /* :1834-1845: before the kick */
+        double *S = s->presstens + 6 * a;
+        S[0] += P[0] * P[0] * tmp; S[1] += P[1] * P[1] * tmp; S[2] += P[2] * P[2] * tmp;
+        S[3] += P[1] * P[2] * tmp; S[4] += P[2] * P[0] * tmp; S[5] += P[0] * P[1] * tmp;
+      }
+      for (d = 0; d < 3; d++) {
+        P[d] = (pfric[d] * P[d] + dt * F[d]) * pifric[d];                            /* :1848-1855 */
+        P[d] *= R[d];                                                                /* :1859-1864 */
+      }
+      dyn[0] += P[0] * P[0] * tmp; dyn[1] += P[1] * P[1] * tmp; dyn[2] += P[2] * P[2] * tmp;   /* :1868-1872 */
+      Ekin_new += (((P[0] * P[0]) + (P[1] * P[1])) + (P[2] * P[2])) * tmp;           /* :1875 */
+      tmp *= dt;
+      for (d = 0; d < 3; d++) X[d] = (rfric[d] * X[d] + P[d] * tmp) * rifric[d];     /* :1878-1883 */
+    }
+  }
+  for (d = 0; d < 3; d++) s->dyn3[d] = dyn[d];
+  s->tot_kin_energy = (s->Ekin_old + Ekin_new) / 4.0;                                /* :1917 */
+  ttt = s->nactive * s->temperature;
+  s->eta += dt * (Ekin_new / ttt - 1.0) * s->isq_tau_eta;
+  s->Ekin_old = Ekin_new;
+  for (d = 0; d < 3; d++) tvec[d] = (1.0 + s->xi3[d] * dt / 2.0) / (1.0 - s->xi3[d] * dt / 2.0);   /* :1923-1937 */
+  s->box_x.x *= tvec[0]; s->box_x.y *= tvec[0]; s->box_y.x *= tvec[1]; s->box_y.y *= tvec[1];
+  s->box_x.z *= tvec[0]; s->box_y.z *= tvec[1]; s->box_z.x *= tvec[2]; s->box_z.y *= tvec[2]; s->box_z.z *= tvec[2];
+  make_box(s);
+  for (d = 0; d < 3; d++) s->pext3[d] += s->dpext3[d];                               /* :1955-1959 */
+}
+
+/* NPT_axial hand-over; Ekin_old < 0: the next move_atoms starts like steps == steps_min (calc_dyn_pressure, xi *= relax_dirs) */
+void orc_set_npt_axial(orc_sim *s, const double *xi3, const double *pext3, const double *dpext3, const int *relax_dirs,
+                       double Ekin_old, const double *dyn3, double isq_tau_xi)
+{
+  int d;
+  for (d = 0; d < 3; d++) { s->xi3[d] = xi3[d]; s->pext3[d] = pext3[d]; s->dpext3[d] = dpext3[d]; s->relax_dirs[d] = relax_dirs[d];
+                            s->dyn3[d] = dyn3 ? dyn3[d] : 0.0; }
+  s->Ekin_old = Ekin_old; s->isq_tau_xi = isq_tau_xi;
+}
+
+/* out13 = xi[3], stress[3] of the last step, pressure_ext[3], dyn_stress[3], Ekin_old */
+void orc_get_npt_axial(const orc_sim *s, double *out13)
+{
+  int d;
+  for (d = 0; d < 3; d++) { out13[d] = s->xi3[d]; out13[3 + d] = s->stress3[d]; out13[6 + d] = s->pext3[d]; out13[9 + d] = s->dyn3[d]; }
+  out13[12] = s->Ekin_old;
 }
 
 /* NPT_iso state: after a restart-like hand-over all of it comes from the caller; a fresh run calls it with
@@ -1226,6 +1307,7 @@ void orc_get_scalars(const orc_sim *s, double out[14])
 {
   int i; for (i = 0; i < 14; i++) out[i] = 0.0;
   out[0] = s->tot_pot_energy; out[1] = s->tot_kin_energy; out[2] = s->virial;
+  out[3] = s->vir[0]; out[4] = s->vir[1]; out[5] = s->vir[2];
   out[9] = s->volume; out[10] = (double) s->nactive; out[11] = s->eta;
   out[12] = s->temperature; out[13] = s->timestep;
 }

@@ -18,7 +18,7 @@ typedef struct orc_sim orc_sim;
 
 /* which table: 0 = pair_pot (radial), 1 = embed_pot (not radial), 2 = rho_h_tab (radial) */
 enum { ORC_PAIR = 0, ORC_EMBED = 1, ORC_RHO = 2, ORC_EMOD = 3, ORC_ADP_U = 4, ORC_ADP_W = 5 };  /* 3: emod_pot of EEAM builds (not radial) */
-enum { ORC_NVE = 0, ORC_NVT = 1, ORC_NPT_ISO = 2 };
+enum { ORC_NVE = 0, ORC_NVT = 1, ORC_NPT_ISO = 2, ORC_NPT_AXIAL = 3 };
 /* table interpolation a reference build selects at compile time (src/potaccess.h:24-36, src/Makefile:1694-1701) */
 enum { ORC_INTERP_3POINT = 0, ORC_INTERP_4POINT = 1, ORC_INTERP_SPLINE = 2 };
 
@@ -44,6 +44,11 @@ void orc_set_integrator(orc_sim *s, int ensemble, double timestep, double temper
  * the first step, like steps == steps_min), pressure_ext, its per-step increment, 1/tau_xi^2 */
 void orc_set_npt(orc_sim *s, double xi, double Ekin_old, double pressure_ext, double d_pressure, double isq_tau_xi);
 void orc_get_npt(const orc_sim *s, double out[4]);
+/* NPT_axial (move_atoms_npt_axial, src/imd_integrate.c:1747-1959): per-axis xi, pressure_ext, its per-step increment, relax_dirs,
+ * Ekin_old (< 0: steps == steps_min), dyn_stress_x/y/z the previous step left; out13 = xi, stress, pressure_ext, dyn_stress, Ekin_old */
+void orc_set_npt_axial(orc_sim *s, const double *xi3, const double *pext3, const double *dpext3, const int *relax_dirs,
+                       double Ekin_old, const double *dyn3, double isq_tau_xi);
+void orc_get_npt_axial(const orc_sim *s, double *out13);
 /* `ber` builds: Berendsen scaling of the momenta inside move_atoms_nve (src/imd_integrate.c:44-53, 341-350) */
 void orc_set_berendsen(orc_sim *s, double tauber, double tot_kin_energy);      /* xi, Ekin_old, pressure of the last step, pressure_ext */
 void orc_set_box(orc_sim *s, const double box[9]);        /* make_box, src/imd_geom_3d.c:52-104 */

@@ -71,6 +71,8 @@ def lib():
         L.orc_set_interpolation.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_npt.argtypes = [C.c_void_p] + [C.c_double] * 5
         L.orc_get_npt.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_npt_axial.argtypes = [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_double]
+        L.orc_get_npt_axial.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_berendsen.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.orc_get_eeam.restype = C.c_long
         L.orc_get_adp.restype = C.c_long
@@ -117,11 +119,24 @@ class OracleIMD:
         lib().orc_set_atoms(self.h, n, *[None if x is None else x.ctypes.data for x in a])
 
     def set_integrator(self, ensemble="nve", timestep=0.001, temperature=0.0, eta=0.0, isq_tau_eta=0.0):
-        ens = {"nve": NVE, "nvt": NVT, "npt_iso": 2}[str(ensemble).lower()]
+        ens = {"nve": NVE, "nvt": NVT, "npt_iso": 2, "npt_axial": 3}[str(ensemble).lower()]
         lib().orc_set_integrator(self.h, ens, timestep, temperature, eta, isq_tau_eta)
 
     def set_npt(self, xi=0.0, Ekin_old=-1.0, pressure_ext=0.0, d_pressure=0.0, isq_tau_xi=0.0):
         lib().orc_set_npt(self.h, float(xi), float(Ekin_old), float(pressure_ext), float(d_pressure), float(isq_tau_xi))
+
+    def set_npt_axial(self, xi, pressure_ext, d_pressure, relax_dirs=(1, 1, 1), Ekin_old=-1.0, dyn_stress=None, isq_tau_xi=0.0):
+        v = [np.ascontiguousarray(x, np.float64) for x in (xi, pressure_ext, d_pressure)]
+        rd = np.ascontiguousarray(relax_dirs, np.int32)
+        dy = None if dyn_stress is None else np.ascontiguousarray(dyn_stress, np.float64)
+        lib().orc_set_npt_axial(self.h, v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data, rd.ctypes.data, float(Ekin_old),
+                                None if dy is None else dy.ctypes.data, float(isq_tau_xi))
+
+    def npt_axial(self):
+        out = np.zeros(13)
+        lib().orc_get_npt_axial(self.h, out.ctypes.data)
+        return dict(xi=out[0:3].copy(), stress=out[3:6].copy(), pressure_ext=out[6:9].copy(), dyn_stress=out[9:12].copy(),
+                    Ekin_old=float(out[12]))
 
     def set_berendsen(self, tauber, tot_kin_energy=0.0):
         lib().orc_set_berendsen(self.h, float(tauber), float(tot_kin_energy))

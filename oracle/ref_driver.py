@@ -46,9 +46,10 @@ class RefIMD:
         L.ref_get_nbl_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.ref_pair_int.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ref_set_eta.argtypes = [C.c_double]
-        self.has_eam = variant.startswith("eam") or variant in ("eeam", "npt", "adp", "ber")
+        self.has_eam = variant.startswith("eam") or variant in ("eeam", "npt", "npt_axial", "adp", "ber")
         self.has_eeam = variant == "eeam"
         self.has_npt = variant == "npt"
+        self.has_npt_axial = variant == "npt_axial"
         self.has_adp = variant == "adp"
         L.ref_get_adp.restype = C.c_long
         L.ref_get_eeam.restype = C.c_long
@@ -121,6 +122,12 @@ class RefIMD:
         out = np.zeros(5)
         self.lib.ref_get_npt(_p(out, C.c_double))
         return dict(zip(("xi", "Ekin_old", "pressure", "pressure_ext", "isq_tau_xi"), out.tolist()))
+
+    def npt_axial(self):
+        out = np.zeros(16)
+        self.lib.ref_get_npt_axial(_p(out, C.c_double))
+        return dict(xi=out[0:3].copy(), stress=out[3:6].copy(), pressure_ext=out[6:9].copy(), dyn_stress=out[9:12].copy(),
+                    Ekin_old=float(out[12]), relax_dirs=out[13:16].astype(np.int32))
 
     def set_eta(self, eta):
         self.lib.ref_set_eta(float(eta))
@@ -218,6 +225,8 @@ def run_protocol(sim, spec):
     out["start"] = sim.atoms()
     if getattr(sim, "has_npt", False):
         out["npt_start"] = sim.npt()
+    if getattr(sim, "has_npt_axial", False):
+        out["npt_axial_start"] = sim.npt_axial()
     out["nbl_count0"] = sim.nbl_count      # builds before the protocol (thermalisation); the protocol's share = nbl_count - this
     out["box"] = sim.box()
     out["celldims"] = sim.celldims()
@@ -243,6 +252,8 @@ def run_protocol(sim, spec):
         fr["after"] = sim.scalars()
         if getattr(sim, "has_npt", False):
             fr["npt"] = sim.npt(); fr["box"] = sim.box()
+        if getattr(sim, "has_npt_axial", False):
+            fr["npt_axial"] = sim.npt_axial(); fr["box"] = sim.box()
         fr["valid"] = sim.have_valid_nbl
         if spec.get("press", False) and s in spec.get("record_atoms", [0]):
             fr["tot_presstens"] = sim.tot_presstens()

@@ -166,6 +166,22 @@ void ref_get_npt(double *out5)
 #endif
 }
 
+/* NPT_axial state (src/globals.h:565-574, 627): xi, stress_x/y/z of the last move_atoms, pressure_ext, dyn_stress_x/y/z
+   (the kinetic part the next move_atoms starts from), Ekin_old, relax_dirs */
+void ref_get_npt_axial(double *out16)
+{
+#ifdef NPT_axial
+  out16[0] = xi.x; out16[1] = xi.y; out16[2] = xi.z;
+  out16[3] = stress_x; out16[4] = stress_y; out16[5] = stress_z;
+  out16[6] = pressure_ext.x; out16[7] = pressure_ext.y; out16[8] = pressure_ext.z;
+  out16[9] = dyn_stress_x; out16[10] = dyn_stress_y; out16[11] = dyn_stress_z;
+  out16[12] = Ekin_old;
+  out16[13] = relax_dirs.x; out16[14] = relax_dirs.y; out16[15] = relax_dirs.z;
+#else
+  int i; for (i = 0; i < 16; i++) out16[i] = 0.0;
+#endif
+}
+
 /* EEAM per-atom fields (src/imd_forces_nbl.c:591-610, 1090-1095), same order as ref_get_atoms */
 long ref_get_eeam(double *eam_p, double *eam_dM)
 {

@@ -119,6 +119,56 @@ def test_oracle_npt_iso_matches_reference_fixture(tmp_path):
     assert np.max(np.abs(a["impuls"] - g["final:impuls"])) <= 1e-9 * np.max(np.abs(g["final:impuls"]))
 
 
+@pytest.mark.parametrize("case", ["cu_npt_axial", "cu_npt_axial_xz"])
+def test_oracle_npt_axial_matches_reference_fixture(case, tmp_path):
+    """move_atoms_npt_axial (src/imd_integrate.c:1747-1959) of the reference's `npt_axial` build: one barostat variable per
+    box axis driven by (dyn_stress + vir)/volume of that axis (P_AXIAL builds accumulate vir_xx/yy/zz in calc_forces,
+    src/imd_forces_nbl.c:548-556), a pressure ramp that differs per axis, and relax_dirs 1 0 1 holding the y axis."""
+    g = common.load_golden(case)
+    paths = common.write_tables(g, str(tmp_path))
+    sim = orc.OracleIMD(1, g["box"], pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
+    sim.set_integrator("npt_axial", float(g["timestep"]), float(g["temperature"]), float(g["eta0"]), float(g["isq_tau_eta"]))
+    sim.set_npt_axial(g["npt_start:xi"], g["npt_start:pressure_ext"], g["npt_start:d_pressure"], g["npt_start:relax_dirs"],
+                      Ekin_old=float(g["npt_start:Ekin_old"]), dyn_stress=g["npt_start:dyn_stress"],
+                      isq_tau_xi=float(g["npt_start:isq_tau_xi"]))
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"])
+    press = bool(int(g["press"]))
+    sim.set_press_calc(press)
+    for s in range(int(g["nsteps"])):
+        sim.calc_forces(s)
+        sc = sim.scalars()
+        tol = 1e-13 if s == 0 else 1e-10
+        assert abs(sc["tot_pot_energy"] - g["epot"][s]) <= tol * abs(g["epot"][s]), s
+        vir = np.array([sc["vir_xx"], sc["vir_yy"], sc["vir_zz"]])
+        assert np.max(np.abs(vir - g["npt:vir"][s])) <= tol * 10 * np.max(np.abs(g["npt:vir"][s])), s
+        if s == 0:
+            assert common.relerr(sim.atoms()["kraft"], g["f0:kraft"]) <= 1e-13
+        rec = press and s in [int(x) for x in g["record"]]
+        if rec:      # virial part of the per-atom tensor (recorded between calc_forces and move_atoms)
+            assert common.relerr(sim.atoms()["presstens"], g[f"f{s}:presstens"]) <= 10 * tol
+        sim.move_atoms()
+        sim.check_nblist()
+        if rec:      # plus the kinetic part, which this integrator adds from the momenta BEFORE the kick (:1834-1845)
+            assert common.relerr(sim.tot_presstens(), g[f"f{s}:tot_presstens"]) <= 10 * tol
+        st, sc = sim.npt_axial(), sim.scalars()
+        for k in ("xi", "stress", "pressure_ext", "dyn_stress"):
+            assert np.max(np.abs(st[k] - g["npt:" + k][s])) <= tol * 10 * np.max(np.abs(g["npt:" + k][s])), (k, s)
+        assert abs(sc["volume"] - g["npt:volume"][s]) <= 1e-13 * g["npt:volume"][s], s
+        assert abs(sc["eta"] - g["eta"][s]) <= tol * 10 * abs(g["eta"][s]), s
+        assert abs(sc["tot_kin_energy"] - g["ekin"][s]) <= tol * abs(g["ekin"][s]), s
+        assert np.max(np.abs(sim.box() - g["npt:box"][s])) <= 1e-13 * np.max(np.abs(g["npt:box"][s])), s
+        assert sim.have_valid_nbl == int(g["valid"][s]), f"check_nblist decision differs at step {s}"
+    if case.endswith("_xz"):          # the held axis did not move
+        assert sim.box()[1, 1] == g["box"][1, 1] and np.all(g["npt:xi"][:, 1] == 0.0)
+    a = sim.atoms()
+    box = sim.box()
+    d = a["ort"] - g["final:ort"]
+    frac = d @ np.linalg.inv(box)
+    d = (frac - np.round(frac)) @ box
+    assert np.max(np.abs(d)) <= 1e-9 * np.max(np.abs(box))
+    assert np.max(np.abs(a["impuls"] - g["final:impuls"])) <= 1e-9 * np.max(np.abs(g["final:impuls"]))
+
+
 def test_oracle_berendsen_matches_reference_fixture(tmp_path):
     """`ber` builds: Berendsen scaling of the momenta inside move_atoms_nve (src/imd_integrate.c:44-53, 341-350),
     driven by the kinetic energy of the PREVIOUS step.  Oracle only so far."""

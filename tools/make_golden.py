@@ -76,6 +76,16 @@ CASES = {
     "cu_npt_iso": dict(kind="cu", ncell=(6, 6, 6), ensemble="npt_iso", starttemp=0.08, warm=25, nsteps=40,
                        record=[0, 39], press=False, variant="npt",
                        extra=dict(endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.5, pressure_start=0.02, pressure_end=0.02)),
+    # `npt_axial` reference build: one barostat per box axis, driven by (dyn_stress + vir)/volume per axis; a pressure
+    # ramp that differs per axis, and a second case with the y axis held (relax_dirs 1 0 1)
+    "cu_npt_axial": dict(kind="cu", ncell=(6, 6, 6), ensemble="npt_axial", starttemp=0.08, warm=25, nsteps=40,
+                         record=[0, 39], press=False, variant="npt_axial",
+                         extra=dict(endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.5, pressure_start=[0.02, 0.01, 0.03],
+                                    pressure_end=[0.03, 0.01, 0.02], maxsteps=100)),
+    "cu_npt_axial_xz": dict(kind="cu", ncell=(6, 5, 6), ensemble="npt_axial", starttemp=0.08, warm=25, nsteps=30,
+                            record=[0, 29], press=True, variant="npt_axial",
+                            extra=dict(endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.4, pressure_start=[0.0, 0.0, 0.02],
+                                       pressure_end=[0.0, 0.0, 0.02], relax_dirs=[1, 0, 1], maxsteps=100)),
     # `adp` reference build (angular-dependent potential).  Oracle fixtures only so far, like cu_npt_iso
     "cu_adp": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=30, nsteps=12,
                    record=[0, 11], press=True, variant="adp", adp=True),
@@ -184,7 +194,7 @@ def make_case(name, c):
     sc0 = out["frames"][0]["scalars"]
     g["timestep"] = sc0["timestep"]; g["temperature"] = sc0["temperature"]; g["eta0"] = sc0["eta"]
     g["nactive"] = sc0["nactive"]
-    g["isq_tau_eta"] = 1.0 / 0.1 ** 2 if c["ensemble"] in ("nvt", "npt_iso") else 0.0
+    g["isq_tau_eta"] = 1.0 / 0.1 ** 2 if c["ensemble"] in ("nvt", "npt_iso", "npt_axial") else 0.0
     if c["variant"] == "ber":
         g["tau_berendsen"] = c["extra"]["tau_berendsen"]
         g["ekin_start"] = out["frames"][0]["scalars"]["tot_kin_energy"]      # what the last warm-up step left
@@ -196,6 +206,20 @@ def make_case(name, c):
         g["npt:pressure"] = np.array([f["npt"]["pressure"] for f in out["frames"]])
         g["npt:volume"] = np.array([f["after"]["volume"] for f in out["frames"]])
         g["npt:box"] = np.array([f["box"] for f in out["frames"]])
+    if c["variant"] == "npt_axial":
+        st = out["npt_axial_start"]
+        for k, v in st.items():
+            g["npt_start:" + k] = v
+        g["npt_start:isq_tau_xi"] = 1.0 / c["extra"]["tau_xi"] ** 2
+        fr = out["frames"]
+        for k in ("xi", "stress", "pressure_ext", "dyn_stress"):
+            g["npt:" + k] = np.array([f["npt_axial"][k] for f in fr])
+        g["npt:Ekin_old"] = np.array([f["npt_axial"]["Ekin_old"] for f in fr])
+        # d_pressure is a function-local static of move_atoms_npt_axial: read it off the ramp it produces
+        g["npt_start:d_pressure"] = fr[0]["npt_axial"]["pressure_ext"] - st["pressure_ext"]
+        g["npt:vir"] = np.array([[f["scalars"]["vir_xx"], f["scalars"]["vir_yy"], f["scalars"]["vir_zz"]] for f in fr])
+        g["npt:volume"] = np.array([f["after"]["volume"] for f in fr])
+        g["npt:box"] = np.array([f["box"] for f in fr])
     for k in ("nummer", "sorte", "vsorte", "masse", "ort", "impuls"):
         g["start:" + k] = out["start"][k]
     for k in ("ort", "impuls"):
