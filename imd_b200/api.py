@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # IMDB200_LIB: another build of the same library (tools/build_variant.sh: kernel experiments, never a fallback)
 LIB_PATH = os.environ.get("IMDB200_LIB") or os.path.join(HERE, "libimd_b200.so")
 
-NVE, NVT, NPT_ISO = 0, 1, 2
+NVE, NVT, NPT_ISO, NPT_AXIAL = 0, 1, 2, 3
 PAIR, EMBED, RHO = 0, 1, 2
 
 
@@ -56,7 +56,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state", "imdb200_set_adp_tables", "imdb200_get_adp", "imdb200_device_count", "imdb200_set_berendsen",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state", "imdb200_set_adp_tables", "imdb200_get_adp", "imdb200_device_count", "imdb200_set_berendsen", "imdb200_set_npt_axial", "imdb200_get_npt_axial",
 ]
 
 _lib = None
@@ -103,6 +103,8 @@ def load_library():
     L.imdb200_get_box.argtypes = [vp, vp]
     L.imdb200_set_npt_state.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.imdb200_get_npt_state.argtypes = [vp, vp]
+    L.imdb200_set_npt_axial.argtypes = [vp, vp, vp, vp, vp, C.c_double, vp]
+    L.imdb200_get_npt_axial.argtypes = [vp, vp]
     L.imdb200_get_atoms.argtypes = [vp] + [vp] * 12
     L.imdb200_natoms_local.restype = C.c_long
     L.imdb200_natoms_local.argtypes = [vp]
@@ -222,7 +224,7 @@ class IMDB200:
             cfg.box_x[d], cfg.box_y[d], cfg.box_z[d] = b[0, d], b[1, d], b[2, d]
             cfg.pbc_dirs[d] = int(pbc[d]); cfg.cpu_dim[d] = int(cpu_dim[d]); cfg.my_coord[d] = int(my_coord[d])
         cfg.nbl_margin = nbl_margin; cfg.nbl_size = nbl_size; cfg.timestep = timestep
-        cfg.ensemble = {"nve": NVE, "nvt": NVT, "npt_iso": NPT_ISO}[str(ensemble).lower()]
+        cfg.ensemble = {"nve": NVE, "nvt": NVT, "npt_iso": NPT_ISO, "npt_axial": NPT_AXIAL}[str(ensemble).lower()]
         cfg.xi = xi; cfg.isq_tau_xi = isq_tau_xi; cfg.pressure_ext = pressure_ext; cfg.d_pressure = d_pressure
         cfg.temperature = temperature; cfg.eta = eta; cfg.isq_tau_eta = isq_tau_eta
         cfg.device = device; cfg.lanes_per_atom = lanes_per_atom
@@ -397,6 +399,20 @@ class IMDB200:
     def set_npt_state(self, xi=0.0, Ekin_old=-1.0, pressure_ext=0.0):
         """NPT_iso hand-over: xi, twice the kinetic energy of the previous step (< 0: from the momenta), pressure_ext."""
         _chk(self.L.imdb200_set_npt_state(self.h, float(xi), float(Ekin_old), float(pressure_ext)))
+
+    def set_npt_axial(self, xi, pressure_ext, d_pressure=(0.0, 0.0, 0.0), relax_dirs=(1, 1, 1), Ekin_old=-1.0, dyn_stress=None):
+        """NPT_axial hand-over (globals xi, pressure_ext, relax_dirs, dyn_stress_x/y/z, Ekin_old of the reference)."""
+        v = [np.ascontiguousarray(x, np.float64) for x in (xi, pressure_ext, d_pressure)]
+        rd = np.ascontiguousarray(relax_dirs, np.int32)
+        dy = None if dyn_stress is None else np.ascontiguousarray(dyn_stress, np.float64)
+        _chk(self.L.imdb200_set_npt_axial(self.h, v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data, rd.ctypes.data,
+                                          float(Ekin_old), None if dy is None else dy.ctypes.data))
+
+    def npt_axial(self):
+        out = np.zeros(13)
+        _chk(self.L.imdb200_get_npt_axial(self.h, out.ctypes.data))
+        return dict(xi=out[0:3].copy(), stress=out[3:6].copy(), pressure_ext=out[6:9].copy(), dyn_stress=out[9:12].copy(),
+                    Ekin_old=float(out[12]))
 
     def npt(self):
         out = np.zeros(4)

@@ -112,6 +112,8 @@ int imdb200_create(const imdb200_config *cfg, imdb200_sim **out)
   s->eta = cfg->eta;
   s->skin_skip = 1; s->disp2 = -1.0;
   s->npt_xi = cfg->xi; s->npt_ekin_old = -1.0; s->npt_pressure_ext = cfg->pressure_ext;
+  for (int d = 0; d < 3; d++) { s->ax_xi[d] = cfg->xi; s->ax_pext[d] = cfg->pressure_ext; s->ax_dpext[d] = cfg->d_pressure; s->ax_relax[d] = 1; }
+  if (cfg->ensemble == IMDB200_ENS_NPT_AXIAL) s->press_calc = 1;   // see imdb200_set_press_calc
   const int rc = create_device_state(s);
   if (rc) { imdb200_destroy(s); return rc; }       // nothing of a half-built handle is left behind
   *out = s;
@@ -365,11 +367,50 @@ static int move_npt(imdb200_sim *s)
   return integrate_npt_after_fetch(s);
 }
 
+// NPT_axial: vir_xx/yy/zz of this step (sums of the per-atom stress), then like move_npt
+static int move_npt_axial(imdb200_sim *s)
+{
+  if (s->npt_ekin_old < 0.0) {                       // steps == steps_min in the reference (:1756-1771)
+    TRY(integrate_axial_dyn_pressure(s));
+    TRY(fetch_scalars(s));
+    s->npt_ekin_old = s->h_scal[SC_EKIN2];
+    s->ax_dyn[0] = s->h_scal[SC_DYNX]; s->ax_dyn[1] = s->h_scal[SC_DYNY]; s->ax_dyn[2] = s->h_scal[SC_DYNZ];
+    for (int d = 0; d < 3; d++) { if (s->cfg.isq_tau_xi == 0.0) s->ax_xi[d] = 0.0; s->ax_xi[d] *= s->ax_relax[d]; }
+  }
+  TRY(integrate_axial_virial(s));
+  TRY(fetch_scalars(s));
+  TRY(integrate_move_axial(s));
+  TRY(fetch_scalars(s));
+  return integrate_axial_after_fetch(s);
+}
+
+int imdb200_set_npt_axial(imdb200_sim *s, const double xi3[3], const double pext3[3], const double dpext3[3],
+                          const int relax3[3], double Ekin_old, const double dyn3[3])
+{
+  if (!s || !xi3 || !pext3) return imdb_fail(IMDB200_ERR_ARG, "null argument");
+  for (int d = 0; d < 3; d++) {
+    s->ax_xi[d] = xi3[d]; s->ax_pext[d] = pext3[d]; s->ax_dpext[d] = dpext3 ? dpext3[d] : 0.0;
+    s->ax_relax[d] = relax3 ? relax3[d] : 1; s->ax_dyn[d] = dyn3 ? dyn3[d] : 0.0;
+  }
+  if (Ekin_old >= 0.0 && !dyn3) return imdb_fail(IMDB200_ERR_ARG, "npt_axial: Ekin_old without dyn_stress");
+  s->npt_ekin_old = Ekin_old;
+  return 0;
+}
+
+int imdb200_get_npt_axial(imdb200_sim *s, double out13[13])
+{
+  if (!s || !out13) return imdb_fail(IMDB200_ERR_ARG, "null argument");
+  for (int d = 0; d < 3; d++) { out13[d] = s->ax_xi[d]; out13[3 + d] = s->ax_stress[d]; out13[6 + d] = s->ax_pext[d]; out13[9 + d] = s->ax_dyn[d]; }
+  out13[12] = s->npt_ekin_old;
+  return 0;
+}
+
 int imdb200_move_atoms(imdb200_sim *s)
 {
   TRY(ready(s));
   if (s->nbl_count == 0) return imdb_fail(IMDB200_ERR_ARG, "move_atoms before the first calc_forces");
   if (s->cfg.ensemble == IMDB200_ENS_NPT_ISO) TRY(move_npt(s));
+  else if (s->cfg.ensemble == IMDB200_ENS_NPT_AXIAL) TRY(move_npt_axial(s));
   else { TRY(integrate_move(s)); TRY(fetch_scalars(s)); }
   s->disp2 = s->h_scal[SC_MAXD2];
   return step_snapshot_disp2(s, 0);
@@ -404,7 +445,9 @@ int imdb200_fix_cells(imdb200_sim *s) { TRY(ready(s)); s->have_valid_nbl = 0; re
 int imdb200_make_nblist(imdb200_sim *s) { TRY(ready(s)); s->have_valid_nbl = 0; return cells_rebuild(s); }
 int imdb200_invalidate_nblist(imdb200_sim *s) { if (!s) return IMDB200_ERR_ARG; s->have_valid_nbl = 0; return 0; }
 int imdb200_set_skin_skip(imdb200_sim *s, int on) { if (!s) return IMDB200_ERR_ARG; s->skin_skip = on ? 1 : 0; return 0; }
-int imdb200_set_press_calc(imdb200_sim *s, int on) { if (!s) return IMDB200_ERR_ARG; s->press_calc = on ? 1 : 0; return 0; }
+// npt_axial needs the per-axis virial every step: its force kernels always run the per-atom-stress instances
+int imdb200_set_press_calc(imdb200_sim *s, int on)
+{ if (!s) return IMDB200_ERR_ARG; s->press_calc = (on || s->cfg.ensemble == IMDB200_ENS_NPT_AXIAL) ? 1 : 0; return 0; }
 
 int imdb200_set_eta(imdb200_sim *s, double eta)
 {
@@ -554,7 +597,8 @@ static int run_async(imdb200_sim *s, int nsteps)
 int imdb200_run(imdb200_sim *s, int nsteps)
 {
   TRY(ready(s));
-  if (s->cfg.ensemble != IMDB200_ENS_NPT_ISO && !s->tabs.have_adp) {
+  const bool host_barostat = s->cfg.ensemble == IMDB200_ENS_NPT_ISO || s->cfg.ensemble == IMDB200_ENS_NPT_AXIAL;
+  if (!host_barostat && !s->tabs.have_adp) {
     TRY(run_async(s, nsteps));
     if (s->is_short && !s->short_warned && s->rank == 0) { fprintf(stderr, "Short distance!\n"); s->short_warned = 1; }
     return 0;
@@ -578,9 +622,10 @@ int imdb200_run(imdb200_sim *s, int nsteps)
     }
     cudaEventRecord(s->ev[3], s->stream);
     if (s->cfg.ensemble == IMDB200_ENS_NPT_ISO) { TRY(fetch_scalars(s)); TRY(move_npt(s)); }   // virial first, see move_npt
+    else if (s->cfg.ensemble == IMDB200_ENS_NPT_AXIAL) TRY(move_npt_axial(s));
     else TRY(integrate_move(s));
     cudaEventRecord(s->ev[4], s->stream);
-    if (s->cfg.ensemble != IMDB200_ENS_NPT_ISO) TRY(fetch_scalars(s));
+    if (!host_barostat) TRY(fetch_scalars(s));
     s->disp2 = s->h_scal[SC_MAXD2];
     TRY(step_snapshot_disp2(s, 0));
     apply_check(s);

@@ -134,7 +134,8 @@ int integrate_move(imdb200_sim *s)
 // what follows the per-atom part: kinetic-energy sums, Nose-Hoover update, stress totals
 int integrate_finish(imdb200_sim *s, int nb)
 {
-  const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT || s->cfg.ensemble == IMDB200_ENS_NPT_ISO, st = s->press_calc != 0;
+  const bool nvt = s->cfg.ensemble == IMDB200_ENS_NVT || s->cfg.ensemble == IMDB200_ENS_NPT_ISO || s->cfg.ensemble == IMDB200_ENS_NPT_AXIAL,
+             st = s->press_calc != 0;
   if (nvt) {
     if (nb > 0) { const int slots[2] = {SC_EKIN1, SC_EKIN2}; TRY(reduce_finish(s, nb, 2, slots, 0)); }
     TRY(comm_sync_scalars(s));    // MPI_Allreduce of E_kin_1/2 (src/imd_integrate.c:1104-1130)
@@ -262,6 +263,145 @@ int integrate_npt_after_fetch(imdb200_sim *s)
   for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) g.box[b][d] *= ttt;
   s->skin_all = 1;                 // the images move with the box: the displacement bound of the skin classes is void
   s->npt_pressure_ext += s->cfg.d_pressure;
+  return geom_make_box(s);
+}
+
+// ---- NPT_axial: Nose-Hoover thermostat + one barostat per box axis (move_atoms_npt_axial, src/imd_integrate.c:1747-1959) ----
+// The per-axis virial is what P_AXIAL builds accumulate in calc_forces (vir_xx -= d.x*force.x, src/imd_forces_nbl.c:548-556,
+// 1275-1279); here it is the sum over atoms of the per-atom stress tensor of the STRESS instances of the force kernels
+// (-1/2 d (x) f per atom and pair end), which this ensemble therefore always runs.
+struct AxArgs {
+  double4 *pos, *mom; const double4 *frc;
+  const double *nblpos; long nstride;
+  const double *restr;
+  double *presstens; long pstride; int stress;
+  long n;
+  double dt, pfric[3], pifric[3], rfric[3], rifric[3];
+  double *partial;
+  unsigned long long *maxd2;
+};
+
+template <bool RESTR>
+__global__ void __launch_bounds__(IBLOCK) k_move_atoms_axial(AxArgs a)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  // twice the kinetic energy before the kick (= the reference's Ekin_old: the sum the previous step formed from the very
+  // same momenta, or calc_dyn_pressure at the first step) and after it (Ekin_new), then dyn_stress_x/y/z
+  double red[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double d2 = 0.0;
+  if (i < a.n) {
+    double4 x = a.pos[i], p = a.mom[i];
+    const double4 f = a.frc[i];
+    double tmp = 1.0 / p.w;
+    red[0] = (p.x * p.x + p.y * p.y + p.z * p.z) * tmp;
+    if (a.stress) {                                                    // kinetic part from the momenta BEFORE the kick (:1834-1845)
+      double *s = a.presstens + i;
+      s[0] += p.x * p.x * tmp; s[a.pstride] += p.y * p.y * tmp; s[2 * a.pstride] += p.z * p.z * tmp;
+      s[3 * a.pstride] += p.y * p.z * tmp; s[4 * a.pstride] += p.z * p.x * tmp; s[5 * a.pstride] += p.x * p.y * tmp;
+    }
+    p.x = (a.pfric[0] * p.x + a.dt * f.x) * a.pifric[0];              // :1848-1855
+    p.y = (a.pfric[1] * p.y + a.dt * f.y) * a.pifric[1];
+    p.z = (a.pfric[2] * p.z + a.dt * f.z) * a.pifric[2];
+    if (RESTR) { const double *r = a.restr + 3 * vsorte_of(x.w); p.x *= r[0]; p.y *= r[1]; p.z *= r[2]; }   // :1859-1864
+    red[2] = p.x * p.x * tmp; red[3] = p.y * p.y * tmp; red[4] = p.z * p.z * tmp;   // :1868-1872
+    red[1] = (p.x * p.x + p.y * p.y + p.z * p.z) * tmp;                // :1875
+    tmp *= a.dt;
+    x.x = (a.rfric[0] * x.x + p.x * tmp) * a.rifric[0];                // :1878-1883
+    x.y = (a.rfric[1] * x.y + p.y * tmp) * a.rifric[1];
+    x.z = (a.rfric[2] * x.z + p.z * tmp) * a.rifric[2];
+    a.mom[i] = p;
+    a.pos[i] = x;
+    d2 = r2_exact(x.x - a.nblpos[i], x.y - a.nblpos[a.nstride + i], x.z - a.nblpos[2 * a.nstride + i]);
+  }
+  d2 = block_max(d2);
+  if (threadIdx.x == 0) atomicMax(a.maxd2, (unsigned long long) __double_as_longlong(d2));
+  block_sum_store<5>(red, a.partial);
+}
+
+// calc_dyn_pressure (:1403-1465) per axis
+__global__ void __launch_bounds__(IBLOCK) k_dyn_pressure_axial(const double4 *mom, long n, double *partial)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  double red[4] = {0.0, 0.0, 0.0, 0.0};
+  if (i < n) { const double4 p = mom[i]; const double tmp = 1.0 / p.w;
+               red[1] = p.x * p.x * tmp; red[2] = p.y * p.y * tmp; red[3] = p.z * p.z * tmp; red[0] = (red[1] + red[2]) + red[3]; }
+  block_sum_store<4>(red, partial);
+}
+
+int integrate_axial_dyn_pressure(imdb200_sim *s)
+{
+  const int nb = cdiv(s->n_own, IBLOCK);
+  if (nb > 0) {
+    k_dyn_pressure_axial<<<nb, IBLOCK, 0, s->stream>>>(s->mom, s->n_own, s->d_partial); LAUNCH_CHECK();
+    const int slots[4] = {SC_EKIN2, SC_DYNX, SC_DYNY, SC_DYNZ};
+    TRY(reduce_finish(s, nb, 4, slots, 0));
+  }
+  return 0;
+}
+
+int integrate_axial_virial(imdb200_sim *s)
+{
+  const int nbp = cdiv(s->n_own, IBLOCK);
+  if (nbp > 0) {
+    k_sum_presstens<<<nbp, IBLOCK, 0, s->stream>>>(s->presstens, s->cap_atoms, s->n_own, s->d_partial); LAUNCH_CHECK();
+    const int slots[6] = {SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX, SC_PXY};
+    TRY(reduce_finish(s, nbp, 6, slots, 0));
+  }
+  return 0;
+}
+
+// The caller has fetched the global vir_xx/yy/zz (SC_PXX..) and holds the global dyn_stress and Ekin_old of the last step.
+int integrate_move_axial(imdb200_sim *s)
+{
+  const double dt = s->cfg.timestep, vol = s->volume;
+  const double vir[3] = {s->h_scal[SC_PXX], s->h_scal[SC_PYY], s->h_scal[SC_PZZ]};
+  AxArgs a;
+  const double ttt = dt * vol * s->cfg.isq_tau_xi / (double) s->nactive;                           // :1782
+  for (int d = 0; d < 3; d++) {
+    s->ax_stress[d] = (s->ax_dyn[d] + vir[d]) / vol;                                               // :1775-1779
+    const double xi_old = s->ax_xi[d];
+    s->ax_xi[d] += ttt * (s->ax_stress[d] - s->ax_pext[d]) * s->ax_relax[d];                       // :1783-1787
+    a.pfric[d]  =        1.0 - (xi_old      + s->eta) * dt / 2.0;                                  // :1790-1803
+    a.pifric[d] = 1.0 / (1.0 + (s->ax_xi[d] + s->eta) * dt / 2.0);
+    a.rfric[d]  =        1.0 + (s->ax_xi[d]         ) * dt / 2.0;
+    a.rifric[d] = 1.0 / (1.0 - (s->ax_xi[d]         ) * dt / 2.0);
+  }
+  a.pos = s->pos; a.mom = s->mom; a.frc = s->frc;
+  a.nblpos = s->nblpos; a.nstride = s->cap_atoms;
+  a.restr = s->restr;
+  a.presstens = s->presstens; a.pstride = s->cap_atoms; a.stress = 1;
+  a.n = s->n_own; a.dt = dt;
+  a.partial = s->d_partial;
+  a.maxd2 = (unsigned long long *) (s->d_scal + SC_MAXD2);
+  const int nb = cdiv(s->n_own, IBLOCK);
+  CUDA_TRY(cudaMemsetAsync(s->d_scal + SC_MAXD2, 0, sizeof(double), s->stream));
+  if (nb > 0) {
+    if (s->n_restr > 0) k_move_atoms_axial<true><<<nb, IBLOCK, 0, s->stream>>>(a);
+    else k_move_atoms_axial<false><<<nb, IBLOCK, 0, s->stream>>>(a);
+    LAUNCH_CHECK();
+    const int slots[5] = {SC_EKIN1, SC_EKIN2, SC_DYNX, SC_DYNY, SC_DYNZ};
+    TRY(reduce_finish(s, nb, 5, slots, 0));
+  }
+  // tot_kin_energy = (Ekin_old + Ekin_new)/4, the eta update from the global Ekin_new (:1917-1920) and the stress totals
+  // of the step (virial + kinetic part) are NVT's
+  return integrate_finish(s, 0);
+}
+
+// After the scalar fetch: dyn_stress and Ekin_old for the next step, the box (:1923-1937), the pressure ramp (:1955-1959).
+int integrate_axial_after_fetch(imdb200_sim *s)
+{
+  const double dt = s->cfg.timestep;
+  s->npt_ekin_old = s->h_scal[SC_EKIN2];
+  s->ax_dyn[0] = s->h_scal[SC_DYNX]; s->ax_dyn[1] = s->h_scal[SC_DYNY]; s->ax_dyn[2] = s->h_scal[SC_DYNZ];
+  double tvec[3];
+  for (int d = 0; d < 3; d++) {
+    tvec[d] = (1.0 + s->ax_xi[d] * dt / 2.0) / (1.0 - s->ax_xi[d] * dt / 2.0);
+    if (tvec[d] < 0) return imdb_fail(IMDB200_ERR_EXPLODE, "box size has become negative!");
+  }
+  Geom &g = s->geom;
+  for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) g.box[b][d] *= tvec[b];   // box_x *= tvec.x, box_y *= tvec.y, box_z *= tvec.z
+  s->skin_all = 1;
+  for (int d = 0; d < 3; d++) s->ax_pext[d] += s->ax_dpext[d];
   return geom_make_box(s);
 }
 

@@ -197,6 +197,8 @@ struct imdb200_sim {
   // NPT_iso: barostat friction, twice the global kinetic energy after the last step (< 0: unknown), external pressure,
   // the pressure the last step used
   double npt_xi, npt_ekin_old, npt_pressure_ext, npt_pressure;
+  // NPT_axial: per-axis xi, stress of the last step, pressure_ext and its increment, dyn_stress the last step left, relax_dirs
+  double ax_xi[3], ax_stress[3], ax_pext[3], ax_dpext[3], ax_dyn[3]; int ax_relax[3];
   double eta;
   double tauber;       // > 0: Berendsen variant of NVE (imdb200_set_berendsen)
   // timers
@@ -218,7 +220,8 @@ struct imdb200_sim {
 #define NBIN_EXTRA 29   // 27 leave directions + 1 dropped + 1 spare (exclusive-scan total)
 
 enum { SC_EPOT = 0, SC_VIRIAL, SC_EKIN, SC_EKIN2, SC_MAXD2, SC_ETA, SC_PXX, SC_PYY, SC_PZZ, SC_PYZ, SC_PZX,
-       SC_PXY, SC_EKIN1, SC_SHORT, SC_COUNT = 16 };   // SC_SHORT: is_short of any rank (max); slot 15 is scratch
+       SC_PXY, SC_EKIN1, SC_SHORT, SC_DYNX, SC_DYNY, SC_DYNZ, SC_COUNT = 20 };   // SC_SHORT: is_short of any rank (max);
+       // SC_DYN*: dyn_stress_x/y/z of NPT_axial; the last slot is scratch
 enum { FL_SHORT = 0, FL_NBL_OVERFLOW, FL_MAXNB, FL_NGHOST, FL_LOST, FL_NSEND, FL_BADTYPE, FL_CELLFULL, FL_COUNT = 8 };
 
 struct StepCtl { int gate; int pad; double disp2; };
@@ -304,6 +307,10 @@ int integrate_move(imdb200_sim *s);           // move_atoms_nve/nvt + check_nbli
 int integrate_move_npt(imdb200_sim *s);       // move_atoms_npt_iso + check_nblist fused; integrate_npt_after_fetch follows the scalar fetch
 int integrate_npt_dyn_pressure(imdb200_sim *s);   // calc_dyn_pressure into SC_EKIN2 (local share)
 int integrate_npt_after_fetch(imdb200_sim *s);
+int integrate_axial_dyn_pressure(imdb200_sim *s);   // calc_dyn_pressure per axis into SC_DYN*, SC_EKIN2 (local share)
+int integrate_axial_virial(imdb200_sim *s);         // vir_xx/yy/zz = sums of the per-atom stress after calc_forces, into SC_PXX..
+int integrate_move_axial(imdb200_sim *s);           // move_atoms_npt_axial + check_nblist; integrate_axial_after_fetch follows the fetch
+int integrate_axial_after_fetch(imdb200_sim *s);
 int reduce_finish(imdb200_sim *s, int nblocks, int nvals, const int *slots, int accumulate_mask, int zero_maxd2 = 0);
 int step_snapshot_disp2(imdb200_sim *s, int reset);   // StepCtl::disp2 <- SC_MAXD2 of the global block (reset: 0)
 

@@ -50,7 +50,7 @@ enum {
   IMDB200_ERR_EXPLODE = -7  /* "system seems to explode!" (src/imd_geom_3d.c:96)          */
 };
 
-enum { IMDB200_ENS_NVE = 0, IMDB200_ENS_NVT = 1, IMDB200_ENS_NPT_ISO = 2 }; /* ensemble keyword, src/imd_param.c:377-444 */
+enum { IMDB200_ENS_NVE = 0, IMDB200_ENS_NVT = 1, IMDB200_ENS_NPT_ISO = 2, IMDB200_ENS_NPT_AXIAL = 3 }; /* ensemble keyword, src/imd_param.c:377-444 */
 
 /* Table interpolation.  The reference fixes it at compile time (src/potaccess.h:24-36; make targets with
  * `4point` or `spline` in their name, src/Makefile:1694-1701); here it is a run-time field of the config.
@@ -224,6 +224,18 @@ int  imdb200_get_scalars(imdb200_sim *sim, imdb200_scalars *out);
  * reference does at steps == steps_min).  out4 = xi, Ekin_old, pressure used by the last step, pressure_ext. */
 int  imdb200_set_npt_state(imdb200_sim *sim, double xi, double Ekin_old, double pressure_ext);
 int  imdb200_get_npt_state(imdb200_sim *sim, double out4[4]);
+/* NPT_axial (ensemble npt_axial, move_atoms_npt_axial, src/imd_integrate.c:1747-1959): Nose-Hoover thermostat + one
+ * barostat per box axis, driven by stress_x/y/z = (dyn_stress + vir)/volume of that axis.  The reference's `npt_axial`
+ * builds define P_AXIAL and accumulate vir_xx/yy/zz in calc_forces (src/imd_forces_nbl.c:548-556); here the ensemble
+ * always runs the per-atom-stress instances of the force kernels and sums their diagonal.  isq_tau_xi, temperature, eta
+ * and isq_tau_eta come from imdb200_config.  xi3 = xi.x/y/z, pressure_ext3 = pressure_start, d_pressure3 =
+ * (pressure_end - pressure_start)/(steps_max - steps_min), relax_dirs3 = relax_dirs (src/globals.h:627);
+ * Ekin_old < 0 makes the next move_atoms start like steps == steps_min (calc_dyn_pressure, xi *= relax_dirs), else
+ * dyn_stress3 = dyn_stress_x/y/z left by the previous step.  out13 = xi[3], stress_x/y/z of the last step, pressure_ext[3],
+ * dyn_stress[3], Ekin_old. */
+int  imdb200_set_npt_axial(imdb200_sim *sim, const double xi3[3], const double pressure_ext3[3], const double d_pressure3[3],
+                           const int relax_dirs3[3], double Ekin_old, const double dyn_stress3[3]);
+int  imdb200_get_npt_axial(imdb200_sim *sim, double out13[13]);
 /* replaces: reading the globals box_x, box_y, box_z (src/globals.h) after lin_deform has changed them;
  * out9 = box_x, box_y, box_z */
 int  imdb200_get_box(imdb200_sim *sim, double out9[9]);

@@ -112,6 +112,67 @@ def test_cuda_npt_iso_matches_reference_fixture(api, tmp_path):
     assert r.returncode == 0 and "NPT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("case,mode", [("cu_npt_axial", "stepwise"), ("cu_npt_axial_xz", "stepwise"), ("cu_npt_axial", "run")])
+def test_cuda_npt_axial_matches_reference_fixture(api, case, mode, tmp_path):
+    """IMDB200_ENS_NPT_AXIAL against the reference's `npt_axial` build (move_atoms_npt_axial, src/imd_integrate.c:1747-1959;
+    P_AXIAL virial components, src/imd_forces_nbl.c:548-556): per-axis xi, stress, pressure ramp, dyn_stress, eta, the box
+    and the trajectory; relax_dirs 1 0 1 holds the y axis; `run` drives the same steps through imdb200_run."""
+    g = common.load_golden(case)
+    paths = common.write_tables(g, str(tmp_path))
+    sim = api.IMDB200(1, g["box"], pair=paths["pair"], embed=paths["embed"], rho=paths["rho"], ensemble="npt_axial",
+                      timestep=float(g["timestep"]), temperature=float(g["temperature"]), eta=float(g["eta0"]),
+                      isq_tau_eta=float(g["isq_tau_eta"]), isq_tau_xi=float(g["npt_start:isq_tau_xi"]))
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"])
+    sim.set_npt_axial(g["npt_start:xi"], g["npt_start:pressure_ext"], g["npt_start:d_pressure"], g["npt_start:relax_dirs"],
+                      Ekin_old=float(g["npt_start:Ekin_old"]), dyn_stress=g["npt_start:dyn_stress"])
+    press = bool(int(g["press"]))
+    sim.set_press_calc(press)
+    worst = {}
+
+    def close(name, got, want, tol, s):
+        e = float(np.max(np.abs(np.asarray(got) - want)) / max(np.max(np.abs(want)), 1e-300))
+        worst[name] = max(worst.get(name, 0.0), e)
+        assert e <= tol, (name, s, got, want, e)
+
+    n = int(g["nsteps"])
+    for s in range(n):
+        tol = 1e-10 if s == 0 else 1e-8
+        if mode == "run":
+            sim.run(1)
+            close("epot", sim.scalars()["tot_pot_energy"], g["epot"][s], tol, s)
+        else:
+            sim.calc_forces(s)
+            close("epot", sim.scalars()["tot_pot_energy"], g["epot"][s], tol, s)
+            rec = s in [int(x) for x in g["record"]]
+            if s == 0:
+                assert common.relerr(sim.atoms()["kraft"], g["f0:kraft"]) <= 1e-10
+            if press and rec:
+                assert common.relerr(sim.atoms()["presstens"], g[f"f{s}:presstens"]) <= 10 * tol
+            sim.move_atoms()
+            sim.check_nblist()
+            if press and rec:      # virial + kinetic part from the momenta before the kick
+                close("tot_presstens", sim.tot_presstens(), g[f"f{s}:tot_presstens"], 10 * tol, s)
+        st, sc = sim.npt_axial(), sim.scalars()
+        for k in ("xi", "stress", "pressure_ext", "dyn_stress"):
+            close(k, st[k], g["npt:" + k][s], 10 * tol, s)
+        close("volume", sc["volume"], g["npt:volume"][s], 1e-10, s)
+        close("eta", sc["eta"], g["eta"][s], 10 * tol, s)
+        close("ekin", sc["tot_kin_energy"], g["ekin"][s], tol, s)
+        close("box", sim.box(), g["npt:box"][s], 1e-10, s)
+        assert sim.have_valid_nbl == int(g["valid"][s]), f"check_nblist decision differs at step {s}"
+    if case.endswith("_xz"):
+        assert sim.box()[1, 1] == g["box"][1, 1]
+    a = sim.atoms()
+    box = sim.box()
+    o = np.argsort(a["nummer"])
+    d = a["ort"][o] - g["final:ort"]
+    frac = d @ np.linalg.inv(box)
+    d = (frac - np.round(frac)) @ box
+    assert np.max(np.abs(d)) <= 1e-8 * np.max(np.abs(box))
+    print(case, mode, {k: f"{v:.1e}" for k, v in worst.items()})
+    sim.close()
+
+
 @pytest.mark.parametrize("name,lanes", [("cu_adp", 1), ("nial_adp", 4)])
 def test_cuda_adp_matches_reference_fixture(api, name, lanes, tmp_path):
     """imdb200_set_adp_tables against the reference's `adp` build: mu, lambda, the ADP energy and the dipole / quadrupole
