@@ -20,7 +20,8 @@
  * below run IMD's own routine (box, host copy) and then the device's (imdb200_lin_deform / imdb200_deform_sample).
  * stress builds: per-atom PRESSTENS is downloaded whenever do_press_calc is set, so that calc_tot_presstens
  * (src/imd_main_3d.c:2069-2130) and the Press_xx.. columns of the .eng file (src/imd_io.c:2474-2480) work unchanged.
- * npt builds: ensemble npt_iso runs on the device (xi, pressure_ext, Ekin_old and the breathing box are mirrored back).
+ * npt builds: ensembles npt_iso and npt_axial run on the device (xi, pressure_ext, Ekin_old, the per-axis stress and the
+ * breathing box are mirrored back).
  *
  * MPI builds (imd_mpi_*, one rank per GPU): cpu_dim / my_coord are IMD's own (setup_mpi_topology,
  * src/imd_geom_mpi_3d.c:32-90), rank 0 creates the ncclUniqueId and MPI_Bcast carries it, every rank uploads the atoms
@@ -212,7 +213,13 @@ static void b200_scalars(int forces, int kinetic)
 {
   imdb200_scalars sc;
   b200_check(imdb200_get_scalars(b200, &sc));
-  if (forces) { tot_pot_energy = sc.tot_pot_energy; virial = sc.virial; }
+  if (forces) {
+    tot_pot_energy = sc.tot_pot_energy; virial = sc.virial;
+#ifdef P_AXIAL   /* these builds accumulate vir_xx/yy/zz instead and leave `virial` at 0 (src/imd_forces_nbl.c:548-556); the
+                    per-axis sums stay in the library, IMD reads them back as stress_x/y/z */
+    virial = 0.0;
+#endif
+  }
   if (kinetic) { tot_kin_energy = sc.tot_kin_energy; eta = sc.eta; }
   have_valid_nbl = sc.have_valid_nbl;
   nbl_count = sc.nbl_count;
@@ -237,6 +244,21 @@ static void b200_mirror_npt(void)
   double st[4];
   b200_check(imdb200_get_npt_state(b200, st));
   xi.x = st[0]; Ekin_old = st[1]; pressure = st[2]; pressure_ext.x = st[3];
+  b200_mirror_box();
+}
+#endif
+
+#ifdef NPT_axial
+/* what move_atoms_npt_axial leaves in IMD's globals (src/imd_integrate.c:1775-1787, 1917-1959) */
+static void b200_mirror_npt_axial(void)
+{
+  double st[13];
+  b200_check(imdb200_get_npt_axial(b200, st));
+  xi.x = st[0]; xi.y = st[1]; xi.z = st[2];
+  stress_x = st[3]; stress_y = st[4]; stress_z = st[5];
+  pressure_ext.x = st[6]; pressure_ext.y = st[7]; pressure_ext.z = st[8];
+  dyn_stress_x = st[9]; dyn_stress_y = st[10]; dyn_stress_z = st[11];
+  Ekin_old = st[12];
   b200_mirror_box();
 }
 #endif
@@ -267,6 +289,9 @@ static void b200_move_atoms(void)
 #ifdef NPT_iso
   if (ensemble == ENS_NPT_ISO) b200_mirror_npt();
 #endif
+#ifdef NPT_axial
+  if (ensemble == ENS_NPT_AXIAL) b200_mirror_npt_axial();
+#endif
 #ifdef STRESS_TENS
   press = do_press_calc;                         /* kinetic part added by move_atoms: the tensor is complete now */
 #endif
@@ -295,7 +320,14 @@ static void b200_init(void)
     cfg.d_pressure = (pressure_end.x - pressure_ext.x) / (steps_max - steps_min);
   } else
 #endif
-  if (ensemble != ENS_NVE && ensemble != ENS_NVT) error("imd_b200 supports the ensembles nve, nvt and npt_iso");
+#ifdef NPT_axial
+  if (ensemble == ENS_NPT_AXIAL) {               /* the per-axis state goes in after imdb200_create, see below */
+    if (use_curr_pressure) error("imd_b200: use_curr_pressure is not supported with ensemble npt_axial");
+    cfg.ensemble = IMDB200_ENS_NPT_AXIAL;
+    cfg.isq_tau_xi = isq_tau_xi;
+  } else
+#endif
+  if (ensemble != ENS_NVE && ensemble != ENS_NVT) error("imd_b200 supports the ensembles nve, nvt, npt_iso and npt_axial");
   cfg.temperature = temperature; cfg.eta = eta; cfg.isq_tau_eta = isq_tau_eta;
   /* `4point` / `spline` make targets (src/Makefile:1694-1701, src/potaccess.h:24-36) */
 #if defined(FOURPOINT)
@@ -313,6 +345,18 @@ static void b200_init(void)
   }
 #endif
   b200_check(imdb200_create(&cfg, &b200));
+#ifdef NPT_axial
+  if (ensemble == ENS_NPT_AXIAL) {               /* src/imd_integrate.c:1756-1771, 1941-1959 */
+    double x3[3], p3[3], d3[3]; int r3[3];
+    x3[0] = xi.x; x3[1] = xi.y; x3[2] = xi.z;
+    p3[0] = pressure_ext.x; p3[1] = pressure_ext.y; p3[2] = pressure_ext.z;
+    d3[0] = (pressure_end.x - pressure_ext.x) / (steps_max - steps_min);
+    d3[1] = (pressure_end.y - pressure_ext.y) / (steps_max - steps_min);
+    d3[2] = (pressure_end.z - pressure_ext.z) / (steps_max - steps_min);
+    r3[0] = relax_dirs.x; r3[1] = relax_dirs.y; r3[2] = relax_dirs.z;
+    b200_check(imdb200_set_npt_axial(b200, x3, p3, d3, r3, -1.0, NULL));
+  }
+#endif
 #ifdef MPI
   if (num_cpus > 1) {
     char id[128];

@@ -141,6 +141,48 @@ def test_full_binding_npt_iso(built_lib, tmp_path):
     assert np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-7
 
 
+def test_full_binding_relax_pressure(built_lib, tmp_path):
+    """relax_pressure (src/imd_deform.c:127-219, called from main_loop src/imd_main_3d.c:756): IMD's own host code forms the
+    deformation from calc_tot_presstens() on the per-atom tensor the engine downloads every step (do_press_calc is on while
+    relax_rate > 0, src/imd_main_3d.c:183-194) and applies it through lin_deform, which the binding routes to the device."""
+    tmp = str(tmp_path)
+    tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+    extra = dict(eng_int=1, checkpt_int=20, relax_rate=0.01, relax_mode="full", bulk_module=1.0, shear_module=0.5)
+    _pair_run(tmp, tabs, ensemble="nve", maxsteps=20, starttemp=0.08, extra=extra)
+    eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
+    assert eg.shape == ec.shape and len(eg) == 21
+    # columns: time Epot T fnorm fmax pressure volume eta box_x.x box_y.y box_z.z Press_xx .. Press_xy
+    assert eg.shape[1] == 17 and abs(ec[-1, 8] - ec[0, 8]) > 0.1     # the box has relaxed noticeably
+    for col in list(range(1, 5)) + list(range(8, 17)):
+        assert np.max(np.abs(eg[:, col] - ec[:, col])) <= 1e-8 * np.max(np.abs(ec[:, col])), col
+    cg, cc = _chkpt(os.path.join(tmp, "gpu.00001.chkpt")), _chkpt(os.path.join(tmp, "cpu.00001.chkpt"))
+    assert cg.shape == cc.shape and np.array_equal(cg[:, 0], cc[:, 0])
+    assert np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-7
+
+
+def test_axial_binding_npt_axial(built_lib, tmp_path):
+    """ensemble npt_axial through the binding (make target imd_nve_nvt_npt_axial_eam_nbl_stress_hpo): per-axis xi, stress,
+    pressure ramp and box live on the device and are mirrored into IMD's globals after every move_atoms
+    (src/imd_integrate.c:1747-1959); stress_x/y/z, the box and Press_xx.. columns of IMD's own .eng writer."""
+    tmp = str(tmp_path)
+    tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+    extra = dict(eng_int=1, checkpt_int=30, endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.5, pressure_start=[0.02, 0.01, 0.03],
+                 pressure_end=[0.03, 0.01, 0.02], relax_dirs=[1, 0, 1])
+    _pair_run(tmp, tabs, exes=("imd_b200_dropin_axial", "imd_ref_serial_axial"), ensemble="npt_axial", maxsteps=30, starttemp=0.08,
+              extra=extra)
+    eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
+    assert eg.shape == ec.shape and len(eg) == 31
+    # columns: time Epot T pressure volume eta stress_x/y/z box_x.x box_y.y box_z.z Press_xx .. Press_xy
+    assert eg.shape[1] == 18 and np.ptp(ec[:, 9]) > 0 and np.ptp(ec[:, 10]) == 0   # x breathes, y is held
+    for col in [1, 2] + list(range(6, 18)):
+        assert np.max(np.abs(eg[:, col] - ec[:, col])) <= 1e-8 * np.max(np.abs(ec[:, col])), col
+    for col in (3, 4, 5):                                 # pressure, volume, eta*tau_eta are printed with %e only
+        assert np.max(np.abs(eg[:, col] - ec[:, col])) <= 2e-6 * np.max(np.abs(ec[:, col])), col
+    cg, cc = _chkpt(os.path.join(tmp, "gpu.00001.chkpt")), _chkpt(os.path.join(tmp, "cpu.00001.chkpt"))
+    assert cg.shape == cc.shape and np.array_equal(cg[:, 0], cc[:, 0])
+    assert np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-7
+
+
 def test_restart_from_checkpoint(built_lib, tmp_path):
     """Restart `-r 1` (src/imd_param.c:3829-3872, .itr + checkpoint readers src/imd_io_3d.c:949-1086): 15 steps, checkpoint 1,
     then both binaries continue from THEIR OWN checkpoint for 15 more steps; the engine is fed by IMD's own reader."""
