@@ -832,7 +832,7 @@ long imdb200_get_nblist(imdb200_sim *s, int *ni, int *nj, signed char *shift3, l
   long cnt = 0;
   for (long i = 0; i < n; i++)
     for (int m = 0; m < nnb[i]; m++) {
-      int j = nbl[nbl_index(i, m, L, s->max_nb / L)];
+      int j = nbl[nbl_index(i, m, L, s->max_nb / L)] & NBL_JMASK;   // bits 29-30: the neighbour's type
       int sx = 0, sy = 0, sz = 0, jn;
       // image shift of j as this rank applies it (periodic wrap); 0 for images of a neighbour domain's atoms
       if (j >= n) { int c = code[cid[j]]; sx = c % 3 - 1; sy = (c / 3) % 3 - 1; sz = c / 9 - 1; jn = gnum[j - n]; }

@@ -436,16 +436,18 @@ struct BuildCtx {                 // what the exact test of one candidate needs
   double4 xi; int i, n_own;
 };
 // the reference's own test operands (see k_build_nbl): mirror = the pair is evaluated from the other atom's side
-__device__ __forceinline__ double nbl_exact_r2(const BuildCtx &b, const Geom &g, int j, bool mirror)
+__device__ __forceinline__ double nbl_exact_r2(const BuildCtx &b, const Geom &g, int j, bool mirror, int &tj)
 {
   if (mirror) {
     const int inv = 26 - b.cell_code[b.cellid[j]];             // our image as the buffer cell on the far side holds it
     const double4 me = image_pos(b.xi, inv, g);
     const int src = b.gsrc[j - b.n_own];
     const double4 xj = src >= 0 ? b.pos[src] : b.ghost_raw[j - b.n_own];
+    tj = sorte_of(xj.w);
     return r2_exact(__dsub_rn(me.x, xj.x), __dsub_rn(me.y, xj.y), __dsub_rn(me.z, xj.z));
   }
   const double4 xj = ld_atom(b.pos + j);
+  tj = sorte_of(xj.w);
   return r2_exact(__dsub_rn(xj.x, b.xi.x), __dsub_rn(xj.y, b.xi.y), __dsub_rn(xj.z, b.xi.z));
 }
 
@@ -509,11 +511,13 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
         BODY \
       } } while (0)
     NBL_WALK({
-      const double r2 = nbl_exact_r2(b, g, j, mirror);
+      int tj;
+      const double r2 = nbl_exact_r2(b, g, j, mirror, tj);
+      const int ent = j | (tj << NBL_TSHIFT);                    // the neighbour's type rides in the entry (NBL_TSHIFT)
       if (!(r2 < g.cellsz) || j == i) keep &= ~(1u << t);
       else if (r2 <= T.t2[0]) {
         keep &= ~(1u << t);
-        if (n0 < max_nb) { if (L == 1) row0[n0 * 32] = j; else nbl[nbl_index(i, n0, L, R)] = j; }
+        if (n0 < max_nb) { if (L == 1) row0[n0 * 32] = ent; else nbl[nbl_index(i, n0, L, R)] = ent; }
         n0++;
       } else {
         int c = 1;
@@ -533,14 +537,16 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
     total = run;
     if (total <= max_nb && total > n0) {
       NBL_WALK({
-        const double r2 = nbl_exact_r2(b, g, j, mirror);
+        int tj;
+        const double r2 = nbl_exact_r2(b, g, j, mirror, tj);
+        const int ent = j | (tj << NBL_TSHIFT);
         int c = 1;
 #pragma unroll
         for (int k = 1; k < NBL_CLASSES; k++) c += r2 > T.t2[k] ? 1 : 0;
         const int sh = NBL_CBITS * c;
         const int p = (int) ((offs >> sh) & ((1u << NBL_CBITS) - 1));
         offs += 1ull << sh;
-        if (L == 1) row0[p * 32] = j; else nbl[nbl_index(i, p, L, R)] = j;
+        if (L == 1) row0[p * 32] = ent; else nbl[nbl_index(i, p, L, R)] = ent;
       });
     }
 #undef NBL_WALK

@@ -429,7 +429,7 @@ int comm_ghost_pos_finish(imdb200_sim *s)
 int comm_ghost_dF_finish(imdb200_sim *s)
 {
   if (s->n_ghost == 0) return 0;
-  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->tabs.ntypes == 1 ? s->posdf : nullptr, s->pos, s->n_own,
+  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->posdf, s->pos, s->n_own,
                                                              s->n_ghost, s->gsrc);
   LAUNCH_CHECK();
   return 0;
@@ -446,7 +446,7 @@ int comm_ghost_dF(imdb200_sim *s)
     k_pack1<<<cdiv(s->n_send, 256), 256, 0, s->stream>>>(s->dF, s->send_idx, s->n_send, s->sendbuf1); LAUNCH_CHECK();
     TRY(exchange_forward<double>(s, s->sendbuf1, s->dF + s->n_own, ncclFloat64, 1));
   }
-  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->tabs.ntypes == 1 ? s->posdf : nullptr, s->pos, s->n_own,
+  k_ghost_dF<<<cdiv(s->n_ghost, 256), 256, 0, s->stream>>>(s->dF, s->posdf, s->pos, s->n_own,
                                                              s->n_ghost, s->gsrc);
   LAUNCH_CHECK();
   return 0;

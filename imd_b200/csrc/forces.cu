@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
 #define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { const int j_ = jq[d]; \
           X[d] = j_ >= 0 ? make_double4(xi.x + 1.0 + (j_ & 7) * 0.3, xi.y + ((j_ >> 3) & 7) * 0.3, xi.z + ((j_ >> 6) & 7) * 0.3, xi.w) : xi; }
 #else
-#define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { const int j_ = jq[d] >= 0 ? jq[d] : (int) i; \
+#define GATHER1(X) _Pragma("unroll") for (int d = 0; d < FDEPTH; d++) { const int j_ = jq[d] >= 0 ? (MULTI ? jq[d] & NBL_JMASK : jq[d]) : (int) i; \
           X[d] = (d < IMDB_TEX1 && a.use_tex) ? ld_atom_tex(a.tpos, j_) : ld_atom(a.pos + j_); }
 #endif
 #if IMDB_DB
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
           a.eam_p[i] = ph;
           a.dM[i] = fma(chi, CUB ? fma(chi, __ldg(m + 6), m2.y) : m2.y, m2.x);
         }
-        if (!MULTI) a.posdf[i] = make_double4(xi.x, xi.y, xi.z, dF);
+        a.posdf[i] = make_double4(xi.x, xi.y, xi.z, dF);     // the pass-2 gather record
       }
       a.frc[i] = make_double4(fx, fy, fz, epot);
       if (STRESS) {                                        // -0.5 d (x) f per atom (:558-581)
@@ -463,9 +463,17 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   const double2 *rH = T.rhoH;
   const double *rH3 = T.rhoH3;                       // cubic modes: rho'/2 = h1 + chi*(h2 + chi*h3)
   constexpr bool FAST2 = !MULTI && !EE && !CUB && !STRESS && TSMEM && IMDB_BRANCHFREE2;
+  // Several species with the tables in shared memory (the host passes TSMEM only when this applies: quadratic, no EEAM, every
+  // rho column on one r^2 grid): (h1,h2) of the DISTINCT rho columns, see DevTables::rhoHd
+  constexpr bool FASTM = MULTI && TSMEM && !CUB && !EE;
   const unsigned s_tab = (unsigned) __cvta_generic_to_shared(smem_raw);
   const unsigned k_max = (unsigned) (T.rho.nrows - 1);
-  if (TSMEM) {
+  const int nuR = T.nuR;
+  if (FASTM) {
+    stage(smem_raw, T.rhoHd, T.rho.nrows * nuR * 16);
+    __syncthreads();
+    rH = reinterpret_cast<const double2 *>(smem_raw);
+  } else if (TSMEM) {
     const int nr = T.rho.nrows * T.rho.ncols;
     stage(smem_raw, T.rhoH, nr * 16);
     if (CUB) stage(smem_raw + (size_t) nr * 16, T.rhoH3, ((nr + 1) & ~1) * 8);
@@ -475,7 +483,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
   }
   const int nt = T.ntypes;
   const double r_end0 = T.rho.end[0], r_is0 = T.rho.invstep[0], r_nb0 = -T.rho.begin[0] * T.rho.invstep[0];
-  const double4 *gat = MULTI ? a.pos : a.posdf;      // single species: x,y,z,dF in one record
+  const double4 *gat = a.posdf;                      // x,y,z,F' in one record; the neighbour's type rides in the list entry
   const long per = (a.wn + gridDim.x - 1) / gridDim.x;
   const long w_end = min(a.wn, (long) (blockIdx.x + 1) * per);
   double red[3] = {0.0, 0.0, 0.0};                  // virial, and with FUSE the two kinetic-energy sums
@@ -492,8 +500,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
     if (act) {
       const double4 xi = gat[i];
-      const int it = MULTI ? sorte_of(xi.w) : 0;
-      const double dFi = MULTI ? a.dF[i] : xi.w;
+      const int it = MULTI ? sorte_of(reinterpret_cast<const double *>(a.pos + i)[3]) : 0;
+      const double dFi = xi.w;
       const double dMi = EE ? a.dM[i] : 0.0;
       const long lslot = slot & ~(long) (IMDB_EXP_BCAST - 1);
       const int nn = (int) ((a.nnbc[lslot / L] >> cls_shift) & ((1u << NBL_CBITS) - 1));
@@ -512,8 +520,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
           X[d] = j_ >= 0 ? make_double4(xi.x + 1.0 + (j_ & 7) * 0.3, xi.y + ((j_ >> 3) & 7) * 0.3, xi.z + ((j_ >> 6) & 7) * 0.3, xi.w) : xi; }
 #else
 #define GATHER2(X, JC) _Pragma("unroll") for (int dd = 0; dd < FDEPTH2; dd++) { const int d = FDEPTH2 - 1 - dd; \
-          const int j = jq[d] >= 0 ? jq[d] : (int) i; if (MULTI || EE) JC[d] = j; \
-          X[d] = (d >= FDEPTH2 - IMDB_TEX2 && a.use_tex) ? ld_atom_tex(MULTI ? a.tpos : a.tposdf, j) : ld_atom(gat + j); }
+          const int e_ = jq[d] >= 0 ? jq[d] : (int) i; if (MULTI || EE) JC[d] = e_; const int j = MULTI ? e_ & NBL_JMASK : e_; \
+          X[d] = (d >= FDEPTH2 - IMDB_TEX2 && a.use_tex) ? ld_atom_tex(a.tposdf, j) : ld_atom(gat + j); }
 #endif
 #if IMDB_DB
       double4 xq[FDEPTH2];
@@ -565,11 +573,32 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
         for (int d = 0; d < FDEPTH2; d++) {
         if (m + d * L >= nn) break;
         const double4 xj = xq[d];
-        const int j = (MULTI || EE) ? jc[d] : 0;
+        const int j = (MULTI || EE) ? (MULTI ? jc[d] & NBL_JMASK : jc[d]) : 0;
         const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         double grad;
-        if (!MULTI) {
+        if (FASTM) {
+          const int jt = jc[d] >> NBL_TSHIFT;
+          const int col1 = jt * nt + it, col2 = it * nt + jt;
+          if (!((r2 < T.rho.end[col1]) || (r2 < T.rho.end[col2]))) continue;            // :1172
+          double t = fma(r2, r_is0, r_nb0);
+          if (t < 0.0) { t = 0.0; is_short = 1; }
+          // DERIV_FUNC evaluates both derivatives with its MIN(r2,end) clamp when either is in range (:1181-1200)
+          const double t1 = fmin(t, T.rho_tmax[col1]);
+          const double tk1 = __dadd_rz(t1, IMDB_TWO52);
+          const double2 h1 = rH[__double2loint(tk1) * nuR + T.umapR[col1]];
+          const double chi1 = t1 - (tk1 - IMDB_TWO52);
+          const double rho_i_strich = fma(chi1, h1.y, h1.x);
+          double rho_j_strich = rho_i_strich;
+          if (col1 != col2) {
+            const double t2 = fmin(t, T.rho_tmax[col2]);
+            const double tk2 = __dadd_rz(t2, IMDB_TWO52);
+            const double2 h2 = rH[__double2loint(tk2) * nuR + T.umapR[col2]];
+            const double chi2 = t2 - (tk2 - IMDB_TWO52);
+            rho_j_strich = fma(chi2, h2.y, h2.x);
+          }
+          grad = dFi * rho_j_strich + xj.w * rho_i_strich;
+        } else if (!MULTI) {
           if (!(r2 < r_end0)) continue;                    // :1172
           int k; double chi;
           tab_index_fast(r2, r_nb0, r_is0, k, chi, is_short);
@@ -588,7 +617,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
             grad = (dFi + xj.w) * hv + (dMi + __ldg(a.dM + j)) * (rv * (hv + hv));
           }
         } else {
-          const int jt = sorte_of(xj.w);
+          const int jt = jc[d] >> NBL_TSHIFT;
           const int col1 = jt * nt + it, col2 = it * nt + jt;
           if (!((r2 < T.rho.end[col1]) || (r2 < T.rho.end[col2]))) continue;
           int k; double chi;
@@ -606,7 +635,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
             if (EE) { const int e = k * T.rho.ncols + col2;
                       rho_j = CUB ? tab_val3(T.rhoAB[e], T.rhoCD[e], chi) : tab_val(T.rhoAB[e], T.rhoC[e], chi); }
           }
-          grad = dFi * rho_j_strich + __ldg(a.dF + j) * rho_i_strich;
+          grad = dFi * rho_j_strich + xj.w * rho_i_strich;
           // + dM_i*rho_j*rho_j' + dM_j*rho_i*rho_i' (:1204-1208); the "strich" values here are rho'/2
           if (EE) grad += 2.0 * (dMi * rho_j * rho_j_strich + __ldg(a.dM + j) * rho_i * rho_i_strich);
         }
@@ -834,17 +863,19 @@ template <int L> static int launch1_L(imdb200_sim *s, const FArgs &a)
 
 template <int L> static int launch2_L(imdb200_sim *s, const FArgs &a, int fuse)
 {
-  const bool multi = s->tabs.ntypes > 1, ts = s->tabs.smem2 > 0 && !(EEAMC && !multi);   // single-species EEAM reads rhoAB/rhoC
-  const int sm = s->tabs.smem2;
-  if (multi) return P2(L, true, false);
+  const bool multi = s->tabs.ntypes > 1;
+  // single-species EEAM reads rhoAB/rhoC; several species stage the distinct (h1,h2) columns (quadratic, no EEAM, one rho grid)
+  const bool ts = multi ? (s->tabs.smem2m > 0 && !EEAMC && !CUBIC) : (s->tabs.smem2 > 0 && !EEAMC);
+  const int sm = multi ? s->tabs.smem2m : s->tabs.smem2;
+  if (multi) return fuse ? P2(L, true, true) : P2(L, true, false);
   return fuse ? P2(L, false, true) : P2(L, false, false);
 }
 
 #if IMDB_BASE_TU
-// move_atoms can ride in the tail of pass 2 when pass 2 does not gather from pos (single species) and neither
-// the per-atom stress nor restriction vectors are in play
+// move_atoms can ride in the tail of pass 2 -- pass 2 gathers posdf, never pos -- when neither the per-atom stress nor
+// restriction vectors are in play
 int forces_can_fuse_move(const imdb200_sim *s)
-{ return s->tabs.have_eam && s->tabs.ntypes == 1 && !s->press_calc && s->n_restr == 0 &&
+{ return s->tabs.have_eam && !s->press_calc && s->n_restr == 0 &&
          s->cfg.ensemble != IMDB200_ENS_NPT_ISO && !s->tabs.have_adp; }
 
 // the passes can run boundary part first / interior part second when there is a boundary-first order and the

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_adp_pass1(AdpArgs a, DevTables T)
     const int it = sorte_of(xi.w), nt = T.ntypes, nn = a.nnb[i];
     double mx = 0.0, my = 0.0, mz = 0.0, lxx = 0.0, lyy = 0.0, lzz = 0.0, lyz = 0.0, lzx = 0.0, lxy = 0.0;
     for (int m = 0; m < nn; m++) {
-      const int j = a.nbl[nbl_index(i, m, a.L, a.R)];
+      const int j = a.nbl[nbl_index(i, m, a.L, a.R)] & NBL_JMASK;
       const double4 xj = ld_atom(a.pos + j);
       const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
       const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_adp_pass2(AdpArgs a, DevTables T)
     double fx = 0.0, fy = 0.0, fz = 0.0, vir = 0.0;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
     for (int m = 0; m < nn; m++) {
-      const int j = a.nbl[nbl_index(i, m, a.L, a.R)];
+      const int j = a.nbl[nbl_index(i, m, a.L, a.R)] & NBL_JMASK;
       const double4 xj = ld_atom(a.pos + j);
       const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
       const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));

@@ -76,6 +76,12 @@ struct DevTables {
   const double *rawP, *rawR;          // [nrows+2][nuP], [nrows+2][nuR]
   int nuP, nuR, raw_ok;               // distinct columns; raw_ok: smem1 holds the raw layout
   signed char umapP[IMDB_MAXCOL], umapR[IMDB_MAXCOL];
+  // Several species, pass 2: (h1,h2) of the DISTINCT rho columns, [nrows][nuR], staged in shared memory (smem2m bytes) when every
+  // rho column lives on one r^2 grid (rho_uniform); rho_tmax[col] = (end-begin)*invstep, the MIN(r2,end) clamp of DERIV_FUNC as an
+  // upper bound on the table coordinate
+  const double2 *rhoHd;
+  double rho_tmax[IMDB_MAXCOL];
+  int rho_uniform, smem2m;
 };
 
 // ---- geometry ------------------------------------------------------------------------------------
@@ -215,6 +221,11 @@ struct imdb200_sim {
 // A pair of group q can only be inside the cut-off once 2*max|displacement| > (q-1)*w, so a force call walks the
 // groups 0..cls only (cls from the last skin check); the entries it leaves out would all fail the r2 test.
 #define NBL_CLASSES 4
+// A list entry is the index of the neighbour (own atom or image, < 2^29, checked in launch_build) with the neighbour's TYPE in
+// bits 29-30 (ntypes <= 4): the several-species force kernels need the type to pick the table column, and with it in the entry
+// pass 2 gathers one 32-byte record (x, y, z, F') per neighbour instead of a position record plus F'.  Single species: plain index.
+#define NBL_TSHIFT 29
+#define NBL_JMASK 0x1fffffff
 #define NBL_CBITS 12
 
 #define NBIN_EXTRA 29   // 27 leave directions + 1 dropped + 1 spare (exclusive-scan total)

@@ -179,6 +179,7 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
   size_t bytes1 = (size_t) pair->maxsteps * pair->ncols * per1 + 8, bytes2 = 0;
   // cellsz = max end of the radial tables (src/imd_potential.c:364, 406)
   double cz = 0.0;
+  std::vector<double2> hh;                                       // (h1,h2) of rho, [nrows][ncols]
   for (int col = 0; col < pair->ncols; col++) cz = cz > pair->end[col] ? cz : pair->end[col];
   if (rho) {
     for (int col = 0; col < rho->ncols; col++) cz = cz > rho->end[col] ? cz : rho->end[col];
@@ -203,7 +204,7 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
     split_coefs(hr, ab, c, cd);
     TRY(upload(s, 3, ab, &T.rhoAB));
     if (cubic) TRY(upload(s, 4, cd, &T.rhoCD)); else TRY(upload(s, 4, c, &T.rhoC));
-    std::vector<double2> hh(ab.size());
+    hh.assign(ab.size(), make_double2(0.0, 0.0));
     std::vector<double> h3((ab.size() + 1) / 2 * 2, 0.0);
     for (int k = 0; k < rho->maxsteps; k++)
       for (int col = 0; col < rho->ncols; col++) {
@@ -251,10 +252,11 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
   if (nt > 1 && !cubic) {
     // raw samples of the distinct columns (see DevTables::rawP): two columns are the same function when their headers
     // and all their samples (pad rows included) agree bit for bit
-    auto distinct = [](const HostTab &h, signed char *umap, std::vector<double> &out) {
+    int rep[IMDB_MAXCOL];
+    auto distinct = [&rep](const HostTab &h, signed char *umap, std::vector<double> &out) {
       const imdb200_pot_table *pt = h.pt;
       const int nc = pt->ncols; const size_t rows = (size_t) pt->maxsteps + 2;
-      int nu = 0, rep[IMDB_MAXCOL];
+      int nu = 0;
       for (int c = 0; c < nc; c++) {
         int u = -1;
         for (int q = 0; q < nu && u < 0; q++) {
@@ -281,6 +283,22 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
       // both raw blocks in one allocation slot would need a 13th slot: the rho block rides behind the fused slot (unused here)
       TRY(upload(s, 6, rr, &T.rawR));
       rawbytes += rr.size() * 8;
+      // pass 2: (h1,h2) of the distinct rho columns (rep[] still holds their representatives); slot 7 is the cubic modes' h3
+      T.rho_uniform = 1;
+      for (int col = 0; col < rho->ncols; col++) {
+        if (rho->begin[col] != rho->begin[0] || rho->invstep[col] != rho->invstep[0]) T.rho_uniform = 0;
+        const double r2a = rho->end[col] - rho->begin[col];          // MIN(r2,end) - begin, then * istep (src/potaccess.h:331-341)
+        T.rho_tmax[col] = r2a * rho->invstep[col];
+      }
+      std::vector<double2> hd((size_t) rho->maxsteps * T.nuR);
+      for (int k = 0; k < rho->maxsteps; k++)
+        for (int q = 0; q < T.nuR; q++) {
+          const size_t e = (size_t) k * rho->ncols + rep[q];
+          hd[(size_t) k * T.nuR + q] = hh[e];
+        }
+      TRY(upload(s, 7, hd, &T.rhoHd));
+      const size_t b2m = hd.size() * 16;
+      T.smem2m = (T.rho_uniform && b2m <= 160 * 1024) ? (int) b2m : 0;
     }
     if (rawbytes <= 160 * 1024) { T.raw_ok = 1; bytes1 = rawbytes + 16; }
   }

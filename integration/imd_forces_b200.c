@@ -226,15 +226,33 @@ static void b200_scalars(int forces, int kinetic)
   last_nbl_len = (int) (sc.nbl_len / 2);        /* the reference counts each pair once */
 }
 
+/* Where every atom sits in IMD's cells (b_cell, b_slot, by upload index): make_box() re-plans the host cells once the box
+   has changed enough (init_cells moves the atoms into a new cell array, src/imd_geom_3d.c:353-398), and the map the
+   downloads write through has to follow. */
+static void b200_remap(void)
+{
+#ifndef MPI
+  int k, i;
+  for (k = 0; k < NCELLS; k++) {
+    cell *p = CELLPTR(k);
+    for (i = 0; i < p->n; i++) { const int a = num2idx[NUMMER(p,i)]; b_cell[a] = k; b_slot[a] = i; }
+  }
+#endif
+}
+
 /* the device's box -> IMD's box_x/y/z (+ make_box for tbox, volume, heights) */
 static void b200_mirror_box(void)
 {
   double b[9];
+  const void *cells_before = (const void *) cell_array;
+  const ivektor dim_before = cell_dim;
   b200_check(imdb200_get_box(b200, b));
   box_x.x = b[0]; box_x.y = b[1]; box_x.z = b[2];
   box_y.x = b[3]; box_y.y = b[4]; box_y.z = b[5];
   box_z.x = b[6]; box_z.y = b[7]; box_z.z = b[8];
   make_box();
+  if ((const void *) cell_array != cells_before || cell_dim.x != dim_before.x || cell_dim.y != dim_before.y ||
+      cell_dim.z != dim_before.z) b200_remap();
 }
 
 #ifdef NPT_iso
