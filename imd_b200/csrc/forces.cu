@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
   constexpr bool FUSED = EAM && !MULTI && SHARED && !CUB;  // one 48-byte record per interval, see DevTables::fused
   constexpr bool FAST1 = FUSED && TSMEM && !STRESS && !EE && IMDB_BRANCHFREE;   // the branch-free block body below
   constexpr bool RAW = MULTI && TSMEM && !CUB;             // several species: raw samples of the distinct columns in shared memory
+  constexpr bool MU = MULTI && !RAW;                       // several species with per-column table headers (general path)
   const double *rawP = nullptr, *rawR = nullptr;
   const unsigned s_tab = (unsigned) __cvta_generic_to_shared(smem_raw);
   const unsigned k_max = (unsigned) (T.fused_rows - 1);
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
     __syncthreads();
     pAB = sAB; rAB = sAB + np; pC = sC; rC = sC + npe;
   }
-  const int nt = T.ntypes;
-  // per-column constants of the single-species case live in registers
+  const int nt = T.ntypes, nuP = T.nuP, nuR = T.nuR;
+  // per-column constants of the single-species case (and of several species with one header per table) live in registers
   const double p_end0 = T.pair.end[0], p_is0 = T.pair.invstep[0], p_nb0 = -T.pair.begin[0] * T.pair.invstep[0];
   const double r_end0 = EAM ? T.rho.end[0] : 0.0, r_is0 = EAM ? T.rho.invstep[0] : 0.0,
                r_nb0 = EAM ? -T.rho.begin[0] * T.rho.invstep[0] : 0.0;
@@ -248,9 +249,14 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
     int it = 0;
     double4 xi = make_double4(0.0, 0.0, 0.0, 0.0);
+    unsigned upk = 0u, urk = 0u;                           // RAW: distinct-column index of (it, jt), four bits per jt
     if (act) {
       xi = a.pos[i];
       if (MULTI) it = sorte_of(xi.w);
+      if (RAW) {
+        for (int jt = 0; jt < nt; jt++) { upk |= (unsigned) T.umapP[it * nt + jt] << (4 * jt);
+                                          if (EAM) urk |= (unsigned) T.umapR[it * nt + jt] << (4 * jt); }
+      }
       const long lslot = slot & ~(long) (IMDB_EXP_BCAST - 1);
       const int nn = (int) ((a.nnbc[lslot / L] >> cls_shift) & ((1u << NBL_CBITS) - 1));
       const int *row = a.nbl + (size_t) (lslot >> 5) * ((size_t) a.rows * 32) + (lslot & 31);
@@ -344,17 +350,18 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
         const double4 xj = xq[d];
         const double dx = xj.x - xi.x, dy = xj.y - xi.y, dz = xj.z - xi.z;
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        const int col = MULTI ? it * nt + sorte_of(xj.w) : 0;
-        const bool inp = r2 <= (MULTI ? T.pair.end[col] : p_end0);               // :493
-        const bool inr = EAM && r2 < (MULTI ? T.rho.end[col] : r_end0);          // :588
+        const int jt = MULTI ? sorte_of(xj.w) : 0;
+        const int col = MULTI ? it * nt + jt : 0;
+        const bool inp = r2 <= (MU ? T.pair.end[col] : p_end0);                  // :493
+        const bool inr = EAM && r2 < (MU ? T.rho.end[col] : r_end0);             // :588
         if (!(inp || inr)) continue;
         int k = 0, kr = 0; double chi = 0.0, chir = 0.0;
-        const double pis = MULTI ? T.pair.invstep[col] : p_is0;
-        if (inp || SHARED) { tab_index_fast(r2, MULTI ? -T.pair.begin[col] * pis : p_nb0, pis, k, chi, is_short); EXP_K(k); }
+        const double pis = MU ? T.pair.invstep[col] : p_is0;
+        if (inp || SHARED) { tab_index_fast(r2, MU ? -T.pair.begin[col] * pis : p_nb0, pis, k, chi, is_short); EXP_K(k); }
         if (EAM) {
           if (SHARED) { kr = k; chir = chi; }
-          else if (inr) { const double ris = MULTI ? T.rho.invstep[col] : r_is0;
-                          tab_index_fast(r2, MULTI ? -T.rho.begin[col] * ris : r_nb0, ris, kr, chir, is_short); }
+          else if (inr) { const double ris = MU ? T.rho.invstep[col] : r_is0;
+                          tab_index_fast(r2, MU ? -T.rho.begin[col] * ris : r_nb0, ris, kr, chir, is_short); }
         }
         double2 fmid = make_double2(0.0, 0.0);
         if (FUSED) fmid = fT[3 * k + 1];                     // (phi c2, rho c2)
@@ -364,8 +371,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
           if (RAW) {
             // PAIR_INT2's own operands: p0, p1, p2 of rows k..k+2, dv = p1-p0, d2v = p2-2p1+p0 (src/potaccess.h:345-349);
             // (c0,c1,c2) = (p0, dv - d2v/2, d2v/2) are what the coefficient tables hold, formed here with the same operations
-            const double *t = rawP + k * T.nuP + T.umapP[col];
-            const double p0 = t[0], p1 = t[T.nuP], p2 = t[2 * T.nuP];
+            const double *t = rawP + k * nuP + ((upk >> (4 * jt)) & 15u);
+            const double p0 = t[0], p1 = t[nuP], p2 = t[2 * nuP];
             const double c2 = 0.5 * ((p2 - 2 * p1) + p0), c1 = (p1 - p0) - c2;
             pot = tab_val(make_double2(p0, c1), c2, chi); grad = tab_grad(make_double2(p0, c1), c2, chi, pis + pis);
           } else {
@@ -384,8 +391,8 @@ __global__ void __launch_bounds__(NT, 1) k_pass1(FArgs a, DevTables T)
           const int e = MULTI ? kr * T.rho.ncols + col : kr;
           double rv;
           if (RAW) {
-            const double *t = rawR + kr * T.nuR + T.umapR[col];
-            const double p0 = t[0], p1 = t[T.nuR], p2 = t[2 * T.nuR];
+            const double *t = rawR + kr * nuR + ((urk >> (4 * jt)) & 15u);
+            const double p0 = t[0], p1 = t[nuR], p2 = t[2 * nuR];
             const double c2 = 0.5 * ((p2 - 2 * p1) + p0), c1 = (p1 - p0) - c2;
             rv = tab_val(make_double2(p0, c1), c2, chir);
           }
@@ -502,6 +509,9 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
       const double4 xi = gat[i];
       const int it = MULTI ? sorte_of(reinterpret_cast<const double *>(a.pos + i)[3]) : 0;
       const double dFi = xi.w;
+      unsigned uk1 = 0u, uk2 = 0u;                        // FASTM: distinct-column index of (jt, it) and (it, jt), four bits per jt
+      if (FASTM) for (int jt = 0; jt < nt; jt++) { uk1 |= (unsigned) T.umapR[jt * nt + it] << (4 * jt);
+                                                   uk2 |= (unsigned) T.umapR[it * nt + jt] << (4 * jt); }
       const double dMi = EE ? a.dM[i] : 0.0;
       const long lslot = slot & ~(long) (IMDB_EXP_BCAST - 1);
       const int nn = (int) ((a.nnbc[lslot / L] >> cls_shift) & ((1u << NBL_CBITS) - 1));
@@ -578,25 +588,16 @@ __global__ void __launch_bounds__(NT, 1) k_pass2(FArgs a, DevTables T)
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         double grad;
         if (FASTM) {
+          // one header for all rho columns (DevTables::multi_uniform): one cut-off, one (k, chi), no clamp inside it
+          if (!(r2 < r_end0)) continue;                                                // :1172
+          int k; double chi;
+          tab_index_fast(r2, r_nb0, r_is0, k, chi, is_short);
           const int jt = jc[d] >> NBL_TSHIFT;
-          const int col1 = jt * nt + it, col2 = it * nt + jt;
-          if (!((r2 < T.rho.end[col1]) || (r2 < T.rho.end[col2]))) continue;            // :1172
-          double t = fma(r2, r_is0, r_nb0);
-          if (t < 0.0) { t = 0.0; is_short = 1; }
-          // DERIV_FUNC evaluates both derivatives with its MIN(r2,end) clamp when either is in range (:1181-1200)
-          const double t1 = fmin(t, T.rho_tmax[col1]);
-          const double tk1 = __dadd_rz(t1, IMDB_TWO52);
-          const double2 h1 = rH[__double2loint(tk1) * nuR + T.umapR[col1]];
-          const double chi1 = t1 - (tk1 - IMDB_TWO52);
-          const double rho_i_strich = fma(chi1, h1.y, h1.x);
+          const unsigned u1 = (uk1 >> (4 * jt)) & 15u, u2 = (uk2 >> (4 * jt)) & 15u;
+          const double2 h1 = rH[k * nuR + u1];
+          const double rho_i_strich = fma(chi, h1.y, h1.x);                            // column (jt, it)
           double rho_j_strich = rho_i_strich;
-          if (col1 != col2) {
-            const double t2 = fmin(t, T.rho_tmax[col2]);
-            const double tk2 = __dadd_rz(t2, IMDB_TWO52);
-            const double2 h2 = rH[__double2loint(tk2) * nuR + T.umapR[col2]];
-            const double chi2 = t2 - (tk2 - IMDB_TWO52);
-            rho_j_strich = fma(chi2, h2.y, h2.x);
-          }
+          if (u1 != u2) { const double2 h2 = rH[k * nuR + u2]; rho_j_strich = fma(chi, h2.y, h2.x); }   // column (it, jt)
           grad = dFi * rho_j_strich + xj.w * rho_i_strich;
         } else if (!MULTI) {
           if (!(r2 < r_end0)) continue;                    // :1172

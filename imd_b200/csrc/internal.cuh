@@ -76,12 +76,11 @@ struct DevTables {
   const double *rawP, *rawR;          // [nrows+2][nuP], [nrows+2][nuR]
   int nuP, nuR, raw_ok;               // distinct columns; raw_ok: smem1 holds the raw layout
   signed char umapP[IMDB_MAXCOL], umapR[IMDB_MAXCOL];
-  // Several species, pass 2: (h1,h2) of the DISTINCT rho columns, [nrows][nuR], staged in shared memory (smem2m bytes) when every
-  // rho column lives on one r^2 grid (rho_uniform); rho_tmax[col] = (end-begin)*invstep, the MIN(r2,end) clamp of DERIV_FUNC as an
-  // upper bound on the table coordinate
+  // Several species, pass 2: (h1,h2) of the DISTINCT rho columns, [nrows][nuR], staged in shared memory (smem2m bytes).
+  // multi_uniform: every column of the pair table has the same begin / end / invstep, and so has every column of the rho
+  // table -- the condition for the shared-memory paths of both passes (raw_ok, smem2m), which keep the headers in registers
   const double2 *rhoHd;
-  double rho_tmax[IMDB_MAXCOL];
-  int rho_uniform, smem2m;
+  int multi_uniform, smem2m;
 };
 
 // ---- geometry ------------------------------------------------------------------------------------

@@ -273,6 +273,7 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
       return nu;
     };
     std::vector<double> rp, rr;
+    size_t b2m = 0;
     T.nuP = distinct(hp, T.umapP, rp);
     if (rp.size() % 2) rp.push_back(0.0);                 // staged 16 bytes at a time
     TRY(upload(s, 11, rp, &T.rawP));
@@ -284,28 +285,29 @@ int tables_upload(imdb200_sim *s, const imdb200_pot_table *pair, const imdb200_p
       TRY(upload(s, 6, rr, &T.rawR));
       rawbytes += rr.size() * 8;
       // pass 2: (h1,h2) of the distinct rho columns (rep[] still holds their representatives); slot 7 is the cubic modes' h3
-      T.rho_uniform = 1;
-      for (int col = 0; col < rho->ncols; col++) {
-        if (rho->begin[col] != rho->begin[0] || rho->invstep[col] != rho->invstep[0]) T.rho_uniform = 0;
-        const double r2a = rho->end[col] - rho->begin[col];          // MIN(r2,end) - begin, then * istep (src/potaccess.h:331-341)
-        T.rho_tmax[col] = r2a * rho->invstep[col];
-      }
       std::vector<double2> hd((size_t) rho->maxsteps * T.nuR);
       for (int k = 0; k < rho->maxsteps; k++)
-        for (int q = 0; q < T.nuR; q++) {
-          const size_t e = (size_t) k * rho->ncols + rep[q];
-          hd[(size_t) k * T.nuR + q] = hh[e];
-        }
+        for (int q = 0; q < T.nuR; q++) hd[(size_t) k * T.nuR + q] = hh[(size_t) k * rho->ncols + rep[q]];
       TRY(upload(s, 7, hd, &T.rhoHd));
-      const size_t b2m = hd.size() * 16;
-      T.smem2m = (T.rho_uniform && b2m <= 160 * 1024) ? (int) b2m : 0;
+      b2m = hd.size() * 16;
     }
-    if (rawbytes <= 160 * 1024) { T.raw_ok = 1; bytes1 = rawbytes + 16; }
+    // One header for all columns of a table (the usual case: alloy EAM files carry one r grid): begin, end and invstep
+    // are scalars in the kernels, and inside the cut-off the MIN(r2,end) clamp of PAIR_INT2 / DERIV_FUNC is inactive.
+    // Tables with per-column headers take the general path (coefficient tables in HBM / L1).
+    T.multi_uniform = 1;
+    for (int col = 0; col < pair->ncols; col++) {
+      if (pair->begin[col] != pair->begin[0] || pair->end[col] != pair->end[0] || pair->invstep[col] != pair->invstep[0]) T.multi_uniform = 0;
+      if (rho && (rho->begin[col] != rho->begin[0] || rho->end[col] != rho->end[0] || rho->invstep[col] != rho->invstep[0])) T.multi_uniform = 0;
+    }
+    T.smem2m = (T.multi_uniform && b2m && b2m <= 160 * 1024) ? (int) b2m : 0;
+    if (T.multi_uniform && rawbytes <= 160 * 1024) { T.raw_ok = 1; bytes1 = rawbytes + 16; }
   }
   // Tables are staged in shared memory when they leave at least ~100 KB of the 228 KB SM array to L1
   // (the position gathers live there); otherwise they stay in HBM and are served by L1/L2.
   const size_t limit = 128 * 1024;
-  T.smem1 = (bytes1 <= limit || T.raw_ok) ? (int) bytes1 : 0;
+  // several species, quadratic: shared memory holds the raw layout or nothing (the kernels' RAW path assumes multi_uniform)
+  if (nt > 1 && !cubic) T.smem1 = T.raw_ok ? (int) bytes1 : 0;
+  else T.smem1 = bytes1 <= limit ? (int) bytes1 : 0;
   T.smem2 = (bytes2 && bytes2 <= limit) ? (int) bytes2 : 0;
   tables_set_cellsz0(s, cz);
   s->have_tabs = 1;

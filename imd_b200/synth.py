@@ -88,11 +88,35 @@ def write_table1(path, r2, columns, fmt="%.16e"):
 
 
 def make_eam_tables(outdir, kind="cu", prefix=None, nr=2001, nrho=4001,
-                    r2_begin=1.0, rho_end=40.0):
-    """Write <prefix>_phi.pot, _rho.pot, _F.pot (format 2).  Returns dict of paths + r_cut."""
+                    r2_begin=1.0, rho_end=40.0, per_column=False):
+    """Write <prefix>_phi.pot, _rho.pot, _F.pot (format 2).  Returns dict of paths + r_cut.
+    per_column: every column gets its own begin / end / step (phi_AB and phi_BA stay one function), the way hand-made IMD
+    tables may look -- the case the kernels' general several-species path exists for."""
     os.makedirs(outdir, exist_ok=True)
     prefix = prefix or kind
     phi, rho, F, nt, rc = eam_functions(kind)
+    if per_column:
+        ncol = nt * nt
+        paths = {
+            "core_potential_file": os.path.join(outdir, f"{prefix}_phi.pot"),
+            "atomic_e-density_file": os.path.join(outdir, f"{prefix}_rho.pot"),
+            "embedding_energy_file": os.path.join(outdir, f"{prefix}_F.pot"),
+        }
+        def grid(b, e):
+            st = (e - b) / (nr - 1)
+            return b, e, st, np.sqrt(b + st * np.arange(nr))
+        pg = [grid(r2_begin + 0.04 * ((c // nt) + (c % nt)), (rc - 0.07 * ((c // nt) + (c % nt))) ** 2) for c in range(ncol)]
+        rg = [grid(r2_begin + 0.03 * (c % nt) + 0.01 * (c // nt), (rc - 0.11 * (c % nt) - 0.02 * (c // nt)) ** 2) for c in range(ncol)]
+        write_table2(paths["core_potential_file"], [g[0] for g in pg], [g[1] for g in pg], [g[2] for g in pg],
+                     [phi(pg[c][3], c // nt, c % nt) for c in range(ncol)])
+        write_table2(paths["atomic_e-density_file"], [g[0] for g in rg], [g[1] for g in rg], [g[2] for g in rg],
+                     [rho(rg[c][3], c // nt, c % nt) for c in range(ncol)])
+        rstep = rho_end / (nrho - 1)
+        x = rstep * np.arange(nrho)
+        write_table2(paths["embedding_energy_file"], [0.0] * nt, [rho_end] * nt, [rstep] * nt, [F(x, a) for a in range(nt)])
+        paths["r_cut"] = rc
+        paths["ntypes"] = nt
+        return paths
     r2_end = rc * rc
     step = (r2_end - r2_begin) / (nr - 1)
     r2 = r2_begin + step * np.arange(nr)

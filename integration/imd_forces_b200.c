@@ -316,11 +316,26 @@ static void b200_move_atoms(void)
   if (sync_due(steps) || press) b200_download(0, sync_due(steps), press);   /* writers run after move_atoms of the same step (src/imd_main_3d.c:690-694) */
 }
 
+#ifdef IMD_B200_BACKTRACE   /* debugging aid of this binding (not part of IMD): where did a SIGSEGV come from */
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void b200_segv(int sig)
+{
+  void *bt[48]; int n = backtrace(bt, 48);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(128 + sig);
+}
+#endif
+
 static void b200_init(void)
 {
   imdb200_config cfg;
   char *e = getenv("IMD_B200_SYNC");
   if (e) sync_int = atoi(e);
+#ifdef IMD_B200_BACKTRACE
+  signal(SIGSEGV, b200_segv);
+#endif
   imdb200_set_error_handler(b200_fatal);
   imdb200_default_config(&cfg);
   cfg.ntypes = ntypes; cfg.total_types = vtypes;
@@ -434,6 +449,49 @@ void __wrap_lin_deform(vektor dx, vektor dy, vektor dz, real scale)
   b200_check(imdb200_lin_deform(b200, ax, ay, az, scale));
   b200_mirror_box();                                                     /* IMD's box follows the device's, bit for bit */
   b200_scalars(0, 0);
+}
+#endif
+
+#ifdef HOMDEF
+/* void relax_pressure(void)  (src/imd_deform.c:127-219), linked with --wrap.  It ends in a call of lin_deform inside its own
+   translation unit, which the linker cannot redirect (--wrap only catches references across object files), so the unmodified
+   function would deform IMD's host copy and leave the device behind.  Its few lines are restated here on IMD's own globals:
+   the deviation of the stress tensor (calc_tot_presstens on the per-atom tensor the engine downloads while relax_rate > 0,
+   src/imd_main_3d.c:183-194) from presstens_ext, turned into a strain by the bulk / shear modulus estimates and applied
+   through the binding's lin_deform. */
+void __real_relax_pressure(void);
+void __wrap_relax_pressure(void)
+{
+  vektor ex = {0.0, 0.0, 0.0}, ey = {0.0, 0.0, 0.0}, ez = {0.0, 0.0, 0.0};
+  if (b200 == NULL) { __real_relax_pressure(); return; }
+#ifdef STRESS_TENS
+  {
+    real sxx, syy, szz, syz, szx, sxy, mean;
+    calc_tot_presstens();
+    sxx = tot_presstens.xx / volume - presstens_ext.xx;  syy = tot_presstens.yy / volume - presstens_ext.yy;
+    szz = tot_presstens.zz / volume - presstens_ext.zz;  syz = tot_presstens.yz / volume - presstens_ext.yz;
+    szx = tot_presstens.zx / volume - presstens_ext.zx;  sxy = tot_presstens.xy / volume - presstens_ext.xy;
+    mean = (sxx * relax_dirs.x + syy * relax_dirs.y + szz * relax_dirs.z) / (relax_dirs.x + relax_dirs.y + relax_dirs.z);   /* :152 */
+    if (relax_mode == RELAX_FULL || relax_mode == RELAX_AXIAL) {            /* :157-163 */
+      ex.x = mean / bulk_module + (sxx - mean) / shear_module;
+      ey.y = mean / bulk_module + (syy - mean) / shear_module;
+      ez.z = mean / bulk_module + (szz - mean) / shear_module;
+    } else ex.x = ey.y = ez.z = mean / bulk_module;                          /* :164-170 */
+    if (relax_mode == RELAX_FULL) {                                          /* :171-177 */
+      ex.y = ey.x = sxy / shear_module;
+      ey.z = ez.y = syz / shear_module;
+      ez.x = ex.z = szx / shear_module;
+    }
+  }
+#else
+  {                                                                          /* scalar pressure, relaxed towards zero :179-204 */
+    real temp = 2.0 * tot_kin_energy / nactive;
+    pressure = temp / (volume / natoms) + virial / (DIM * volume);
+    ex.x = ey.y = ez.z = pressure / bulk_module;
+  }
+#endif
+  if (relax_mode == RELAX_AXIAL) { ex.x *= relax_dirs.x; ey.y *= relax_dirs.y; ez.z *= relax_dirs.z; }   /* :206-212 */
+  __wrap_lin_deform(ex, ey, ez, relax_rate);
 }
 #endif
 

@@ -286,6 +286,67 @@ def test_cuda_vs_oracle_seeded_16k(api, lanes, tmp_path):
     c.close()
 
 
+def _thermal_nial(tmp_path, ncell, temp=0.06, seed=5, **tabkw):
+    tabs = synth.make_eam_tables(str(tmp_path), "nial", **tabkw)
+    a0 = 2.88
+    ix, iy, iz = np.meshgrid(np.arange(ncell[0]), np.arange(ncell[1]), np.arange(ncell[2]), indexing="ij")
+    cells = np.stack([ix, iy, iz], -1).reshape(-1, 1, 3).astype(np.float64)
+    ort = ((cells + np.array([[0.25, 0.25, 0.25], [0.75, 0.75, 0.75]])[None]) * a0).reshape(-1, 3)   # B2: Ni corner, Al centre
+    n = len(ort)
+    typ = (np.arange(n) % 2).astype(np.int32)
+    rng = np.random.default_rng(seed)
+    ort = ort + rng.normal(0, 0.04, ort.shape)
+    masse = np.where(typ == 0, synth.NI_MASS, synth.AL_MASS)
+    p = synth.maxwell_momenta(n, masse, temp, seed)
+    box = np.diag([ncell[0] * a0, ncell[1] * a0, ncell[2] * a0]).astype(np.float64)
+    kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"])
+    return kw, box, np.arange(n, dtype=np.int32), typ, masse, ort, p
+
+
+@pytest.mark.parametrize("per_column", [True, False])
+def test_cuda_two_species_vs_oracle_seeded(api, per_column, tmp_path):
+    """3 456 thermal Ni-Al atoms through the CPU oracle and the CUDA path.  per_column: every table column has its own
+    begin / end / step, which takes the kernels' general several-species path (per-column headers, the MIN(r2,end) clamp of
+    DERIV_FUNC when only one of the two densities is in range); else the shared-memory paths with one header per table."""
+    from oracle import oracle as orc
+    kw, box, num, typ, m, x, p = _thermal_nial(tmp_path, (12, 12, 12), nr=601, nrho=801, per_column=per_column)
+    o = orc.OracleIMD(2, box, **kw)
+    o.set_atoms(num, typ, m, x, p); o.set_integrator("nvt", 0.001, 0.06, 0.0, 100.0)
+    c = api.IMDB200(2, box, ensemble="nvt", timestep=0.001, temperature=0.06, eta=0.0, isq_tau_eta=100.0, **kw)
+    c.set_atoms(num, typ, m, x, p)
+    for s in range(6):
+        o.calc_forces(s); c.calc_forces(s)
+        if s in (0, 5):
+            a, b = o.atoms(), c.atoms()
+            tol = 1e-10 if s == 0 else 1e-8
+            for k in ("kraft", "poteng", "rho", "dF"):
+                assert common.relerr(b[k], a[k]) <= tol, (s, k, common.relerr(b[k], a[k]))
+            so, sc = o.scalars(), c.scalars()
+            assert abs(sc["tot_pot_energy"] - so["tot_pot_energy"]) <= tol * abs(so["tot_pot_energy"])
+            assert abs(sc["virial"] - so["virial"]) <= tol * abs(so["virial"])
+        o.move_atoms(); c.move_atoms(); o.check_nblist(); c.check_nblist()
+        assert o.have_valid_nbl == c.have_valid_nbl
+        assert abs(c.scalars()["tot_kin_energy"] - o.scalars()["tot_kin_energy"]) <= 1e-9 * o.scalars()["tot_kin_energy"]
+    c.close()
+
+
+@pytest.mark.parametrize("ensemble", ["nve", "nvt"])
+def test_cuda_two_species_run_loop_equals_stepwise_calls(api, ensemble, tmp_path):
+    """Several species: imdb200_run (move_atoms fused into the tail of pass 2, which gathers (x,y,z,F') records and takes
+    the neighbour's type from the list entry) against the three separate calls: bit-identical."""
+    kw, box, num, typ, m, x, p = _thermal_nial(tmp_path, (10, 10, 10), temp=0.12, nr=601, nrho=801)
+    kw = dict(kw, ensemble=ensemble, timestep=0.001, temperature=0.12, eta=0.0, isq_tau_eta=100.0)
+    a = api.IMDB200(2, box, **kw); a.set_atoms(num, typ, m, x, p)
+    b = api.IMDB200(2, box, **kw); b.set_atoms(num, typ, m, x, p)
+    a.run(30)
+    for s in range(30):
+        b.calc_forces(s); b.move_atoms(); b.check_nblist()
+    A, B = a.atoms(), b.atoms()
+    assert np.array_equal(A["ort"], B["ort"]) and np.array_equal(A["impuls"], B["impuls"])
+    assert a.nbl_count == b.nbl_count and a.nbl_count >= 2
+    a.close(); b.close()
+
+
 def test_cuda_run_loop_equals_stepwise_calls(api, tmp_path):
     """imdb200_run (device-resident loop) must give bit-identical state to the three separate calls."""
     tabs, box, num, typ, m, x, p = _thermal_cu(tmp_path, (8, 8, 8), temp=0.15)
