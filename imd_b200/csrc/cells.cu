@@ -473,7 +473,8 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
     const int cz = c1 % g.cdim[2], cy = (c1 / g.cdim[2]) % g.cdim[1], cx = c1 / (g.cdim[2] * g.cdim[1]);
     unsigned *const my = bits + threadIdx.x;
     // ---- phase 1 ----
-    int cs = 0;
+    unsigned long long nz = 0ull;                             // words with survivors (WT = 1, 2: at most 54 words), so that the walks
+    int cs = 0;                                               // below jump to the next one instead of scanning for it
     for (int l = -1; l <= 1; l++)
       for (int m = -1; m <= 1; m++) {
         const int crow = ((cx + l) * g.cdim[1] + (cy + m)) * g.cdim[2] + cz;
@@ -485,7 +486,9 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
           if (nj > 32 * W) atomicMax(&flags[FL_CELLFULL], nj);
           for (int w = 0; w < W; w++) {
             const int lo = 32 * w, cntw = min(nj - lo, 32);
-            my[(cs * W + w) * BS] = cntw > 0 ? nbl_scan_word(posf, j0 + lo, cntw, xf, yf, zf, cutf) : 0u;
+            const unsigned wd = cntw > 0 ? nbl_scan_word(posf, j0 + lo, cntw, xf, yf, zf, cutf) : 0u;
+            my[(cs * W + w) * BS] = wd;
+            if (WT > 0 && wd) nz |= 1ull << (cs * W + w);
           }
         }
       }
@@ -496,11 +499,13 @@ k_build_nbl2(const double4 *__restrict__ pos, const float4 *__restrict__ posf, i
     unsigned long long counts = 0ull;
 #define NBL_WALK(BODY) do { \
       int wi = -1, jb = 0; bool mirror = false; unsigned word = 0u, keep = 0u; \
+      unsigned long long todo = nz; nz = 0ull; \
       for (;;) { \
         if (word == 0u) {                       /* this lane moves on to its next non-empty word */ \
-          if (wi >= 0) my[wi * BS] = keep; \
-          for (++wi; wi < nwords; ++wi) { word = my[wi * BS]; if (word) break; } \
-          if (wi >= nwords) break; \
+          if (wi >= 0) { my[wi * BS] = keep; if (WT > 0 && keep) nz |= 1ull << wi; } \
+          if (WT > 0) { if (todo == 0ull) break; wi = __ffsll((long long) todo) - 1; todo &= todo - 1; word = my[wi * BS]; } \
+          else { for (++wi; wi < nwords; ++wi) { word = my[wi * BS]; if (word) break; } \
+                 if (wi >= nwords) break; } \
           const int cs_ = wi / W, l_ = cs_ / 9 - 1, m_ = (cs_ / 3) % 3 - 1, n_ = cs_ % 3 - 1; \
           const int j0_ = cell_start[((cx + l_) * g.cdim[1] + (cy + m_)) * g.cdim[2] + cz + n_]; \
           const bool upper_ = (l_ > 0) || (l_ == 0 && (m_ > 0 || (m_ == 0 && n_ >= 0))); \
