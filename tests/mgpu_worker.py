@@ -42,7 +42,8 @@ def make(g, tabdir, grid, **kw):
                        timestep=float(g["timestep"]), temperature=float(g["temperature"]), eta=float(g["eta0"]),
                        isq_tau_eta=float(g["isq_tau_eta"]),
                        total_types=int(g["total_types"]) if "total_types" in g else None,
-                       interp=str(g["interp"]) if "interp" in g else "3point", emod=paths.get("emod"), **kw)
+                       interp=str(g["interp"]) if "interp" in g else "3point", emod=paths.get("emod"),
+                       adp_u=paths.get("adp_u"), adp_w=paths.get("adp_w"), **kw)
     if "restrictions" in g:
         sim.set_restrictions(g["restrictions"])
     # every rank is handed ALL atoms and keeps those of its own domain
@@ -145,6 +146,103 @@ def case_overlap(grid, rank):
     return sim
 
 
+def case_overlap_nial(grid, rank):
+    """Two species through imdb200_run over the process grid: pass 2 with the neighbour's type in the list entry, move_atoms
+    fused into its tail, boundary-first split launches and the peer-memory halo -- against the same run on one GPU."""
+    tmp = tempfile.mkdtemp(prefix=f"ovn{rank}_")
+    tabs = synth.make_eam_tables(tmp, "nial", nr=601, nrho=801)
+    nc, a0 = (28, 28, 28), 2.88
+    ix, iy, iz = np.meshgrid(np.arange(nc[0]), np.arange(nc[1]), np.arange(nc[2]), indexing="ij")
+    cells = np.stack([ix, iy, iz], -1).reshape(-1, 1, 3).astype(np.float64)
+    ort = ((cells + np.array([[0.25, 0.25, 0.25], [0.75, 0.75, 0.75]])[None]) * a0).reshape(-1, 3)
+    n = len(ort)
+    typ = (np.arange(n) % 2).astype(np.int32)
+    ort = ort + np.random.default_rng(4).normal(0, 0.04, ort.shape)
+    m = np.where(typ == 0, synth.NI_MASS, synth.AL_MASS)
+    p = synth.maxwell_momenta(n, m, 0.10, 11)
+    box = np.diag([nc[0] * a0, nc[1] * a0, nc[2] * a0]).astype(np.float64)
+    num = np.arange(n, dtype=np.int32)
+    kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"],
+              ensemble="nvt", timestep=0.001, temperature=0.10, eta=0.0, isq_tau_eta=100.0)
+    sim = idist.create(2, box, cpu_dim=grid, device=int(os.environ.get("LOCAL_RANK", "0")), **kw)
+    sim.set_atoms(num, typ, m, ort, p)
+    for _ in range(3):
+        sim.run(20)
+    a = idist.gather_atoms(sim)
+    sc = sim.scalars()
+    if rank == 0:
+        ref = api.IMDB200(2, box, device=0, **kw)
+        ref.set_atoms(num, typ, m, ort, p)
+        ref.run(60)
+        b = ref.atoms()
+        rs = ref.scalars()
+        assert np.array_equal(a["nummer"], b["nummer"])
+        d = a["ort"] - b["ort"]
+        frac = d @ np.linalg.inv(box)
+        d = (frac - np.round(frac)) @ box
+        print("overlap_nial: max |dx|", np.abs(d).max(), "max |dp|", np.abs(a["impuls"] - b["impuls"]).max(), "builds", sim.nbl_count)
+        assert np.abs(d).max() < 1e-9 and np.abs(a["impuls"] - b["impuls"]).max() < 1e-10
+        assert abs(sc["tot_pot_energy"] - rs["tot_pot_energy"]) < 1e-10 * abs(rs["tot_pot_energy"])
+        assert abs(sc["tot_kin_energy"] - rs["tot_kin_energy"]) < 1e-9 * abs(rs["tot_kin_energy"])
+        assert abs(sc["eta"] - rs["eta"]) < 1e-9 * max(abs(rs["eta"]), 1e-12)
+        assert sim.nbl_count == ref.nbl_count and sim.nbl_count >= 3
+        ref.close()
+    return sim
+
+
+def case_npt(name, grid, rank):
+    """npt_iso / npt_axial over the process grid against the reference's fixture: the barostat scalars are formed from sums
+    over all domains (virial or per-axis virial, kinetic parts), every rank breathes the same box."""
+    g = common.load_golden(name)
+    axial = str(g["ensemble"]) == "npt_axial"
+    kw = dict(isq_tau_xi=float(g["npt_start:isq_tau_xi"]))
+    if not axial:
+        kw["pressure_ext"] = float(g["npt_start:pressure_ext"])
+    sim = make(g, tempfile.mkdtemp(prefix=f"npt{rank}_"), grid, **kw)
+    if axial:
+        sim.set_npt_axial(g["npt_start:xi"], g["npt_start:pressure_ext"], g["npt_start:d_pressure"], g["npt_start:relax_dirs"],
+                          Ekin_old=float(g["npt_start:Ekin_old"]), dyn_stress=g["npt_start:dyn_stress"])
+    else:
+        sim.set_npt_state(xi=float(g["npt_start:xi"]), Ekin_old=float(g["npt_start:Ekin_old"]),
+                          pressure_ext=float(g["npt_start:pressure_ext"]))
+    worst = {}
+
+    def close(k, got, want, tol, s):
+        e = float(np.max(np.abs(np.asarray(got) - want)) / max(np.max(np.abs(want)), 1e-300))
+        worst[k] = max(worst.get(k, 0.0), e)
+        assert e <= tol, (k, s, got, want, e)
+
+    for s in range(int(g["nsteps"])):
+        tol = 1e-10 if s == 0 else 1e-8
+        sim.calc_forces(s)
+        close("epot", sim.scalars()["tot_pot_energy"], g["epot"][s], tol, s)
+        sim.move_atoms()
+        sim.check_nblist()
+        sc = sim.scalars()
+        if axial:
+            st = sim.npt_axial()
+            for k in ("xi", "stress", "pressure_ext", "dyn_stress"):
+                close(k, st[k], g["npt:" + k][s], 10 * tol, s)
+        else:
+            st = sim.npt()
+            close("xi", st["xi"], g["npt:xi"][s], 10 * tol, s)
+            close("pressure", st["pressure"], g["npt:pressure"][s], 10 * tol, s)
+        close("volume", sc["volume"], g["npt:volume"][s], 1e-10, s)
+        close("eta", sc["eta"], g["eta"][s], 10 * tol, s)
+        close("ekin", sc["tot_kin_energy"], g["ekin"][s], tol, s)
+        close("box", sim.box(), g["npt:box"][s], 1e-10, s)
+        assert sim.have_valid_nbl == int(g["valid"][s]), f"check_nblist decision differs at step {s}"
+    a = idist.gather_atoms(sim)
+    if rank == 0:
+        box = sim.box()
+        d = a["ort"] - g["final:ort"]
+        frac = d @ np.linalg.inv(box)
+        d = (frac - np.round(frac)) @ box
+        assert np.max(np.abs(d)) <= 1e-8 * np.max(np.abs(box))
+        print("npt", name, {k: f"{v:.1e}" for k, v in worst.items()})
+    return sim
+
+
 def case_send_forces(grid, rank):
     """send_forces analogue: every image carries 1.0; after the reverse exchange an owner holds the number of
     its images, which is fixed by the geometry: prod(1 + [low layer] + [high layer]) - 1 over the axes."""
@@ -201,6 +299,10 @@ def main():
         sim = case_send_forces(grid, rank)
     elif case == "overlap":
         sim = case_overlap(grid, rank)
+    elif case == "overlap_nial":
+        sim = case_overlap_nial(grid, rank)
+    elif case.startswith("npt:"):
+        sim = case_npt(case.split(":", 1)[1], grid, rank)
     else:
         raise SystemExit(f"unknown case {case}")
     dist.barrier()

@@ -61,6 +61,25 @@ def test_overlapped_halo_matches_single_gpu_run(built_lib):
     _run("overlap", (2, 1, 1), 29626)
 
 
+def test_two_species_overlapped_halo_matches_single_gpu_run(built_lib):
+    """43 904 thermal Ni-Al atoms under NVT through imdb200_run on two domains: several-species pass 2 (type in the list
+    entry, one gather record), fused move_atoms, split launches, peer-memory halo; against the run on one GPU."""
+    _run("overlap_nial", (2, 1, 1), 29629)
+
+
+@pytest.mark.parametrize("name", ["cu_npt_iso", "cu_npt_axial", "cu_npt_axial_xz"])
+def test_two_domains_npt(built_lib, name):
+    """Barostat ensembles on two domains against the reference's npt fixtures (global virial / per-axis virial and kinetic
+    sums over both ranks; both ranks breathe the same box and re-plan their halo)."""
+    _run("npt:" + name, (2, 1, 1), 29630)
+
+
+@pytest.mark.parametrize("name", ["cu_adp", "nial_adp"])
+def test_two_domains_adp(built_lib, name):
+    """ADP on two domains: mu and lambda travel with F' in the halo (nine components, src/imd_comm_force_3d.c:1047-1057)."""
+    _run("fixture:" + name, (2, 1, 1), 29631)
+
+
 @pytest.mark.parametrize("name", ["cu_big", "nial_big"])
 def test_two_domains_match_large_reference_fixture(built_lib, name):
     """131 072 Cu / 54 000 Ni-Al atoms on two domains against the unmodified single-process reference."""
