@@ -593,6 +593,8 @@ static int alloc_nbl(imdb200_sim *s, int max_nb)
   if (s->nnbc) cudaFree(s->nnbc);
   s->nbl = nullptr; s->nnb = nullptr; s->nnbc = nullptr;
   CUDA_TRY(cudaMalloc(&s->nbl, (size_t) n_pad * max_nb * sizeof(int)));
+  // slots behind an atom's last entry are never walked, but imdb200_get_nblist copies whole rows out (initcheck-clean)
+  CUDA_TRY(cudaMemsetAsync(s->nbl, 0, (size_t) n_pad * max_nb * sizeof(int), s->stream));
   CUDA_TRY(cudaMalloc(&s->nnb, (size_t) n_pad * sizeof(int)));
   CUDA_TRY(cudaMalloc(&s->nnbc, (size_t) n_pad * sizeof(unsigned long long)));
   s->max_nb = max_nb;

@@ -8,10 +8,10 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for tool in memcheck racecheck initcheck; do
   echo "== compute-sanitizer --tool $tool: smoke"
-  compute-sanitizer --tool $tool --error-exitcode 9 python __graft_entry__.py smoke nobuild > gpurun_out/sanitize_${tool}_smoke.log 2>&1
+  timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 python __graft_entry__.py smoke nobuild > gpurun_out/sanitize_${tool}_smoke.log 2>&1
   echo "   exit $?  ($(grep -c 'ERROR SUMMARY' gpurun_out/sanitize_${tool}_smoke.log) summaries: $(grep 'ERROR SUMMARY' gpurun_out/sanitize_${tool}_smoke.log | tail -1))"
 done
 echo "== compute-sanitizer --tool memcheck: fixture tests (single species, two species, deformation)"
-compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x \
-  -k "cu_nve-1 or nial_nvt-4 or cu_lindef-1 or cu_eeam-1" > gpurun_out/sanitize_memcheck_fixtures.log 2>&1
-echo "   exit $?  $(grep 'ERROR SUMMARY' gpurun_out/sanitize_memcheck_fixtures.log | tail -1)"
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x \
+  -k "cu_nve-1 or nial_nvt-4 or cu_lindef-1 or cu_eeam-1 or two_species or npt_axial" > gpurun_out/sanitize_memcheck_fixtures.log 2>&1
+echo "   exit $?  $(grep 'ERROR SUMMARY' gpurun_out/sanitize_memcheck_fixtures.log | tail -1)  $(tail -n 1 gpurun_out/sanitize_memcheck_fixtures.log)"
