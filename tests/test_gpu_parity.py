@@ -112,17 +112,21 @@ def test_cuda_npt_iso_matches_reference_fixture(api, tmp_path):
     assert r.returncode == 0 and "NPT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("case,mode", [("cu_npt_axial", "stepwise"), ("cu_npt_axial_xz", "stepwise"), ("cu_npt_axial", "run")])
+@pytest.mark.parametrize("case,mode", [("cu_npt_axial", "stepwise"), ("cu_npt_axial_xz", "stepwise"), ("cu_npt_axial", "run"),
+                                       ("cu_npt_axial_restr", "stepwise")])
 def test_cuda_npt_axial_matches_reference_fixture(api, case, mode, tmp_path):
     """IMDB200_ENS_NPT_AXIAL against the reference's `npt_axial` build (move_atoms_npt_axial, src/imd_integrate.c:1747-1959;
     P_AXIAL virial components, src/imd_forces_nbl.c:548-556): per-axis xi, stress, pressure ramp, dyn_stress, eta, the box
     and the trajectory; relax_dirs 1 0 1 holds the y axis; `run` drives the same steps through imdb200_run."""
     g = common.load_golden(case)
     paths = common.write_tables(g, str(tmp_path))
-    sim = api.IMDB200(1, g["box"], pair=paths["pair"], embed=paths["embed"], rho=paths["rho"], ensemble="npt_axial",
-                      timestep=float(g["timestep"]), temperature=float(g["temperature"]), eta=float(g["eta0"]),
-                      isq_tau_eta=float(g["isq_tau_eta"]), isq_tau_xi=float(g["npt_start:isq_tau_xi"]))
-    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"])
+    sim = api.IMDB200(1, g["box"], pbc=tuple(int(x) for x in g["pbc"]), pair=paths["pair"], embed=paths["embed"], rho=paths["rho"],
+                      ensemble="npt_axial", timestep=float(g["timestep"]), temperature=float(g["temperature"]), eta=float(g["eta0"]),
+                      isq_tau_eta=float(g["isq_tau_eta"]), isq_tau_xi=float(g["npt_start:isq_tau_xi"]),
+                      total_types=int(g["total_types"]) if "total_types" in g else None)
+    if "restrictions" in g:          # a pinned layer: restriction vectors act on the momenta after the kick (:1859-1864)
+        sim.set_restrictions(g["restrictions"])
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"], vsorte=g["start:vsorte"])
     sim.set_npt_axial(g["npt_start:xi"], g["npt_start:pressure_ext"], g["npt_start:d_pressure"], g["npt_start:relax_dirs"],
                       Ekin_old=float(g["npt_start:Ekin_old"]), dyn_stress=g["npt_start:dyn_stress"])
     press = bool(int(g["press"]))

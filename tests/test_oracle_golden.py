@@ -119,19 +119,21 @@ def test_oracle_npt_iso_matches_reference_fixture(tmp_path):
     assert np.max(np.abs(a["impuls"] - g["final:impuls"])) <= 1e-9 * np.max(np.abs(g["final:impuls"]))
 
 
-@pytest.mark.parametrize("case", ["cu_npt_axial", "cu_npt_axial_xz"])
+@pytest.mark.parametrize("case", ["cu_npt_axial", "cu_npt_axial_xz", "cu_npt_axial_restr"])
 def test_oracle_npt_axial_matches_reference_fixture(case, tmp_path):
     """move_atoms_npt_axial (src/imd_integrate.c:1747-1959) of the reference's `npt_axial` build: one barostat variable per
     box axis driven by (dyn_stress + vir)/volume of that axis (P_AXIAL builds accumulate vir_xx/yy/zz in calc_forces,
     src/imd_forces_nbl.c:548-556), a pressure ramp that differs per axis, and relax_dirs 1 0 1 holding the y axis."""
     g = common.load_golden(case)
     paths = common.write_tables(g, str(tmp_path))
-    sim = orc.OracleIMD(1, g["box"], pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
+    sim = orc.OracleIMD(1, g["box"], pbc=tuple(int(x) for x in g["pbc"]), pair=paths["pair"], embed=paths["embed"], rho=paths["rho"])
     sim.set_integrator("npt_axial", float(g["timestep"]), float(g["temperature"]), float(g["eta0"]), float(g["isq_tau_eta"]))
+    if "restrictions" in g:          # the pinned layer: restriction vectors act on the momenta after the kick (:1859-1864)
+        sim.set_restrictions(g["restrictions"])
     sim.set_npt_axial(g["npt_start:xi"], g["npt_start:pressure_ext"], g["npt_start:d_pressure"], g["npt_start:relax_dirs"],
                       Ekin_old=float(g["npt_start:Ekin_old"]), dyn_stress=g["npt_start:dyn_stress"],
                       isq_tau_xi=float(g["npt_start:isq_tau_xi"]))
-    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"])
+    sim.set_atoms(g["start:nummer"], g["start:sorte"], g["start:masse"], g["start:ort"], g["start:impuls"], vsorte=g["start:vsorte"])
     press = bool(int(g["press"]))
     sim.set_press_calc(press)
     for s in range(int(g["nsteps"])):

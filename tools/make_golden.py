@@ -86,6 +86,13 @@ CASES = {
                             record=[0, 29], press=True, variant="npt_axial",
                             extra=dict(endtemp=0.08, tau_eta=0.1, eta=0.0, tau_xi=0.4, pressure_start=[0.0, 0.0, 0.02],
                                        pressure_end=[0.0, 0.0, 0.02], relax_dirs=[1, 0, 1], maxsteps=100)),
+    # npt_axial on a slab whose bottom layer (virtual type 1) may not move in z: the restriction vectors multiply the momenta
+    # AFTER the kick in this integrator (src/imd_integrate.c:1859-1864)
+    "cu_npt_axial_restr": dict(kind="cu_vtypes", ncell=(5, 5, 4), ensemble="npt_axial", starttemp=0.06, warm=20, nsteps=20,
+                               record=[0, 19], press=False, variant="npt_axial", restr_only=True,
+                               extra=dict(pbc_dirs=[1, 1, 0], total_types=2, restrictionvector=[1, 1, 1, 0],
+                                          endtemp=0.06, tau_eta=0.1, eta=0.0, tau_xi=0.5, pressure_start=[0.0, 0.0, 0.0],
+                                          pressure_end=[0.0, 0.0, 0.0], relax_dirs=[1, 1, 0], maxsteps=100)),
     # `adp` reference build (angular-dependent potential).  Oracle fixtures only so far, like cu_npt_iso
     "cu_adp": dict(kind="cu", ncell=(5, 5, 5), ensemble="nve", starttemp=0.08, warm=30, nsteps=12,
                    record=[0, 11], press=True, variant="adp", adp=True),
@@ -146,9 +153,10 @@ def make_case(name, c):
         p = synth.cu_param(tmp, ncell=c["ncell"], ensemble=c["ensemble"], starttemp=c["starttemp"], tables=tabs,
                            coordname=cfgfile, extra=extra)
         # keys that take "<vtype> x y z" appear once per virtual type: append the second lines by hand
-        with open(p, "a") as f:
-            f.write("deform_shift 0 1.0 0.0 0.0\ndeform_shear 0 0.0 0.0 4.0e-4\ndeform_base 0 0.0 0.0 0.0\n"
-                    "deform_shift 1 0.012 0.0 0.0\n")
+        if not c.get("restr_only"):
+            with open(p, "a") as f:
+                f.write("deform_shift 0 1.0 0.0 0.0\ndeform_shear 0 0.0 0.0 4.0e-4\ndeform_base 0 0.0 0.0 0.0\n"
+                        "deform_shift 1 0.012 0.0 0.0\n")
         ntypes = 1
     elif c["kind"] == "nial":
         tabs = synth.make_eam_tables(tmp, "nial", **res)
@@ -180,6 +188,9 @@ def make_case(name, c):
         g["lindef_every"] = c["lindef_every"]; g["lindef_size"] = e["lindef_size"]
         g["lindef_x"] = np.array(e["lindef_x"]); g["lindef_y"] = np.array(e["lindef_y"]); g["lindef_z"] = np.array(e["lindef_z"])
         g["final:box"] = out["final_box"]
+    if c.get("restr_only"):
+        g["total_types"] = 2
+        g["restrictions"] = np.array([[1.0, 1.0, 1.0], [1.0, 1.0, 0.0]])
     if c.get("deform_every"):
         g["deform_every"] = c["deform_every"]; g["deform_size"] = c["extra"]["deform_size"]
         g["total_types"] = 2
