@@ -56,7 +56,7 @@ EXPORTS = [
     "imdb200_lin_deform", "imdb200_deform_sample", "imdb200_get_scalars", "imdb200_get_atoms",
     "imdb200_natoms_local", "imdb200_get_nblist", "imdb200_pair_int", "imdb200_get_timers",
     "imdb200_read_pot_table", "imdb200_free_pot_table", "imdb200_calc_cpu_dim", "imdb200_cart_rank",
-    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state", "imdb200_set_adp_tables", "imdb200_get_adp", "imdb200_device_count", "imdb200_set_berendsen", "imdb200_set_npt_axial", "imdb200_get_npt_axial",
+    "imdb200_cart_coords", "imdb200_halo_peers", "imdb200_send_forces", "imdb200_nghost_local", "imdb200_get_box", "imdb200_set_eeam_table", "imdb200_get_eeam", "imdb200_halo_message_order", "imdb200_set_npt_state", "imdb200_get_npt_state", "imdb200_set_adp_tables", "imdb200_get_adp", "imdb200_device_count", "imdb200_set_berendsen", "imdb200_set_npt_axial", "imdb200_get_npt_axial", "imdb200_set_momenta",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load_library():
     L.imdb200_set_press_calc.argtypes = [vp, C.c_int]
     L.imdb200_set_skin_skip.argtypes = [vp, C.c_int]
     L.imdb200_set_eta.argtypes = [vp, C.c_double]
+    L.imdb200_set_momenta.argtypes = [vp, C.c_long, vp, vp]
     L.imdb200_set_temperature.argtypes = [vp, C.c_double]
     L.imdb200_set_berendsen.argtypes = [vp, C.c_double, C.c_double]
     L.imdb200_lin_deform.argtypes = [vp, vp, vp, vp, C.c_double]
@@ -328,6 +329,11 @@ class IMDB200:
     def set_berendsen(self, tauber, tot_kin_energy=0.0):
         """Berendsen variant of NVE (`ber` builds): tau_berendsen and the kinetic energy of the previous step."""
         _chk(self.L.imdb200_set_berendsen(self.h, float(tauber), float(tot_kin_energy)))
+
+    def set_momenta(self, nummer, impuls):
+        """Overwrite the momenta of the local atoms, matched by atom number (Andersen thermostat: maxwell() on the host)."""
+        num = np.ascontiguousarray(nummer, np.int32); p = np.ascontiguousarray(impuls, np.float64)
+        _chk(self.L.imdb200_set_momenta(self.h, len(num), num.ctypes.data, p.ctypes.data))
 
     def set_eta(self, eta):
         _chk(self.L.imdb200_set_eta(self.h, float(eta)))

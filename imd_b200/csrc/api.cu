@@ -458,6 +458,44 @@ int imdb200_set_eta(imdb200_sim *s, double eta)
   CUDA_TRY(cudaMemcpy(s->d_scal + SC_ETA, &eta, sizeof(double), cudaMemcpyHostToDevice));
   return 0;
 }
+__global__ void k_set_momenta(double4 *mom, const double *buf, long n)
+{
+  const long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = mom[i];
+  p.x = buf[3 * i]; p.y = buf[3 * i + 1]; p.z = buf[3 * i + 2];       // .w keeps the mass
+  mom[i] = p;
+}
+
+int imdb200_set_momenta(imdb200_sim *s, long n, const int *nummer, const double *impuls)
+{
+  if (!s || !nummer || !impuls) return imdb_fail(IMDB200_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  if (n != s->n_own) return imdb_fail(IMDB200_ERR_ARG, "set_momenta: %ld atoms given, this rank holds %ld", n, s->n_own);
+  if (n == 0) return 0;
+  // the device order is cell-sorted: bring the caller's rows into it through the atom numbers
+  std::vector<int> dnum(n);
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  CUDA_TRY(cudaMemcpy(dnum.data(), s->nummer, n * sizeof(int), cudaMemcpyDeviceToHost));
+  int mx = 0;
+  for (long a = 0; a < n; a++) { if (nummer[a] < 0) return imdb_fail(IMDB200_ERR_ARG, "negative atom number"); if (nummer[a] > mx) mx = nummer[a]; }
+  std::vector<int> where((size_t) mx + 1, -1);
+  for (long a = 0; a < n; a++) where[nummer[a]] = (int) a;
+  std::vector<double> buf((size_t) 3 * n);
+  for (long i = 0; i < n; i++) {
+    const int a = (dnum[i] >= 0 && dnum[i] <= mx) ? where[dnum[i]] : -1;
+    if (a < 0) return imdb_fail(IMDB200_ERR_ARG, "set_momenta: atom %d of this rank is not in the caller's list", dnum[i]);
+    buf[3 * i] = impuls[3 * (size_t) a]; buf[3 * i + 1] = impuls[3 * (size_t) a + 1]; buf[3 * i + 2] = impuls[3 * (size_t) a + 2];
+  }
+  double *d_buf = nullptr;
+  CUDA_TRY(cudaMalloc(&d_buf, buf.size() * sizeof(double)));
+  cudaError_t e = cudaMemcpy(d_buf, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { k_set_momenta<<<cdiv(n, 256), 256, 0, s->stream>>>(s->mom, d_buf, n); g_kernel_launches++; e = cudaStreamSynchronize(s->stream); }
+  cudaFree(d_buf);
+  if (e != cudaSuccess) return imdb_fail(IMDB200_ERR_CUDA, "set_momenta: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int imdb200_set_berendsen(imdb200_sim *s, double tauber, double tot_kin_energy)
 {
   if (!s) return IMDB200_ERR_ARG;

@@ -188,6 +188,11 @@ int  imdb200_invalidate_nblist(imdb200_sim *sim);         /* have_valid_nbl = 0 
  * on = 0 walks every stored entry like the reference does (test hook). */
 int  imdb200_set_skin_skip(imdb200_sim *sim, int on);
 int  imdb200_set_eta(imdb200_sim *sim, double eta);
+/* Overwrite the momenta of this rank's atoms, matched by atom number; positions, forces and the neighbour list stay as
+ * they are.  replaces: host code that re-draws IMPULS between two steps -- maxwell(temperature) every `tempintv` steps in
+ * `and` builds (Andersen thermostat, src/imd_integrate.c:491-495), which the binding keeps on the host (src/imd_maxwell.c
+ * draws from drand48 in cell order).  n must be the local atom count; atoms this rank does not own are an error. */
+int  imdb200_set_momenta(imdb200_sim *sim, long n, const int *nummer, const double *impuls);
 int  imdb200_set_temperature(imdb200_sim *sim, double temperature);
 /* replaces: the BER branch of move_atoms_nve in `ber` builds (src/imd_integrate.c:44-53, 341-350) and the parameter
    tau_berendsen (global tauber).  tauber > 0 switches the Berendsen scaling of the momenta on (ensemble nve; the target is

@@ -314,6 +314,28 @@ static void b200_move_atoms(void)
   press = do_press_calc;                         /* kinetic part added by move_atoms: the tensor is complete now */
 #endif
   if (sync_due(steps) || press) b200_download(0, sync_due(steps), press);   /* writers run after move_atoms of the same step (src/imd_main_3d.c:690-694) */
+#ifdef AND
+  { /* Andersen thermostat: every tempintv-th call of move_atoms_nve ends in maxwell(temperature) (src/imd_integrate.c:491-495);
+       the host keeps maxwell, the new momenta go to the device by atom number */
+    static int and_count = 0;
+    ++and_count;
+    if (ensemble == ENS_NVE && tempintv != 0 && 0 == and_count % tempintv) {
+      long n = 0; int k, i;
+      if (!sync_due(steps)) b200_download(0, 1, 0);
+      maxwell(temperature);
+      for (k = 0; k < NCELLS; k++) {
+        cell *p = CELLPTR(k);
+        for (i = 0; i < p->n; i++, n++) {
+          b_num[n] = NUMMER(p,i);
+          b_impuls[3*n] = IMPULS(p,i,X); b_impuls[3*n+1] = IMPULS(p,i,Y); b_impuls[3*n+2] = IMPULS(p,i,Z);
+        }
+      }
+      b200_check(imdb200_set_momenta(b200, n, b_num, b_impuls));
+      for (n = 0; n < b200_n; n++) num2idx[b_num[n]] = (int) n;    /* b_num was re-filled in today's cell order */
+      b200_remap();
+    }
+  }
+#endif
 }
 
 #ifdef IMD_B200_BACKTRACE   /* debugging aid of this binding (not part of IMD): where did a SIGSEGV come from */
@@ -333,6 +355,9 @@ static void b200_init(void)
   imdb200_config cfg;
   char *e = getenv("IMD_B200_SYNC");
   if (e) sync_int = atoi(e);
+#ifdef AND
+  sync_int = 1;                                  /* the host cells have to follow every step, see calc_forces */
+#endif
 #ifdef IMD_B200_BACKTRACE
   signal(SIGSEGV, b200_segv);
 #endif
@@ -420,6 +445,12 @@ static void b200_init(void)
 /* void calc_forces(int steps)  (src/imd_forces_nbl.c:281-1999) */
 void calc_forces(int steps)
 {
+#ifdef AND
+  /* Andersen builds re-draw the momenta with IMD's own maxwell() (src/imd_integrate.c:491-495), which walks the HOST cells in
+     order and takes one drand48 triple per atom: the host cells have to evolve exactly as in the reference, so IMD's own
+     fix_cells() runs on the (downloaded) host positions wherever the reference runs it (src/imd_forces_nbl.c:304-311). */
+  if (0 == have_valid_nbl) { fix_cells(); if (b200 != NULL) b200_remap(); }
+#endif
   if (b200 == NULL) b200_init();
   else if (move_atoms != b200_move_atoms) {      /* a new simulation phase re-selected the integrator */
     imd_move_atoms = move_atoms; move_atoms = b200_move_atoms;

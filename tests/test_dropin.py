@@ -183,6 +183,26 @@ def test_axial_binding_npt_axial(built_lib, tmp_path):
     assert np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-7
 
 
+def test_andersen_binding(built_lib, tmp_path):
+    """`and` builds (Andersen thermostat, src/imd_integrate.c:491-495): every tempintv-th move_atoms ends in IMD's own
+    maxwell(temperature), which draws one drand48 triple per atom in the order of the HOST cells.  The binding keeps maxwell on
+    the host, lets IMD's own fix_cells() evolve the host cells at every list build exactly as in the reference, and sends the
+    new momenta to the device by atom number (imdb200_set_momenta).  Three re-draws in 60 steps of a hot crystal (atoms change
+    cells in between): Epot and T per step and the final checkpoint against the unmodified serial `and` build."""
+    tmp = str(tmp_path)
+    tabs = synth.make_eam_tables(tmp, "cu", nr=601, nrho=801)
+    extra = dict(eng_int=1, checkpt_int=60, tempintv=20, endtemp=0.12)
+    _pair_run(tmp, tabs, exes=("imd_b200_dropin_and", "imd_ref_serial_and"), ensemble="nve", maxsteps=60, starttemp=0.12, extra=extra)
+    eg, ec = _eng(os.path.join(tmp, "gpu.eng")), _eng(os.path.join(tmp, "cpu.eng"))
+    assert eg.shape == ec.shape and len(eg) == 61
+    assert ec[20, 2] > ec[19, 2] * 1.04 and ec[40, 2] > ec[39, 2] * 1.04          # the re-draws are visible in T
+    assert np.max(np.abs(eg[:, 1] - ec[:, 1]) / np.abs(ec[:, 1])) <= 1e-8
+    assert np.max(np.abs(eg[:, 2] - ec[:, 2]) / np.abs(ec[:, 2])) <= 1e-8
+    cg, cc = _chkpt(os.path.join(tmp, "gpu.00001.chkpt")), _chkpt(os.path.join(tmp, "cpu.00001.chkpt"))
+    assert cg.shape == cc.shape and np.array_equal(cg[:, 0], cc[:, 0])
+    assert np.max(np.abs(cg[:, 6:9] - cc[:, 6:9])) < 1e-6                         # velocities: the same random numbers per atom
+
+
 def test_restart_from_checkpoint(built_lib, tmp_path):
     """Restart `-r 1` (src/imd_param.c:3829-3872, .itr + checkpoint readers src/imd_io_3d.c:949-1086): 15 steps, checkpoint 1,
     then both binaries continue from THEIR OWN checkpoint for 15 more steps; the engine is fed by IMD's own reader."""
