@@ -351,6 +351,28 @@ def test_cuda_two_species_run_loop_equals_stepwise_calls(api, ensemble, tmp_path
     a.close(); b.close()
 
 
+def test_cuda_set_momenta_by_atom_number(api, tmp_path):
+    """imdb200_set_momenta (the Andersen hand-over of the binding): rows in any order, matched by atom number against the
+    device's cell-sorted order; positions, forces and the neighbour list stay as they are; a wrong count is refused."""
+    tabs, box, num, typ, m, x, p = _thermal_cu(tmp_path, (6, 6, 6))
+    kw = dict(pair=tabs["core_potential_file"], embed=tabs["embedding_energy_file"], rho=tabs["atomic_e-density_file"])
+    sim = api.IMDB200(1, box, ensemble="nve", timestep=0.001, **kw)
+    sim.set_atoms(num, typ, m, x, p)
+    sim.calc_forces(0)                                   # the device order is cell-sorted from here on
+    before = sim.atoms()
+    rng = np.random.default_rng(11)
+    newp = rng.normal(0, 0.02, p.shape)
+    perm = rng.permutation(len(num))
+    sim.set_momenta(num[perm], newp[perm])
+    after = sim.atoms()
+    assert np.array_equal(after["impuls"], newp)
+    assert np.array_equal(after["ort"], before["ort"]) and np.array_equal(after["kraft"], before["kraft"])
+    assert np.array_equal(after["masse"], before["masse"]) and sim.have_valid_nbl == 1
+    with pytest.raises(Exception):
+        sim.set_momenta(num[:-1], newp[:-1])
+    sim.close()
+
+
 def test_cuda_run_loop_equals_stepwise_calls(api, tmp_path):
     """imdb200_run (device-resident loop) must give bit-identical state to the three separate calls."""
     tabs, box, num, typ, m, x, p = _thermal_cu(tmp_path, (8, 8, 8), temp=0.15)
